@@ -1,0 +1,335 @@
+// Per-Gaussian backward: dL/d{conic, mean2D, colour} -> dL/d{mean3D, cov3D, SH, scale, rotation}. sm_100a.
+//
+// One fused kernel replaces the reference's two launches computeCov2DCUDA (src/cuda_rasterizer/
+// backward.cu:140-275) and preprocessCUDA<3> (:371-435) with its helpers computeColorFromSH backward
+// (:20-135) and computeCov3D backward (:279-366); fusing removes the dL_dmean3D read-modify-write
+// and one pass over means/radii (559 instead of 623 algorithmic B per visible Gaussian).
+// The 3D covariance is recomputed from scale/rotation with the forward's exact operation DAG instead
+// of being stored by the forward and re-read here.
+//
+// Reference quirks kept on purpose: gradients w.r.t. the quaternion AS PASSED (no normalisation
+// Jacobian, backward.cu:361-365), dL_dscale w.r.t. the modifier-scaled scale (:340-342), clamped
+// colour channels pass no gradient (:41-43), Gaussians with radii <= 0 are skipped (outputs stay at the
+// caller's zeros).
+#include "gsr_common.cuh"
+
+namespace gsr {
+namespace {
+
+__device__ constexpr float kC0 = 0.28209479177387814f;
+__device__ constexpr float kC1 = 0.4886025119029199f;
+__device__ constexpr float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                     -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                     0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                     -0.5900435899266435f};
+
+struct GeomBwdArgs {
+  int P, D, M;
+  float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
+  const float* means3D;
+  const int* radii;
+  const float* shs;
+  const uint8_t* clamped;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* cam_pos;
+  const float* dL_dmean2D;  // [P,3]
+  const float* dL_dconic;   // [P,4]
+  const float* dL_dcolor;   // [P,3]
+  float* dL_dmean3D;
+  float* dL_dcov3D;
+  float* dL_dsh;
+  float* dL_dscale;
+  float* dL_drot;
+  int vec_sh;  // M == 16 and shs / dL_dsh 16-byte aligned
+};
+
+__device__ __forceinline__ float dot3_ref(float a, float b, float c, float d, float e, float f) {
+  return __fmaf_rn(e, f, __fmaf_rn(a, b, __fmul_rn(c, d)));
+}
+__device__ __forceinline__ float xform_row(const float* m, int r, float x, float y, float z) {
+  return __fadd_rn(dot3_ref(x, m[r], y, m[4 + r], z, m[8 + r]), m[12 + r]);
+}
+
+// SH basis values and their partial derivatives w.r.t. the (normalised) direction components.
+__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float b[16], float bx[16], float by[16],
+                                         float bz[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) b[i] = bx[i] = by[i] = bz[i] = 0.f;
+  b[0] = kC0;
+  if (deg < 1) return;
+  b[1] = -kC1 * y, b[2] = kC1 * z, b[3] = -kC1 * x;
+  by[1] = -kC1, bz[2] = kC1, bx[3] = -kC1;
+  if (deg < 2) return;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  b[4] = kC2[0] * xy, b[5] = kC2[1] * yz, b[6] = kC2[2] * (2.f * zz - xx - yy), b[7] = kC2[3] * xz,
+  b[8] = kC2[4] * (xx - yy);
+  bx[4] = kC2[0] * y, by[4] = kC2[0] * x;
+  by[5] = kC2[1] * z, bz[5] = kC2[1] * y;
+  bx[6] = kC2[2] * -2.f * x, by[6] = kC2[2] * -2.f * y, bz[6] = kC2[2] * 4.f * z;
+  bx[7] = kC2[3] * z, bz[7] = kC2[3] * x;
+  bx[8] = kC2[4] * 2.f * x, by[8] = kC2[4] * -2.f * y;
+  if (deg < 3) return;
+  b[9] = kC3[0] * y * (3.f * xx - yy);
+  b[10] = kC3[1] * xy * z;
+  b[11] = kC3[2] * y * (4.f * zz - xx - yy);
+  b[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+  b[13] = kC3[4] * x * (4.f * zz - xx - yy);
+  b[14] = kC3[5] * z * (xx - yy);
+  b[15] = kC3[6] * x * (xx - 3.f * yy);
+  bx[9] = kC3[0] * 6.f * xy, by[9] = kC3[0] * 3.f * (xx - yy);
+  bx[10] = kC3[1] * yz, by[10] = kC3[1] * xz, bz[10] = kC3[1] * xy;
+  bx[11] = kC3[2] * -2.f * xy, by[11] = kC3[2] * (4.f * zz - xx - 3.f * yy), bz[11] = kC3[2] * 8.f * yz;
+  bx[12] = kC3[3] * -6.f * xz, by[12] = kC3[3] * -6.f * yz, bz[12] = kC3[3] * 3.f * (2.f * zz - xx - yy);
+  bx[13] = kC3[4] * (4.f * zz - 3.f * xx - yy), by[13] = kC3[4] * -2.f * xy, bz[13] = kC3[4] * 8.f * xz;
+  bx[14] = kC3[5] * 2.f * xz, by[14] = kC3[5] * -2.f * yz, bz[14] = kC3[5] * (xx - yy);
+  bx[15] = kC3[6] * 3.f * (xx - yy), by[15] = kC3[6] * -6.f * xy;
+}
+
+template <bool kVec16>
+__global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
+  __shared__ float s_view[16], s_proj[16], s_cam[3];
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    s_view[tid] = __ldg(a.viewmatrix + tid);
+  } else if (tid < 32) {
+    s_proj[tid - 16] = __ldg(a.projmatrix + tid - 16);
+  } else if (tid < 35) {
+    s_cam[tid - 32] = __ldg(a.cam_pos + tid - 32);
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * 256 + tid;
+  if (idx >= a.P) return;
+  if (!(a.radii[idx] > 0)) return;
+
+  const float* V = s_view;
+  const float* PM = s_proj;
+  const float mx = __ldg(a.means3D + 3 * (size_t)idx), my = __ldg(a.means3D + 3 * (size_t)idx + 1),
+              mz = __ldg(a.means3D + 3 * (size_t)idx + 2);
+
+  // ---- forward recomputation: 3D covariance (same DAG as preprocess.cu) --------------------------
+  float c0, c1, c2, c3, c4, c5;
+  float sx = 0.f, sy = 0.f, sz = 0.f, qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+  float A0 = 0, A1 = 0, A2 = 0, B0 = 0, B1 = 0, B2 = 0, C0 = 0, C1 = 0, C2 = 0;  // rows of M = S*R
+  float R00 = 0, R01 = 0, R02 = 0, R10 = 0, R11 = 0, R12 = 0, R20 = 0, R21 = 0, R22 = 0;
+  if (a.cov3D_precomp) {
+    const float* cp = a.cov3D_precomp + (size_t)idx * 6;
+    c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2), c3 = __ldg(cp + 3), c4 = __ldg(cp + 4), c5 = __ldg(cp + 5);
+  } else {
+    sx = __fmul_rn(__ldg(a.scales + 3 * (size_t)idx), a.scale_modifier);
+    sy = __fmul_rn(__ldg(a.scales + 3 * (size_t)idx + 1), a.scale_modifier);
+    sz = __fmul_rn(__ldg(a.scales + 3 * (size_t)idx + 2), a.scale_modifier);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+    qr = q.x, qx = q.y, qy = q.z, qz = q.w;
+    const float xz = __fmul_rn(qx, qz), rx = __fmul_rn(qr, qx), rz = __fmul_rn(qr, qz);
+    const float yy = __fmul_rn(qy, qy), zz = __fmul_rn(qz, qz);
+    const float xz_p_ry = __fmaf_rn(qr, qy, xz), yz_p_rx = __fmaf_rn(qy, qz, rx);
+    const float xz_m_ry = __fmaf_rn(-qr, qy, xz), xy_m_rz = __fmaf_rn(qx, qy, -rz);
+    const float xy_p_rz = __fmaf_rn(qx, qy, rz), yz_m_rx = __fmaf_rn(qy, qz, -rx);
+    const float xx_p_yy = __fmaf_rn(qx, qx, yy), yy_p_zz = __fadd_rn(yy, zz), xx_p_zz = __fmaf_rn(qx, qx, zz);
+    R00 = __fadd_rn(-__fadd_rn(yy_p_zz, yy_p_zz), 1.0f), R01 = __fadd_rn(xy_p_rz, xy_p_rz),
+    R02 = __fadd_rn(xz_m_ry, xz_m_ry);
+    R10 = __fadd_rn(xy_m_rz, xy_m_rz), R11 = __fadd_rn(-__fadd_rn(xx_p_zz, xx_p_zz), 1.0f),
+    R12 = __fadd_rn(yz_p_rx, yz_p_rx);
+    R20 = __fadd_rn(xz_p_ry, xz_p_ry), R21 = __fadd_rn(yz_m_rx, yz_m_rx),
+    R22 = __fadd_rn(-__fadd_rn(xx_p_yy, xx_p_yy), 1.0f);
+    A0 = __fmul_rn(sx, R00), A1 = __fmul_rn(sx, R01), A2 = __fmul_rn(sx, R02);
+    B0 = __fmul_rn(sy, R10), B1 = __fmul_rn(sy, R11), B2 = __fmul_rn(sy, R12);
+    C0 = __fmul_rn(sz, R20), C1 = __fmul_rn(sz, R21), C2 = __fmul_rn(sz, R22);
+    c0 = dot3_ref(A0, A0, B0, B0, C0, C0), c1 = dot3_ref(A0, A1, B0, B1, C0, C1);
+    c2 = dot3_ref(A0, A2, B0, B2, C0, C2), c3 = dot3_ref(A1, A1, B1, B1, C1, C1);
+    c4 = dot3_ref(A1, A2, B1, B2, C1, C2), c5 = dot3_ref(A2, A2, B2, B2, C2, C2);
+  }
+
+  // ---- conic backward (reference computeCov2DCUDA) ----------------------------------------------
+  const float tz = xform_row(V, 2, mx, my, mz);
+  const float tx0 = xform_row(V, 0, mx, my, mz), ty0 = xform_row(V, 1, mx, my, mz);
+  const float limx = __fmul_rn(a.tan_fovx, 1.3f), limy = __fmul_rn(a.tan_fovy, 1.3f);
+  const float txtz = __fdiv_rn(tx0, tz), tytz = __fdiv_rn(ty0, tz);
+  const float tx = __fmul_rn(fminf(fmaxf(txtz, -limx), limx), tz);
+  const float ty = __fmul_rn(fminf(fmaxf(tytz, -limy), limy), tz);
+  const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+  const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+  const float J00 = __fdiv_rn(a.focal_x, tz), J11 = __fdiv_rn(a.focal_y, tz);
+  const float tz_sq = __fmul_rn(tz, tz);
+  const float J02 = __fdiv_rn(-__fmul_rn(a.focal_x, tx), tz_sq), J12 = __fdiv_rn(-__fmul_rn(a.focal_y, ty), tz_sq);
+  const float T00 = __fmaf_rn(J02, V[2], __fmul_rn(V[0], J00)), T01 = __fmaf_rn(J02, V[6], __fmul_rn(V[4], J00)),
+              T02 = __fmaf_rn(J02, V[10], __fmul_rn(V[8], J00));
+  const float T10 = __fmaf_rn(J12, V[2], __fmul_rn(V[1], J11)), T11 = __fmaf_rn(J12, V[6], __fmul_rn(V[5], J11)),
+              T12 = __fmaf_rn(J12, V[10], __fmul_rn(V[9], J11));
+  const float u0 = dot3_ref(T00, c0, T01, c1, T02, c2), u1 = dot3_ref(T00, c1, T01, c3, T02, c4),
+              u2 = dot3_ref(T00, c2, T01, c4, T02, c5);
+  const float v0 = dot3_ref(T10, c0, T11, c1, T12, c2), v1 = dot3_ref(T10, c1, T11, c3, T12, c4),
+              v2 = dot3_ref(T10, c2, T11, c4, T12, c5);
+  const float ca = __fadd_rn(dot3_ref(T00, u0, T01, u1, T02, u2), 0.3f);
+  const float cb = dot3_ref(T00, v0, T01, v1, T02, v2);
+  const float cc = __fadd_rn(dot3_ref(T10, v0, T11, v1, T12, v2), 0.3f);
+
+  const float4 dcon = __ldg(reinterpret_cast<const float4*>(a.dL_dconic) + idx);  // x, y, (unused), w
+  const float denom = ca * cc - cb * cb;
+  const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+  float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (denom2inv != 0.f) {
+    dL_da = denom2inv * (-cc * cc * dcon.x + 2.f * cb * cc * dcon.y + (denom - ca * cc) * dcon.w);
+    dL_dc = denom2inv * (-ca * ca * dcon.w + 2.f * ca * cb * dcon.y + (denom - ca * cc) * dcon.x);
+    dL_db = denom2inv * 2.f * (cb * cc * dcon.x - (denom + 2.f * cb * cb) * dcon.y + ca * cb * dcon.w);
+    dcov[0] = T00 * T00 * dL_da + T00 * T10 * dL_db + T10 * T10 * dL_dc;
+    dcov[3] = T01 * T01 * dL_da + T01 * T11 * dL_db + T11 * T11 * dL_dc;
+    dcov[5] = T02 * T02 * dL_da + T02 * T12 * dL_db + T12 * T12 * dL_dc;
+    dcov[1] = 2.f * T00 * T01 * dL_da + (T00 * T11 + T01 * T10) * dL_db + 2.f * T10 * T11 * dL_dc;
+    dcov[2] = 2.f * T00 * T02 * dL_da + (T00 * T12 + T02 * T10) * dL_db + 2.f * T10 * T12 * dL_dc;
+    dcov[4] = 2.f * T02 * T01 * dL_da + (T01 * T12 + T02 * T11) * dL_db + 2.f * T11 * T12 * dL_dc;
+  }
+  {
+    float* o = a.dL_dcov3D + (size_t)idx * 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o[i] = dcov[i];
+  }
+  // dL/dT (upper 2x3), with u_k = sum_j T0j Vrk[j][k], v_k = sum_j T1j Vrk[j][k]
+  const float dT00 = 2.f * u0 * dL_da + v0 * dL_db, dT01 = 2.f * u1 * dL_da + v1 * dL_db,
+              dT02 = 2.f * u2 * dL_da + v2 * dL_db;
+  const float dT10 = 2.f * v0 * dL_dc + u0 * dL_db, dT11 = 2.f * v1 * dL_dc + u1 * dL_db,
+              dT12 = 2.f * v2 * dL_dc + u2 * dL_db;
+  const float dJ00 = V[0] * dT00 + V[4] * dT01 + V[8] * dT02;
+  const float dJ02 = V[2] * dT00 + V[6] * dT01 + V[10] * dT02;
+  const float dJ11 = V[1] * dT10 + V[5] * dT11 + V[9] * dT12;
+  const float dJ12 = V[2] * dT10 + V[6] * dT11 + V[10] * dT12;
+  const float itz = 1.f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+  const float dtx = x_grad_mul * -a.focal_x * itz2 * dJ02;
+  const float dty = y_grad_mul * -a.focal_y * itz2 * dJ12;
+  const float dtz = -a.focal_x * itz2 * dJ00 - a.focal_y * itz2 * dJ11 + (2.f * a.focal_x * tx) * itz3 * dJ02 +
+                    (2.f * a.focal_y * ty) * itz3 * dJ12;
+  float gmx = V[0] * dtx + V[1] * dty + V[2] * dtz;
+  float gmy = V[4] * dtx + V[5] * dty + V[6] * dtz;
+  float gmz = V[8] * dtx + V[9] * dty + V[10] * dtz;
+
+  // ---- projection backward: dL/dmean2D -> dL/dmean3D (reference preprocessCUDA, backward.cu:399-416) ----
+  {
+    const float hw = (PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15]) + 0.0000001f;
+    const float m_w = 1.0f / hw;
+    const float mul1 = (PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12]) * m_w * m_w;
+    const float mul2 = (PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13]) * m_w * m_w;
+    const float d2x = __ldg(a.dL_dmean2D + 3 * (size_t)idx), d2y = __ldg(a.dL_dmean2D + 3 * (size_t)idx + 1);
+    gmx += (PM[0] * m_w - PM[3] * mul1) * d2x + (PM[1] * m_w - PM[3] * mul2) * d2y;
+    gmy += (PM[4] * m_w - PM[7] * mul1) * d2x + (PM[5] * m_w - PM[7] * mul2) * d2y;
+    gmz += (PM[8] * m_w - PM[11] * mul1) * d2x + (PM[9] * m_w - PM[11] * mul2) * d2y;
+  }
+
+  // ---- SH backward (reference computeColorFromSH backward) -------------------------------------
+  if (a.shs) {
+    const float ox = mx - s_cam[0], oy = my - s_cam[1], oz = mz - s_cam[2];
+    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+    const float x = ox / len, y = oy / len, z = oz / len;
+    const uint32_t cl = a.clamped[idx];
+    float dRGB[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dRGB[c] = ((cl >> c) & 1u) ? 0.f : __ldg(a.dL_dcolor + 3 * (size_t)idx + c);
+    float b[16], bx[16], by[16], bz[16];
+    sh_basis(a.D, x, y, z, b, bx, by, bz);
+    const int ncoef = (a.D + 1) * (a.D + 1);
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;  // dL/d(dir)
+    if (kVec16) {
+      float4 in4[12], out4[12];
+      const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)idx * 12;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) in4[i] = __ldg(g4 + i);
+      const float* sh = reinterpret_cast<const float*>(in4);
+      float* o = reinterpret_cast<float*>(out4);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const bool on = k < ncoef;
+          o[k * 3 + c] = on ? b[k] * dRGB[c] : 0.f;
+          if (on && k > 0) {
+            const float w = sh[k * 3 + c] * dRGB[c];
+            ddx += bx[k] * w, ddy += by[k] * w, ddz += bz[k] * w;
+          }
+        }
+      }
+      float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)idx * 12;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) d4[i] = out4[i];
+    } else {
+      const float* sh = a.shs + (size_t)idx * a.M * 3;
+      float* o = a.dL_dsh + (size_t)idx * a.M * 3;
+      for (int k = 0; k < ncoef && k < a.M; ++k) {
+        for (int c = 0; c < 3; ++c) {
+          o[k * 3 + c] = b[k] * dRGB[c];
+          if (k > 0) {
+            const float w = __ldg(sh + k * 3 + c) * dRGB[c];
+            ddx += bx[k] * w, ddy += by[k] * w, ddz += bz[k] * w;
+          }
+        }
+      }
+    }
+    // through the normalisation dir = o/|o| (reference dnormvdv, auxiliary.h:93-103)
+    const float sum2 = ox * ox + oy * oy + oz * oz;
+    const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    gmx += ((sum2 - ox * ox) * ddx - oy * ox * ddy - oz * ox * ddz) * inv32;
+    gmy += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * inv32;
+    gmz += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * inv32;
+  }
+  a.dL_dmean3D[3 * (size_t)idx] = gmx;
+  a.dL_dmean3D[3 * (size_t)idx + 1] = gmy;
+  a.dL_dmean3D[3 * (size_t)idx + 2] = gmz;
+
+  // ---- scale / rotation backward (reference computeCov3D backward) ------------------------------
+  if (a.scales && !a.cov3D_precomp) {
+    // dL/dSigma as a symmetric matrix; dL/dM = 2 M dL/dSigma, M rows = (A,B,C)
+    const float S00 = dcov[0], S01 = 0.5f * dcov[1], S02 = 0.5f * dcov[2], S11 = dcov[3], S12 = 0.5f * dcov[4],
+                S22 = dcov[5];
+    const float dA0 = 2.f * (A0 * S00 + A1 * S01 + A2 * S02), dA1 = 2.f * (A0 * S01 + A1 * S11 + A2 * S12),
+                dA2 = 2.f * (A0 * S02 + A1 * S12 + A2 * S22);
+    const float dB0 = 2.f * (B0 * S00 + B1 * S01 + B2 * S02), dB1 = 2.f * (B0 * S01 + B1 * S11 + B2 * S12),
+                dB2 = 2.f * (B0 * S02 + B1 * S12 + B2 * S22);
+    const float dC0 = 2.f * (C0 * S00 + C1 * S01 + C2 * S02), dC1 = 2.f * (C0 * S01 + C1 * S11 + C2 * S12),
+                dC2 = 2.f * (C0 * S02 + C1 * S12 + C2 * S22);
+    a.dL_dscale[3 * (size_t)idx] = R00 * dA0 + R01 * dA1 + R02 * dA2;
+    a.dL_dscale[3 * (size_t)idx + 1] = R10 * dB0 + R11 * dB1 + R12 * dB2;
+    a.dL_dscale[3 * (size_t)idx + 2] = R20 * dC0 + R21 * dC1 + R22 * dC2;
+    // E[i][j] = s_i * dM[i][j]
+    const float E00 = sx * dA0, E01 = sx * dA1, E02 = sx * dA2;
+    const float E10 = sy * dB0, E11 = sy * dB1, E12 = sy * dB2;
+    const float E20 = sz * dC0, E21 = sz * dC1, E22 = sz * dC2;
+    float4 dq;
+    dq.x = 2.f * qz * (E01 - E10) + 2.f * qy * (E20 - E02) + 2.f * qx * (E12 - E21);
+    dq.y = 2.f * qy * (E10 + E01) + 2.f * qz * (E20 + E02) + 2.f * qr * (E12 - E21) - 4.f * qx * (E22 + E11);
+    dq.z = 2.f * qx * (E10 + E01) + 2.f * qr * (E20 - E02) + 2.f * qz * (E12 + E21) - 4.f * qy * (E22 + E00);
+    dq.w = 2.f * qr * (E01 - E10) + 2.f * qx * (E20 + E02) + 2.f * qy * (E12 + E21) - 4.f * qz * (E11 + E00);
+    reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int* radii, float focal_x, float focal_y,
+                            cudaStream_t s) {
+  GeomBwdArgs a;
+  a.P = f.P, a.D = f.D, a.M = f.M;
+  a.scale_modifier = f.scale_modifier, a.tan_fovx = f.tan_fovx, a.tan_fovy = f.tan_fovy;
+  a.focal_x = focal_x, a.focal_y = focal_y;
+  a.means3D = f.means3D, a.radii = radii, a.shs = f.colors_precomp ? nullptr : f.shs, a.clamped = g.clamped;
+  a.scales = f.scales, a.rotations = f.rotations, a.cov3D_precomp = f.cov3D_precomp;
+  a.viewmatrix = f.viewmatrix, a.projmatrix = f.projmatrix, a.cam_pos = f.cam_pos;
+  a.dL_dmean2D = f.dL_dmean2D, a.dL_dconic = f.dL_dconic, a.dL_dcolor = f.dL_dcolor;
+  a.dL_dmean3D = f.dL_dmean3D, a.dL_dcov3D = f.dL_dcov3D, a.dL_dsh = f.dL_dsh, a.dL_dscale = f.dL_dscale,
+  a.dL_drot = f.dL_drot;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al16(f.dL_dconic) || (!f.cov3D_precomp && (!al16(f.rotations) || !al16(f.dL_drot))))
+    return cudaErrorMisalignedAddress;
+  a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && al16(f.dL_dsh);
+  const int blocks = (f.P + 255) / 256;
+  if (a.vec_sh)
+    geom_bwd_kernel<true><<<blocks, 256, 0, s>>>(a);
+  else
+    geom_bwd_kernel<false><<<blocks, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gsr

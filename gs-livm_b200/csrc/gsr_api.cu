@@ -1,0 +1,275 @@
+// C ABI of libgsr_b200 (declared in include/gsr.h): scratch-state carving, stage orchestration and
+// error handling for one forward / backward. Mirrors the control flow of the reference's
+// CudaRasterizer::Rasterizer::forward/backward (src/cuda_rasterizer/rasterizer_impl.cu:181-457)
+// with our kernels; nothing here touches the CPU oracle and there is no fallback path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+static thread_local char t_err[512] = "";
+static thread_local void* t_shim_stream = nullptr;
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define GSR_CUDA(expr, what)                                                                      \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) return fail(GSR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__));   \
+  } while (0)
+
+// debug == the reference's CHECK_CUDA(A, debug): synchronise and surface asynchronous errors per stage
+#define GSR_STAGE(expr, what, debug, stream)                                                      \
+  do {                                                                                            \
+    GSR_CUDA((expr), what);                                                                       \
+    if (debug) GSR_CUDA(cudaStreamSynchronize(stream), what);                                     \
+  } while (0)
+
+GeomState carve_geom(char* chunk, int P) {
+  GeomState g;
+  carve(chunk, g.rec, (size_t)P);
+  carve(chunk, g.tiles_touched, (size_t)P);
+  carve(chunk, g.point_offsets, (size_t)P);
+  carve(chunk, g.internal_radii, (size_t)P);
+  carve(chunk, g.clamped, (size_t)P);
+  g.scan_temp_bytes = scan_temp_bytes(P);
+  carve(chunk, g.scan_temp, g.scan_temp_bytes);
+  return g;
+}
+
+ImageState carve_image(char* chunk, int width, int height) {
+  ImageState s;
+  const size_t N = (size_t)width * height;
+  const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+  carve(chunk, s.final_T, N);
+  carve(chunk, s.n_contrib, N);
+  carve(chunk, s.ranges, tiles);
+  carve(chunk, s.tile_last, tiles);
+  return s;
+}
+
+BinningState carve_binning(char* chunk, int R) {
+  BinningState b;
+  const size_t n = (size_t)R;
+  carve(chunk, b.inst, n);
+  carve(chunk, b.keys_unsorted, n);
+  carve(chunk, b.keys, n);
+  carve(chunk, b.vals_unsorted, n);
+  carve(chunk, b.vals, n + 4);  // +16 B: blend_bwd bulk-copies ids from an aligned-down start
+  b.sort_temp_bytes = sort_temp_bytes(R);
+  carve(chunk, b.sort_temp, b.sort_temp_bytes);
+  return b;
+}
+
+template <typename F>
+static size_t required_bytes(F carve_fn) {
+  // carve from address 0 and read back the end, then add one alignment unit because the caller's
+  // buffer may start anywhere (same trick as the reference's required<T>, rasterizer_impl.h:61-66)
+  return carve_fn() + kAlign;
+}
+
+// One pinned int per host thread for the R read-back (reference: blocking cudaMemcpy D2H,
+// rasterizer_impl.cu:277).
+static int* pinned_counter() {
+  static thread_local int* p = nullptr;
+  if (!p) {
+    if (cudaMallocHost(reinterpret_cast<void**>(&p), sizeof(int)) != cudaSuccess) p = nullptr;
+  }
+  return p;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return t_err; }
+
+void gsr_shim_set_stream(void* stream) { t_shim_stream = stream; }
+void* gsr_shim_get_stream(void) { return t_shim_stream; }
+
+size_t gsr_required_geom(int P) {
+  if (P < 0) return 0;
+  return required_bytes([&] {
+    GeomState g = carve_geom(nullptr, P);
+    return (size_t)(reinterpret_cast<uintptr_t>(g.scan_temp) + g.scan_temp_bytes);
+  });
+}
+
+size_t gsr_required_image(int width, int height) {
+  if (width < 0 || height < 0) return 0;
+  return required_bytes([&] {
+    ImageState s = carve_image(nullptr, width, height);
+    const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    return (size_t)(reinterpret_cast<uintptr_t>(s.tile_last + tiles));
+  });
+}
+
+size_t gsr_required_binning(int R) {
+  if (R < 0) return 0;
+  return required_bytes([&] {
+    BinningState b = carve_binning(nullptr, R);
+    return (size_t)(reinterpret_cast<uintptr_t>(b.sort_temp) + b.sort_temp_bytes);
+  });
+}
+
+int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ctx, gsr_alloc_fn binning_alloc,
+                void* binning_ctx, gsr_alloc_fn image_alloc, void* image_ctx, void* stream_v, int* num_rendered) {
+  if (!args || !geom_alloc || !binning_alloc || !image_alloc || !num_rendered)
+    return fail(GSR_ERR_INVALID, "gsr_forward: null argument");
+  const gsr_fwd_args& a = *args;
+  *num_rendered = 0;
+  if (a.P <= 0 || a.width <= 0 || a.height <= 0) return fail(GSR_ERR_INVALID, "gsr_forward: P, width, height must be > 0");
+  if (!a.means3D || !a.opacities || !a.viewmatrix || !a.projmatrix || !a.cam_pos || !a.background || !a.out_color ||
+      !a.out_depth || !a.out_acc)
+    return fail(GSR_ERR_INVALID, "gsr_forward: null input/output pointer");
+  if (!a.colors_precomp && (!a.shs || a.M <= 0)) return fail(GSR_ERR_INVALID, "gsr_forward: need shs or colors_precomp");
+  if (!a.colors_precomp && (a.D < 0 || a.D > 3 || (a.D + 1) * (a.D + 1) > a.M))
+    return fail(GSR_ERR_INVALID, "gsr_forward: SH degree %d needs %d coefficients, M = %d", a.D, (a.D + 1) * (a.D + 1), a.M);
+  if (!a.cov3D_precomp && (!a.scales || !a.rotations))
+    return fail(GSR_ERR_INVALID, "gsr_forward: need scales+rotations or cov3D_precomp");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int debug = a.debug;
+
+  const float focal_y = a.height / (2.0f * a.tan_fovy);  // rasterizer_impl.cu:210-211
+  const float focal_x = a.width / (2.0f * a.tan_fovx);
+  const int grid_x = (a.width + kTile - 1) / kTile, grid_y = (a.height + kTile - 1) / kTile;
+  const int tiles = grid_x * grid_y;
+
+  char* geom_chunk = geom_alloc(geom_ctx, gsr_required_geom(a.P));
+  if (!geom_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: geometry allocator returned NULL");
+  GeomState geom = carve_geom(geom_chunk, a.P);
+  int* radii = a.radii ? a.radii : geom.internal_radii;
+
+  char* img_chunk = image_alloc(image_ctx, gsr_required_image(a.width, a.height));
+  if (!img_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: image allocator returned NULL");
+  ImageState img = carve_image(img_chunk, a.width, a.height);
+
+  GSR_STAGE(launch_preprocess_fwd(a, geom, radii, focal_x, focal_y, stream), "preprocess_fwd", debug, stream);
+  GSR_STAGE(run_scan(geom, a.P, stream), "scan", debug, stream);
+
+  int* h_count = pinned_counter();
+  if (!h_count) return fail(GSR_ERR_CUDA, "gsr_forward: cudaMallocHost failed");
+  GSR_CUDA(cudaMemcpyAsync(h_count, geom.point_offsets + (a.P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream),
+           "read num_rendered");
+  GSR_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)tiles * sizeof(uint2), stream), "clear ranges");
+  GSR_CUDA(cudaStreamSynchronize(stream), "read num_rendered");
+  const int R = *h_count;
+  if (R < 0) return fail(GSR_ERR_INVALID, "gsr_forward: instance count overflows int32");
+
+  char* bin_chunk = binning_alloc(binning_ctx, gsr_required_binning(R));
+  if (!bin_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: binning allocator returned NULL");
+  BinningState bin = carve_binning(bin_chunk, R);
+
+  if (R > 0) {
+    GSR_STAGE(launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream), "duplicate_with_keys", debug,
+              stream);
+    const int bit = (int)higher_msb((uint32_t)tiles);
+    GSR_STAGE(run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
+    GSR_STAGE(launch_finalize_binning(R, bin, geom, a.colors_precomp, img.ranges, stream), "finalize_binning", debug,
+              stream);
+  }
+  GSR_STAGE(launch_blend_fwd(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream),
+            "blend_fwd", debug, stream);
+  *num_rendered = R;
+  return GSR_OK;
+}
+
+int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
+  if (!args) return fail(GSR_ERR_INVALID, "gsr_backward: null argument");
+  const gsr_bwd_args& a = *args;
+  if (a.P <= 0 || a.width <= 0 || a.height <= 0 || a.R < 0) return fail(GSR_ERR_INVALID, "gsr_backward: bad sizes");
+  if (!a.geom_buffer || !a.binning_buffer || !a.image_buffer) return fail(GSR_ERR_INVALID, "gsr_backward: null state buffer");
+  if (!a.means3D || !a.viewmatrix || !a.projmatrix || !a.cam_pos || !a.background || !a.dL_dpix || !a.dL_dacc ||
+      !a.dL_dmean2D || !a.dL_dconic || !a.dL_dopacity || !a.dL_dcolor || !a.dL_dmean3D || !a.dL_dcov3D)
+    return fail(GSR_ERR_INVALID, "gsr_backward: null input/output pointer");
+  if (!a.colors_precomp && (!a.shs || !a.dL_dsh)) return fail(GSR_ERR_INVALID, "gsr_backward: need shs + dL_dsh");
+  if (!a.cov3D_precomp && (!a.scales || !a.rotations || !a.dL_dscale || !a.dL_drot))
+    return fail(GSR_ERR_INVALID, "gsr_backward: need scales/rotations and their gradient outputs");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int debug = a.debug;
+
+  GeomState geom = carve_geom(a.geom_buffer, a.P);
+  BinningState bin = carve_binning(a.binning_buffer, a.R);
+  ImageState img = carve_image(a.image_buffer, a.width, a.height);
+  const int* radii = a.radii ? a.radii : geom.internal_radii;
+  const float focal_y = a.height / (2.0f * a.tan_fovy);
+  const float focal_x = a.width / (2.0f * a.tan_fovx);
+
+  if (a.R > 0) {
+    GSR_STAGE(launch_blend_bwd(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
+                               a.dL_dconic, a.dL_dopacity, a.dL_dcolor, stream),
+              "blend_bwd", debug, stream);
+  }
+  GSR_STAGE(launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);
+  return GSR_OK;
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* /*projmatrix*/,
+                     unsigned char* present, void* stream) {
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSR_ERR_INVALID, "gsr_mark_visible: bad argument");
+  if (P == 0) return GSR_OK;
+  GSR_CUDA(launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(stream)), "mark_visible");
+  return GSR_OK;
+}
+
+static gsr_array_view view_of(void* p, size_t stride, size_t count) {
+  gsr_array_view v;
+  v.ptr = p, v.stride = stride, v.count = count;
+  return v;
+}
+
+int gsr_view_geom(char* geom_buffer, int P, gsr_geom_view* out) {
+  if (!geom_buffer || P < 0 || !out) return fail(GSR_ERR_INVALID, "gsr_view_geom: bad argument");
+  GeomState g = carve_geom(geom_buffer, P);
+  char* r = reinterpret_cast<char*>(g.rec);
+  const size_t n = (size_t)P, st = sizeof(SplatRecord);
+  out->means2D = view_of(r + 0, st, n);
+  out->extent = view_of(r + 8, st, n);
+  out->conic_opacity = view_of(r + 16, st, n);
+  out->rgb = view_of(r + 32, st, n);
+  out->depths = view_of(r + 44, st, n);
+  out->clamped = view_of(g.clamped, 1, n);
+  out->internal_radii = view_of(g.internal_radii, 4, n);
+  out->tiles_touched = view_of(g.tiles_touched, 4, n);
+  out->point_offsets = view_of(g.point_offsets, 4, n);
+  return GSR_OK;
+}
+
+int gsr_view_binning(char* binning_buffer, int R, gsr_binning_view* out) {
+  if (!binning_buffer || R < 0 || !out) return fail(GSR_ERR_INVALID, "gsr_view_binning: bad argument");
+  BinningState b = carve_binning(binning_buffer, R);
+  const size_t n = (size_t)R;
+  out->point_list_keys_unsorted = view_of(b.keys_unsorted, 8, n);
+  out->point_list_unsorted = view_of(b.vals_unsorted, 4, n);
+  out->point_list_keys = view_of(b.keys, 8, n);
+  out->point_list = view_of(b.vals, 4, n);
+  out->instance_records = view_of(b.inst, sizeof(SplatRecord), n);
+  return GSR_OK;
+}
+
+int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* out) {
+  if (!image_buffer || width <= 0 || height <= 0 || !out) return fail(GSR_ERR_INVALID, "gsr_view_image: bad argument");
+  ImageState s = carve_image(image_buffer, width, height);
+  const size_t N = (size_t)width * height;
+  const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+  out->accum_alpha = view_of(s.final_T, 4, N);
+  out->n_contrib = view_of(s.n_contrib, 4, N);
+  out->ranges = view_of(s.ranges, 8, tiles);
+  out->tile_last = view_of(s.tile_last, 4, tiles);
+  return GSR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// Shared declarations of libgsr_b200: scratch-state layout, launch prototypes, small PTX helpers.
+//
+// The three byte buffers (geometry / image / binning) play the role of the reference's
+// GeometryState / ImageState / BinningState (include/gs/cuda_rasterizer/rasterizer_impl.h:20-67,
+// src/cuda_rasterizer/rasterizer_impl.cu:137-177), but the layout inside them is B200-first:
+// per-Gaussian data needed by the blend is one 48-byte record (three float4) so that the blend
+// kernels can stage contiguous batches of sorted instances with one TMA bulk copy per batch.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gsr.h"
+
+namespace gsr {
+
+constexpr int kTile = 16;           // BLOCK_X == BLOCK_Y (config.h:16-17)
+constexpr int kTilePixels = 256;    // threads per blend CTA
+constexpr int kBatch = 256;         // sorted instances staged per TMA bulk copy
+constexpr int kAlign = 128;         // sub-array alignment, same as the reference's obtain(..., 128)
+
+// One Gaussian as the blend sees it (48 B). Written by preprocess per Gaussian, then gathered into
+// sorted-instance order by finalize_binning.
+//   q0 = { mean2D.x, mean2D.y, extent.x, extent.y }   extent = conservative half-size of {alpha >= 1/255}
+//   q1 = { conic.x, conic.y, conic.z, opacity }       (reference conic_opacity, forward.cu:284)
+//   q2 = { r, g, b, depth }                           (reference rgb + depths, forward.cu:274-280)
+struct alignas(16) SplatRecord {
+  float4 q0, q1, q2;
+};
+static_assert(sizeof(SplatRecord) == 48, "record must be 3 x 16 B for bulk copies");
+
+struct GeomState {
+  SplatRecord* rec;         // [P]
+  uint32_t* tiles_touched;  // [P]
+  uint32_t* point_offsets;  // [P] inclusive prefix sum of tiles_touched
+  int* internal_radii;      // [P] only used when the caller passes radii == nullptr
+  uint8_t* clamped;         // [P] bit c set = colour channel c was clamped at 0 (forward.cu:72-74)
+  char* scan_temp;          // CUB DeviceScan temp
+  size_t scan_temp_bytes;
+};
+
+struct ImageState {
+  float* final_T;       // [W*H]   reference accum_alpha
+  uint32_t* n_contrib;  // [W*H]
+  uint2* ranges;        // [tiles]
+  uint32_t* tile_last;  // [tiles] max n_contrib in the tile: where the backward starts
+};
+
+struct BinningState {
+  uint64_t* keys_unsorted;  // [R]
+  uint32_t* vals_unsorted;  // [R]
+  uint64_t* keys;           // [R] sorted
+  uint32_t* vals;           // [R] sorted == reference point_list
+  SplatRecord* inst;        // [R] records in sorted order
+  char* sort_temp;
+  size_t sort_temp_bytes;
+};
+
+template <typename T>
+inline void carve(char*& chunk, T*& ptr, size_t count) {
+  uintptr_t p = (reinterpret_cast<uintptr_t>(chunk) + kAlign - 1) & ~uintptr_t(kAlign - 1);
+  ptr = reinterpret_cast<T*>(p);
+  chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(int R);
+GeomState carve_geom(char* chunk, int P);
+ImageState carve_image(char* chunk, int width, int height);
+BinningState carve_binning(char* chunk, int R);
+
+struct Camera {
+  float view[16];
+  float proj[16];
+  float campos[3];
+};
+
+// ---- kernel launchers (each returns the cudaError_t of the launch) ----------------------------
+cudaError_t launch_preprocess_fwd(const gsr_fwd_args& a, const GeomState& g, int* radii, float focal_x, float focal_y,
+                                  cudaStream_t s);
+cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
+                                cudaStream_t s);
+cudaError_t run_scan(const GeomState& g, int P, cudaStream_t s);
+cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, const BinningState& b, int grid_x,
+                                       int grid_y, cudaStream_t s);
+cudaError_t run_sort(const BinningState& b, int R, int end_bit, cudaStream_t s);
+cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomState& g, const float* colors_precomp,
+                                    uint2* ranges, cudaStream_t s);
+cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,
+                             const float* background, float* out_color, float* out_depth, float* out_acc,
+                             cudaStream_t s);
+cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const BinningState& b,
+                             const float* background, const float* dL_dpix, const float* dL_dacc, float* dL_dmean2D,
+                             float* dL_dconic, float* dL_dopacity, float* dL_dcolor, cudaStream_t s);
+cudaError_t launch_geom_bwd(const gsr_bwd_args& a, const GeomState& g, const int* radii, float focal_x, float focal_y,
+                            cudaStream_t s);
+
+uint32_t higher_msb(uint32_t n);  // reference getHigherMsb, rasterizer_impl.cu:35-48
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst, src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace gsr

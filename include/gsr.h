@@ -1,0 +1,188 @@
+/*
+ * gsr.h — C ABI of the B200-native differentiable Gaussian-splatting rasterizer (libgsr_b200.so).
+ *
+ * This is the drop-in boundary for GS-LIVM's `src/cuda_rasterizer` hot path. Every entry point takes
+ * plain pointers and sizes only (no torch / C++ types) and replaces one reference interface:
+ *
+ *   gsr_forward       <- CudaRasterizer::Rasterizer::forward    (include/gs/cuda_rasterizer/rasterizer.h:23-51,
+ *                                                                src/cuda_rasterizer/rasterizer_impl.cu:181-342)
+ *   gsr_backward      <- CudaRasterizer::Rasterizer::backward   (rasterizer.h:53-88, rasterizer_impl.cu:346-457)
+ *   gsr_mark_visible  <- CudaRasterizer::Rasterizer::markVisible(rasterizer.h:21, rasterizer_impl.cu:128-135)
+ *   gsr_required_*    <- CudaRasterizer::required<GeometryState|ImageState|BinningState>
+ *                                                               (include/gs/cuda_rasterizer/rasterizer_impl.h:61-66)
+ *   gsr_view_*        <- GeometryState/ImageState/BinningState::fromChunk (rasterizer_impl.cu:137-177);
+ *                        debug/parity accessors only — the layout inside the three byte buffers is OURS.
+ *
+ * The C++ class `CudaRasterizer::Rasterizer` with the reference's exact signatures is provided on top of
+ * this ABI by include/cuda_rasterizer/rasterizer.h + csrc/rasterizer_shim.cpp (same library), so the
+ * reference's src/gs/rasterize_points.cu and src/gs/rasterizer.cu compile and link unchanged.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers on the current CUDA device, FP32 / INT32, contiguous, laid out
+ *    exactly as the reference expects them (means3D[P,3], shs[P,M,3], out_color[3,H,W] planar, ...).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, what the reference uses).
+ *  - Functions return GSR_OK (0) or a negative gsr_status; they never throw. gsr_last_error() returns a
+ *    thread-local human-readable message for the last failure on the calling thread.
+ *  - The three allocator callbacks are invoked once each, in the order geometry -> image -> binning
+ *    (binning only after the number of rendered instances R is known), like the reference does
+ *    (rasterizer_impl.cu:213-215,225-227,279-281). The memory must stay valid until the matching backward.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point returns GSR_ERR_CUDA.
+ */
+#ifndef GSR_B200_H_INCLUDED
+#define GSR_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+#define GSR_ABI_VERSION 1
+#define GSR_NUM_CHANNELS 3 /* NUM_CHANNELS, include/gs/cuda_rasterizer/config.h:15 */
+#define GSR_BLOCK_X 16     /* BLOCK_X, config.h:16 */
+#define GSR_BLOCK_Y 16     /* BLOCK_Y, config.h:17 */
+
+typedef enum gsr_status {
+  GSR_OK = 0,
+  GSR_ERR_INVALID = -1, /* bad argument combination (cf. std::runtime_error, rasterizer_impl.cu:229-231) */
+  GSR_ERR_CUDA = -2,    /* a CUDA runtime call or kernel failed */
+  GSR_ERR_ALLOC = -3    /* an allocator callback returned NULL */
+} gsr_status;
+
+/* Scratch allocator: must return `bytes` bytes of device memory (any alignment; we align to 128 inside). */
+typedef char* (*gsr_alloc_fn)(void* ctx, size_t bytes);
+
+/* Arguments of one forward render; field meanings == reference Rasterizer::forward parameters. */
+typedef struct gsr_fwd_args {
+  int P;                       /* number of Gaussians */
+  int D;                       /* active SH degree (0..3) */
+  int M;                       /* SH coefficients per Gaussian per channel stored in `shs` (0 if unused) */
+  int width, height;           /* image size in pixels */
+  const float* background;     /* [3] */
+  const float* means3D;        /* [P,3] */
+  const float* shs;            /* [P,M,3] or NULL when colors_precomp is given */
+  const float* colors_precomp; /* [P,3] or NULL -> colours from SH */
+  const float* opacities;      /* [P] activated */
+  const float* scales;         /* [P,3] activated, or NULL when cov3D_precomp is given */
+  float scale_modifier;
+  const float* rotations;      /* [P,4] (r,x,y,z); NOT normalised inside (reference forward.cu:146) */
+  const float* cov3D_precomp;  /* [P,6] or NULL */
+  const float* viewmatrix;     /* [16] column-major as the reference indexes it (auxiliary.h:48-55) */
+  const float* projmatrix;     /* [16] */
+  const float* cam_pos;        /* [3] */
+  float tan_fovx, tan_fovy;
+  int prefiltered;             /* accepted for signature parity; unused (reference preprocess ignores it) */
+  float* out_color;            /* [3,H,W] */
+  float* out_depth;            /* [1,H,W]  un-normalised sum z*alpha*T (forward.cu:386) */
+  float* out_acc;              /* [1,H,W]  silhouette sum alpha*T      (forward.cu:387) */
+  int* radii;                  /* [P] or NULL -> internal */
+  int debug;                   /* !=0: synchronise + check after every stage (CHECK_CUDA, auxiliary.h:146-154) */
+} gsr_fwd_args;
+
+/* Arguments of one backward; == reference Rasterizer::backward parameters. Gradient outputs must be
+ * pre-zeroed by the caller (rasterize_points.cu:173-181); there is no dL_ddepth input (rasterizer.cu:77-80). */
+typedef struct gsr_bwd_args {
+  int P, D, M, R;
+  int width, height;
+  const float* background;
+  const float* means3D;
+  const float* shs;
+  const float* colors_precomp;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* cam_pos;
+  float tan_fovx, tan_fovy;
+  const int* radii;      /* [P] as written by the forward, or NULL -> internal */
+  char* geom_buffer;     /* the three buffers the forward's allocators returned */
+  char* binning_buffer;
+  char* image_buffer;
+  const float* dL_dpix;  /* [3,H,W] */
+  const float* dL_dacc;  /* [1,H,W] */
+  float* dL_dmean2D;     /* [P,3] (z unused) */
+  float* dL_dconic;      /* [P,2,2] (index 2 unused) */
+  float* dL_dopacity;    /* [P,1] */
+  float* dL_dcolor;      /* [P,3] */
+  float* dL_dmean3D;     /* [P,3] */
+  float* dL_dcov3D;      /* [P,6] */
+  float* dL_dsh;         /* [P,M,3] */
+  float* dL_dscale;      /* [P,3] */
+  float* dL_drot;        /* [P,4] */
+  int debug;
+} gsr_bwd_args;
+
+/* Debug / parity view of the opaque buffers. Strides are in BYTES; count = number of elements. */
+typedef struct gsr_array_view {
+  void* ptr;
+  size_t stride;
+  size_t count;
+} gsr_array_view;
+
+typedef struct gsr_geom_view {
+  gsr_array_view means2D;       /* float2 per Gaussian */
+  gsr_array_view extent;        /* float2 per Gaussian: conservative |dx|,|dy| bound of alpha>=1/255 (ours) */
+  gsr_array_view conic_opacity; /* float4 per Gaussian */
+  gsr_array_view rgb;           /* float3 per Gaussian */
+  gsr_array_view depths;        /* float per Gaussian */
+  gsr_array_view clamped;       /* uint8 bitmask per Gaussian: bit c = channel c clamped */
+  gsr_array_view internal_radii;/* int32 per Gaussian */
+  gsr_array_view tiles_touched; /* uint32 per Gaussian */
+  gsr_array_view point_offsets; /* uint32 per Gaussian (inclusive scan) */
+} gsr_geom_view;
+
+typedef struct gsr_binning_view {
+  gsr_array_view point_list_keys_unsorted; /* uint64 */
+  gsr_array_view point_list_unsorted;      /* uint32 */
+  gsr_array_view point_list_keys;          /* uint64, sorted */
+  gsr_array_view point_list;               /* uint32, sorted */
+  gsr_array_view instance_records;         /* 48-byte packed per-instance records in sorted order (ours) */
+} gsr_binning_view;
+
+typedef struct gsr_image_view {
+  gsr_array_view accum_alpha; /* float per pixel: final transmittance T */
+  gsr_array_view n_contrib;   /* uint32 per pixel */
+  gsr_array_view ranges;      /* uint2 per tile */
+  gsr_array_view tile_last;   /* uint32 per tile: max n_contrib over the tile's pixels (ours) */
+} gsr_image_view;
+
+GSR_API int gsr_abi_version(void);
+GSR_API const char* gsr_last_error(void);
+
+GSR_API size_t gsr_required_geom(int P);
+GSR_API size_t gsr_required_image(int width, int height);
+GSR_API size_t gsr_required_binning(int R);
+
+GSR_API int gsr_forward(const gsr_fwd_args* args,
+                gsr_alloc_fn geom_alloc, void* geom_ctx,
+                gsr_alloc_fn binning_alloc, void* binning_ctx,
+                gsr_alloc_fn image_alloc, void* image_ctx,
+                void* stream, int* num_rendered);
+
+GSR_API int gsr_backward(const gsr_bwd_args* args, void* stream);
+
+GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream);
+
+GSR_API int gsr_view_geom(char* geom_buffer, int P, gsr_geom_view* out);
+GSR_API int gsr_view_binning(char* binning_buffer, int R, gsr_binning_view* out);
+GSR_API int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* out);
+
+/* Stream used by the C++ shim (CudaRasterizer::Rasterizer has no stream parameter). Default NULL =
+ * legacy default stream, identical to the reference's launches. Thread-local. */
+GSR_API void gsr_shim_set_stream(void* stream);
+GSR_API void* gsr_shim_get_stream(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H_INCLUDED */
