@@ -1,0 +1,12 @@
+"""gs-livm_b200: B200-native (sm_100a) differentiable Gaussian-splatting rasterizer, drop-in for GS-LIVM's
+`src/cuda_rasterizer` hot path. Imported as `gs_livm_b200` (see ../gs_livm_b200.py).
+
+Layout
+  csrc/          hand-written CUDA kernels, the C ABI (include/gsr.h) and the C++ operator shim
+  _lib.py        ctypes binding of libgsr_b200.so (fails loudly when the library is missing)
+  rasterizer.py  Python mirror of the reference's LibTorch operator surface
+                 (GaussianRasterizationSettings / GaussianRasterizer / _RasterizeGaussians)
+  scene.py       synthetic NTU-VIRAL-shaped scenes and GS-LIVM camera conventions
+  window.py      view-sharded keyframe window with NCCL gradient all-reduce (multi-GPU)
+"""
+__version__ = "0.1.0"

@@ -109,7 +109,38 @@ __global__ void __launch_bounds__(256) finalize_binning_kernel(int R, const uint
   dst[0] = a, dst[1] = b, dst[2] = c;
 }
 
+// Launch order of the blend CTAs: tiles bucketed by floor(log2(list length)) and emitted longest
+// bucket first (coarse LPT scheduling; the order inside a bucket is irrelevant). One CTA.
+__global__ void __launch_bounds__(1024) order_tiles_kernel(int tiles, const uint2* __restrict__ ranges,
+                                                          uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_count[33], s_base[33];
+  if (threadIdx.x < 33) s_count[threadIdx.x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    atomicAdd(&s_count[32 - __clz(r.y - r.x)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+    for (int b = 32; b >= 0; --b) {
+      s_base[b] = acc;
+      acc += s_count[b];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const uint2 r = ranges[t];
+    order[atomicAdd(&s_base[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)t;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s) {
+  order_tiles_kernel<<<1, 1024, 0, s>>>(tiles, ranges, tile_order);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* radii, const BinningState& b, int grid_x,
                                        int grid_y, cudaStream_t s) {

@@ -3,17 +3,21 @@
 // Replaces FORWARD::render / renderCUDA<3> (reference src/cuda_rasterizer/forward.cu:291-441).
 //
 // Design ("blend_fwd"):
-//  * one CTA (256 threads, 8 warps) per tile; each warp owns an 8x4-pixel sub-tile;
-//  * batches of 256 sorted instances (48-byte records, contiguous thanks to finalize_binning) are
-//    staged into shared memory by ONE elected thread with a TMA bulk copy (cp.async.bulk ->
-//    SASS UBLKCP) completing on an mbarrier; two stages, so the copy of batch b+1/b+2 overlaps the
-//    math of batch b and no thread spends registers or LSU slots on staging;
+//  * one CTA per tile: 8 consumer warps, each owning an 8x4-pixel sub-tile, plus 1 producer warp;
+//  * warp-specialised TMA pipeline: the producer's elected lane stages batches of 256 sorted instances
+//    (48-byte records, contiguous thanks to finalize_binning) into a 4-deep shared-memory ring with
+//    cp.async.bulk (SASS UBLKCP) completing on per-stage "full" mbarriers; consumer warps release a
+//    stage by arriving on its "empty" mbarrier. There is NO CTA-wide barrier in the loop: a warp whose
+//    sub-tile is cheap runs ahead of one whose sub-tile is dense (ncu on the first version of this
+//    kernel showed 60 % of all stall samples on the per-batch __syncthreads);
 //  * per batch every warp first tests 32 records per instruction against its sub-tile with the
 //    per-Gaussian conservative extent (preprocess.cu) and __ballot_sync, then walks only the
-//    survivors; a record that cannot reach alpha >= 1/255 anywhere in the sub-tile costs 1/32 of
-//    a lane-iteration instead of a full one. Skipped pairs are exactly pairs the reference `continue`s
-//    on, so results are unchanged (including n_contrib, which indexes the full list);
-//  * warp-level early termination by __all_sync(done), CTA-level by __syncthreads_or.
+//    survivors; skipped pairs are exactly pairs the reference `continue`s on, so results (including
+//    n_contrib, which indexes the full list) are unchanged;
+//  * survivors are processed four at a time: the four alphas (conic form + expf) are independent and
+//    overlap in the pipeline, only the cheap transmittance recurrence is applied in order;
+//  * CTAs are launched heaviest-tile-first (tile_order, written by finalize_binning) so the long
+//    tiles do not end up alone in the tail of the grid.
 //
 // Numerics: the per-pair operation DAG (which product is fused, order of accumulation) mirrors the
 // reference's sm_100a SASS through explicit _rn intrinsics; exp is the
@@ -23,21 +27,79 @@
 namespace gsr {
 namespace {
 
-constexpr int kStages = 2;
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kIlp = 4;
 constexpr uint32_t kFull = 0xffffffffu;
 
-__global__ void __launch_bounds__(kTilePixels) blend_fwd_kernel(
-    const uint2* __restrict__ ranges, const SplatRecord* __restrict__ inst, int W, int H, int grid_x,
-    const float* __restrict__ bg, float* __restrict__ out_color, float* __restrict__ out_depth,
-    float* __restrict__ out_acc, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-    uint32_t* __restrict__ tile_last) {
-  __shared__ __align__(128) float4 s_rec[kStages][kBatch * 3];
-  __shared__ __align__(8) uint64_t s_full[kStages];
-  __shared__ uint32_t s_last;
+struct __align__(128) FwdSmem {
+  float4 rec[kStages][kBatch * 3];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint32_t warps_done;
+  uint32_t last;
+};
+
+__global__ void __launch_bounds__(kThreads) blend_fwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const SplatRecord* __restrict__ inst,
+    int W, int H, int grid_x, const float* __restrict__ bg, float* __restrict__ out_color,
+    float* __restrict__ out_depth, float* __restrict__ out_acc, float* __restrict__ final_T,
+    uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ tile_last) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
+  const int tile = (int)tile_order[blockIdx.x];
+  const uint2 range = ranges[tile];
+  const int total = (int)(range.y - range.x);
+  const int nbatch = (total + kBatch - 1) / kBatch;
+  const SplatRecord* src = inst + range.x;
+  volatile uint32_t* warps_done = &sm.warps_done;
+
+  if (tid == 0) {
+    sm.warps_done = 0;
+    sm.last = 0;
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------ producer warp: one elected lane --------------------------------
+    if (lane == 0) {
+      int issued = 0;
+      for (int b = 0; b < nbatch; ++b) {
+        const int stage = b % kStages;
+        if (b >= kStages) {
+          const uint32_t parity = (uint32_t)(b / kStages - 1) & 1u;
+          bool stop = false;
+          while (!mbar_try_wait(&sm.empty[stage], parity)) {
+            if (*warps_done == kConsumerWarps) {
+              stop = true;
+              break;
+            }
+          }
+          if (stop) break;
+        }
+        if (*warps_done == kConsumerWarps) break;
+        const uint32_t bytes = (uint32_t)min(kBatch, total - b * kBatch) * (uint32_t)sizeof(SplatRecord);
+        mbar_expect_tx(&sm.full[stage], bytes);
+        bulk_g2s(sm.rec[stage], src + (size_t)b * kBatch, bytes, &sm.full[stage]);
+        issued = b + 1;
+      }
+      // never leave the CTA with a bulk copy still in flight towards its shared memory
+      for (int b = max(0, issued - kStages); b < issued; ++b)
+        mbar_wait(&sm.full[b % kStages], (uint32_t)(b / kStages) & 1u);
+    }
+    return;
+  }
+
+  // ---------------------------------- consumer warps ---------------------------------------------
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
   const int wx = tile_x * kTile + (warp & 1) * 8, wy = tile_y * kTile + (warp >> 1) * 4;
   const int px = wx + (lane & 7), py = wy + (lane >> 3);
@@ -45,38 +107,29 @@ __global__ void __launch_bounds__(kTilePixels) blend_fwd_kernel(
   const float pxf = (float)px, pyf = (float)py;
   const float wx0 = (float)wx, wx1 = (float)(wx + 7), wy0 = (float)wy, wy1 = (float)(wy + 3);
 
-  const uint2 range = ranges[tile];
-  const int total = (int)(range.y - range.x);
-  const int nbatch = (total + kBatch - 1) / kBatch;
-  const SplatRecord* src = inst + range.x;
-
-  if (tid == 0) {
-    s_last = 0;
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    for (int b = 0; b < min(nbatch, kStages); ++b) {
-      const uint32_t bytes = (uint32_t)min(kBatch, total - b * kBatch) * (uint32_t)sizeof(SplatRecord);
-      mbar_expect_tx(&s_full[b], bytes);
-      bulk_g2s(s_rec[b], src + (size_t)b * kBatch, bytes, &s_full[b]);
-    }
-  }
-
   float T = 1.0f, A = 0.f, D = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
   uint32_t last_contributor = 0;
   bool done = !inside;
   bool warp_done = __all_sync(kFull, done);
+  if (warp_done && lane == 0) atomicAdd(&sm.warps_done, 1u);
 
   for (int b = 0; b < nbatch; ++b) {
-    const int stage = b & 1;
-    mbar_wait(&s_full[stage], (uint32_t)(b >> 1) & 1u);
-    const int cnt = min(kBatch, total - b * kBatch);
-    const float4* s = s_rec[stage];
-
+    const int stage = b % kStages;
+    {
+      const uint32_t parity = (uint32_t)(b / kStages) & 1u;
+      bool stop = false;
+      while (!mbar_try_wait(&sm.full[stage], parity)) {
+        if (*warps_done == kConsumerWarps) {
+          stop = true;
+          break;
+        }
+      }
+      if (stop || *warps_done == kConsumerWarps) break;
+    }
     if (!warp_done) {
+      const int cnt = min(kBatch, total - b * kBatch);
+      const float4* s = sm.rec[stage];
+      const uint32_t base = (uint32_t)(b * kBatch + 1);
       for (int k = 0; k < cnt; k += 32) {
         const int j = k + lane;
         bool hit = false;
@@ -86,53 +139,52 @@ __global__ void __launch_bounds__(kTilePixels) blend_fwd_kernel(
         }
         uint32_t m = __ballot_sync(kFull, hit);
         while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int jj = k + bit;
-          if (!done) {
-            const float4 q0 = s[3 * jj];
-            const float4 q1 = s[3 * jj + 1];  // {conic.x, conic.y, conic.z, opacity}
+          // up to kIlp survivors at a time: alphas first (independent), then the ordered recurrence
+          int jj[kIlp];
+          float alpha[kIlp];
+#pragma unroll
+          for (int u = 0; u < kIlp; ++u) {
+            const bool valid = m != 0;
+            jj[u] = valid ? k + __ffs(m) - 1 : jj[0];
+            m &= m - 1;
+            const float4 q0 = s[3 * jj[u]];
+            const float4 q1 = s[3 * jj[u] + 1];  // {conic.x, conic.y, conic.z, opacity}
             const float dx = __fadd_rn(q0.x, -pxf);
             const float dy = __fadd_rn(q0.y, -pyf);
             const float quad = __fmaf_rn(dx, __fmul_rn(dx, q1.x), __fmul_rn(dy, __fmul_rn(dy, q1.z)));
             const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, q1.y)));
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, __fmul_rn(q1.w, expf(power)));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-            if (test_T < 0.0001f) {
-              done = true;
-              continue;
+            const float a = fminf(0.99f, __fmul_rn(q1.w, expf(power)));
+            // reference: `if (power > 0) continue; ... if (alpha < 1/255) continue;`
+            alpha[u] = (valid && !(power > 0.0f) && !(a < 1.0f / 255.0f)) ? a : -1.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < kIlp; ++u) {
+            if (alpha[u] >= 0.0f && !done) {
+              const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha[u]));
+              if (test_T < 0.0001f) {
+                done = true;
+              } else {
+                const float4 q2 = s[3 * jj[u] + 2];  // {r, g, b, depth}
+                A = __fmaf_rn(T, alpha[u], A);
+                D = __fmaf_rn(T, __fmul_rn(alpha[u], q2.w), D);
+                C0 = __fmaf_rn(T, __fmul_rn(alpha[u], q2.x), C0);
+                C1 = __fmaf_rn(T, __fmul_rn(alpha[u], q2.y), C1);
+                C2 = __fmaf_rn(T, __fmul_rn(alpha[u], q2.z), C2);
+                T = test_T;
+                last_contributor = base + (uint32_t)jj[u];
+              }
             }
-            const float4 q2 = s[3 * jj + 2];  // {r, g, b, depth}
-            A = __fmaf_rn(T, alpha, A);
-            D = __fmaf_rn(T, __fmul_rn(alpha, q2.w), D);
-            C0 = __fmaf_rn(T, __fmul_rn(alpha, q2.x), C0);
-            C1 = __fmaf_rn(T, __fmul_rn(alpha, q2.y), C1);
-            C2 = __fmaf_rn(T, __fmul_rn(alpha, q2.z), C2);
-            T = test_T;
-            last_contributor = (uint32_t)(b * kBatch + jj + 1);
           }
         }
         if (__all_sync(kFull, done)) {
           warp_done = true;
+          if (lane == 0) atomicAdd(&sm.warps_done, 1u);
           break;
         }
       }
     }
-
-    // every warp is finished with this stage -> it may be refilled; also the CTA-level early-out
-    const int alive = __syncthreads_or(!warp_done);
-    if (!alive) {
-      if (tid == 0 && b + 1 < nbatch) mbar_wait(&s_full[(b + 1) & 1], (uint32_t)((b + 1) >> 1) & 1u);
-      break;
-    }
-    if (tid == 0 && b + kStages < nbatch) {
-      const int nb = b + kStages;
-      const uint32_t bytes = (uint32_t)min(kBatch, total - nb * kBatch) * (uint32_t)sizeof(SplatRecord);
-      mbar_expect_tx(&s_full[stage], bytes);
-      bulk_g2s(s_rec[stage], src + (size_t)nb * kBatch, bytes, &s_full[stage]);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);
   }
 
   if (inside) {
@@ -147,9 +199,10 @@ __global__ void __launch_bounds__(kTilePixels) blend_fwd_kernel(
     out_acc[pix] = A;
   }
   const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
-  if (lane == 0 && wmax) atomicMax(&s_last, wmax);
-  __syncthreads();
-  if (tid == 0) tile_last[tile] = s_last;
+  if (lane == 0 && wmax) atomicMax(&sm.last, wmax);
+  // consumer-only barrier (the producer warp may already have exited)
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+  if (tid == 0) tile_last[tile] = sm.last;
 }
 
 }  // namespace
@@ -158,9 +211,19 @@ cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const
                              const float* background, float* out_color, float* out_depth, float* out_acc,
                              cudaStream_t s) {
   const int grid_x = (width + kTile - 1) / kTile, grid_y = (height + kTile - 1) / kTile;
-  blend_fwd_kernel<<<grid_x * grid_y, kTilePixels, 0, s>>>(img.ranges, b.inst, width, height, grid_x, background,
-                                                          out_color, out_depth, out_acc, img.final_T, img.n_contrib,
-                                                          img.tile_last);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(blend_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(FwdSmem));
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  blend_fwd_kernel<<<grid_x * grid_y, kThreads, sizeof(FwdSmem), s>>>(img.ranges, img.tile_order, b.inst, width,
+                                                                     height, grid_x, background, out_color, out_depth,
+                                                                     out_acc, img.final_T, img.n_contrib,
+                                                                     img.tile_last);
   return cudaGetLastError();
 }
 

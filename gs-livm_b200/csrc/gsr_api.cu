@@ -22,6 +22,36 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- optional per-stage CUDA-event timing (bench.py's roofline numbers) ---------------------------
+// When enabled, an event is recorded on the launch stream before/after every stage of the last
+// forward and backward; gsr_stage_times() synchronises on them and returns milliseconds.
+struct StageTimer {
+  bool enabled = false;
+  bool created = false;
+  bool seen[GSR_NUM_STAGES] = {};
+  cudaEvent_t beg[GSR_NUM_STAGES], end[GSR_NUM_STAGES];
+};
+static thread_local StageTimer t_timer;
+
+struct StageScope {
+  int id;
+  cudaStream_t s;
+  bool on;
+  StageScope(int id_, cudaStream_t s_) : id(id_), s(s_), on(t_timer.enabled) {
+    if (!on) return;
+    if (!t_timer.created) {
+      for (int i = 0; i < GSR_NUM_STAGES; ++i) cudaEventCreate(&t_timer.beg[i]), cudaEventCreate(&t_timer.end[i]);
+      t_timer.created = true;
+    }
+    cudaEventRecord(t_timer.beg[id], s);
+  }
+  ~StageScope() {
+    if (!on) return;
+    cudaEventRecord(t_timer.end[id], s);
+    t_timer.seen[id] = true;
+  }
+};
+
 #define GSR_CUDA(expr, what)                                                                      \
   do {                                                                                            \
     cudaError_t e__ = (expr);                                                                     \
@@ -29,9 +59,12 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // debug == the reference's CHECK_CUDA(A, debug): synchronise and surface asynchronous errors per stage
-#define GSR_STAGE(expr, what, debug, stream)                                                      \
+#define GSR_STAGE(id, expr, what, debug, stream)                                                  \
   do {                                                                                            \
-    GSR_CUDA((expr), what);                                                                       \
+    {                                                                                             \
+      StageScope scope__(id, stream);                                                             \
+      GSR_CUDA((expr), what);                                                                     \
+    }                                                                                             \
     if (debug) GSR_CUDA(cudaStreamSynchronize(stream), what);                                     \
   } while (0)
 
@@ -55,6 +88,7 @@ ImageState carve_image(char* chunk, int width, int height) {
   carve(chunk, s.n_contrib, N);
   carve(chunk, s.ranges, tiles);
   carve(chunk, s.tile_last, tiles);
+  carve(chunk, s.tile_order, tiles);
   return s;
 }
 
@@ -97,6 +131,19 @@ extern "C" {
 int gsr_abi_version(void) { return GSR_ABI_VERSION; }
 const char* gsr_last_error(void) { return t_err; }
 
+void gsr_stage_timing_enable(int on) { t_timer.enabled = on != 0; }
+
+int gsr_stage_times(float* ms, int n) {
+  if (!ms || n < GSR_NUM_STAGES) return fail(GSR_ERR_INVALID, "gsr_stage_times: need room for %d floats", GSR_NUM_STAGES);
+  for (int i = 0; i < GSR_NUM_STAGES; ++i) {
+    ms[i] = -1.0f;
+    if (!t_timer.created || !t_timer.seen[i]) continue;
+    GSR_CUDA(cudaEventSynchronize(t_timer.end[i]), "stage timer");
+    GSR_CUDA(cudaEventElapsedTime(&ms[i], t_timer.beg[i], t_timer.end[i]), "stage timer");
+  }
+  return GSR_OK;
+}
+
 void gsr_shim_set_stream(void* stream) { t_shim_stream = stream; }
 void* gsr_shim_get_stream(void) { return t_shim_stream; }
 
@@ -113,7 +160,7 @@ size_t gsr_required_image(int width, int height) {
   return required_bytes([&] {
     ImageState s = carve_image(nullptr, width, height);
     const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    return (size_t)(reinterpret_cast<uintptr_t>(s.tile_last + tiles));
+    return (size_t)(reinterpret_cast<uintptr_t>(s.tile_order + tiles));
   });
 }
 
@@ -157,8 +204,8 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   if (!img_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: image allocator returned NULL");
   ImageState img = carve_image(img_chunk, a.width, a.height);
 
-  GSR_STAGE(launch_preprocess_fwd(a, geom, radii, focal_x, focal_y, stream), "preprocess_fwd", debug, stream);
-  GSR_STAGE(run_scan(geom, a.P, stream), "scan", debug, stream);
+  GSR_STAGE(GSR_STAGE_PREPROCESS, launch_preprocess_fwd(a, geom, radii, focal_x, focal_y, stream), "preprocess_fwd", debug, stream);
+  GSR_STAGE(GSR_STAGE_SCAN, run_scan(geom, a.P, stream), "scan", debug, stream);
 
   int* h_count = pinned_counter();
   if (!h_count) return fail(GSR_ERR_CUDA, "gsr_forward: cudaMallocHost failed");
@@ -174,14 +221,15 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   BinningState bin = carve_binning(bin_chunk, R);
 
   if (R > 0) {
-    GSR_STAGE(launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream), "duplicate_with_keys", debug,
+    GSR_STAGE(GSR_STAGE_DUPLICATE, launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream), "duplicate_with_keys", debug,
               stream);
     const int bit = (int)higher_msb((uint32_t)tiles);
-    GSR_STAGE(run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
-    GSR_STAGE(launch_finalize_binning(R, bin, geom, a.colors_precomp, img.ranges, stream), "finalize_binning", debug,
+    GSR_STAGE(GSR_STAGE_SORT, run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
+    GSR_STAGE(GSR_STAGE_FINALIZE, launch_finalize_binning(R, bin, geom, a.colors_precomp, img.ranges, stream), "finalize_binning", debug,
               stream);
   }
-  GSR_STAGE(launch_blend_fwd(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream),
+  GSR_STAGE(GSR_STAGE_FINALIZE, launch_order_tiles(tiles, img.ranges, img.tile_order, stream), "order_tiles", debug, stream);
+  GSR_STAGE(GSR_STAGE_BLEND_FWD, launch_blend_fwd(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream),
             "blend_fwd", debug, stream);
   *num_rendered = R;
   return GSR_OK;
@@ -209,11 +257,11 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   const float focal_x = a.width / (2.0f * a.tan_fovx);
 
   if (a.R > 0) {
-    GSR_STAGE(launch_blend_bwd(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
+    GSR_STAGE(GSR_STAGE_BLEND_BWD, launch_blend_bwd(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
                                a.dL_dconic, a.dL_dopacity, a.dL_dcolor, stream),
               "blend_bwd", debug, stream);
   }
-  GSR_STAGE(launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);
+  GSR_STAGE(GSR_STAGE_GEOM_BWD, launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);
   return GSR_OK;
 }
 
@@ -269,6 +317,7 @@ int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* ou
   out->n_contrib = view_of(s.n_contrib, 4, N);
   out->ranges = view_of(s.ranges, 8, tiles);
   out->tile_last = view_of(s.tile_last, 4, tiles);
+  out->tile_order = view_of(s.tile_order, 4, tiles);
   return GSR_OK;
 }
 

@@ -44,6 +44,7 @@ struct ImageState {
   uint32_t* n_contrib;  // [W*H]
   uint2* ranges;        // [tiles]
   uint32_t* tile_last;  // [tiles] max n_contrib in the tile: where the backward starts
+  uint32_t* tile_order; // [tiles] tile ids, longest instance lists first (launch order of the blend CTAs)
 };
 
 struct BinningState {
@@ -86,6 +87,7 @@ cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* rad
 cudaError_t run_sort(const BinningState& b, int R, int end_bit, cudaStream_t s);
 cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomState& g, const float* colors_precomp,
                                     uint2* ranges, cudaStream_t s);
+cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s);
 cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,
                              const float* background, float* out_color, float* out_depth, float* out_acc,
                              cudaStream_t s);
@@ -109,6 +111,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

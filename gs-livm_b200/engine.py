@@ -1,0 +1,124 @@
+"""Allocation-free forward/backward driver over the C ABI: persistent scratch arenas, outputs and gradient
+buffers, so that a mapping iteration issues no allocator traffic (the reference re-`resize_`s its three
+scratch tensors from 0 bytes on every render, src/gs/rasterize_points.cu:83-90).
+
+This is the C-ABI-level path bench.py times with device-resident inputs; the tensor-level operator that
+mirrors the reference one-to-one lives in rasterizer.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .scene import Camera
+
+GRAD_LAYOUT = (  # name, floats per Gaussian — one flat buffer, so a window's all-reduce is ONE collective
+    ("dL_dmean3D", 3), ("dL_dsh", None), ("dL_dscale", 3), ("dL_drot", 4), ("dL_dopacity", 1),
+    ("dL_dmean2D", 3), ("dL_dconic", 4), ("dL_dcolor", 3), ("dL_dcov3D", 6),
+)
+
+
+class _Arena:
+    """Grow-only device byte arena handed to the C ABI's allocator callback."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = torch.empty(0, dtype=torch.uint8, device=device)
+        self.fn = _lib.ALLOC_FN(self._alloc)
+        self.requested = 0
+
+    def _alloc(self, _ctx, nbytes):
+        self.requested = int(nbytes)
+        if self.buf.numel() < nbytes:
+            self.buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return self.buf.data_ptr()
+
+
+class RasterContext:
+    """One (Gaussian set, image size) rasterization context on one device."""
+
+    def __init__(self, P: int, M: int, width: int, height: int, device, sh_degree: int = 3):
+        self.lib = _lib.load()
+        self.P, self.M, self.W, self.H, self.D = int(P), int(M), int(width), int(height), int(sh_degree)
+        self.device = torch.device(device)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.out_color = torch.zeros((3, self.H, self.W), **f32)
+        self.out_depth = torch.zeros((1, self.H, self.W), **f32)
+        self.out_acc = torch.zeros((1, self.H, self.W), **f32)
+        self.radii = torch.zeros((self.P,), dtype=torch.int32, device=self.device)
+        self.geom, self.binning, self.image = _Arena(self.device), _Arena(self.device), _Arena(self.device)
+        # flat gradient buffer; the leading 59 floats per Gaussian (mean3D, sh, scale, rot, opacity) are what a
+        # multi-GPU window all-reduces (236 B per Gaussian at M = 16)
+        sizes = [(n, (self.M * 3 if w is None else w)) for n, w in GRAD_LAYOUT]
+        total = sum(w for _, w in sizes) * self.P
+        self.grad_flat = torch.zeros((total,), **f32)
+        self.grads: Dict[str, torch.Tensor] = {}
+        off = 0
+        for n, w in sizes:
+            self.grads[n] = self.grad_flat[off:off + w * self.P].view(self.P, w)
+            off += w * self.P
+        self.param_grad_floats = (3 + self.M * 3 + 3 + 4 + 1) * self.P
+        self.num_rendered = 0
+        self._fwd_args: Optional[_lib.FwdArgs] = None
+        self._keep = None
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, scene: Dict[str, torch.Tensor], cam: Camera, scale_modifier: float = 1.0, debug: bool = False):
+        a = _lib.FwdArgs()
+        a.P, a.D, a.M, a.width, a.height = self.P, self.D, self.M, self.W, self.H
+        a.background, a.means3D, a.shs = scene["background"].data_ptr(), scene["means3D"].data_ptr(), scene["shs"].data_ptr()
+        a.colors_precomp, a.opacities, a.scales = None, scene["opacities"].data_ptr(), scene["scales"].data_ptr()
+        a.scale_modifier, a.rotations, a.cov3D_precomp = float(scale_modifier), scene["rotations"].data_ptr(), None
+        a.viewmatrix, a.projmatrix, a.cam_pos = cam.viewmatrix.data_ptr(), cam.projmatrix.data_ptr(), cam.camera_center.data_ptr()
+        a.tan_fovx, a.tan_fovy, a.prefiltered = float(cam.tanfovx), float(cam.tanfovy), 0
+        a.out_color, a.out_depth, a.out_acc = self.out_color.data_ptr(), self.out_depth.data_ptr(), self.out_acc.data_ptr()
+        a.radii, a.debug = self.radii.data_ptr(), int(debug)
+        n = C.c_int(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        st = self.lib.gsr_forward(C.byref(a), self.geom.fn, None, self.binning.fn, None, self.image.fn, None, stream,
+                                  C.byref(n))
+        _lib.check(st, "gsr_forward")
+        self.num_rendered = n.value
+        self._fwd_args, self._keep = a, (scene, cam)
+        return self.out_color, self.out_depth, self.out_acc
+
+    def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False) -> Dict[str, torch.Tensor]:
+        """Gradients of the last forward. Outputs are zero-filled here (the contract of the reference's
+        backward: rasterize_points.cu:173-181) inside whatever region the caller is timing."""
+        f = self._fwd_args
+        if f is None:
+            raise RuntimeError("backward() before forward()")
+        self.grad_flat.zero_()
+        g = self.grads
+        a = _lib.BwdArgs()
+        a.P, a.D, a.M, a.R, a.width, a.height = self.P, self.D, self.M, self.num_rendered, self.W, self.H
+        a.background, a.means3D, a.shs, a.colors_precomp = f.background, f.means3D, f.shs, None
+        a.scales, a.scale_modifier, a.rotations, a.cov3D_precomp = f.scales, f.scale_modifier, f.rotations, None
+        a.viewmatrix, a.projmatrix, a.cam_pos = f.viewmatrix, f.projmatrix, f.cam_pos
+        a.tan_fovx, a.tan_fovy, a.radii = f.tan_fovx, f.tan_fovy, self.radii.data_ptr()
+        a.geom_buffer, a.binning_buffer, a.image_buffer = (self.geom.buf.data_ptr(), self.binning.buf.data_ptr(),
+                                                           self.image.buf.data_ptr())
+        a.dL_dpix, a.dL_dacc = dL_dcolor.data_ptr(), dL_dacc.data_ptr()
+        a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = g["dL_dmean2D"].data_ptr(), g["dL_dconic"].data_ptr(), g["dL_dopacity"].data_ptr()
+        a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D = g["dL_dcolor"].data_ptr(), g["dL_dmean3D"].data_ptr(), g["dL_dcov3D"].data_ptr()
+        a.dL_dsh, a.dL_dscale, a.dL_drot = g["dL_dsh"].data_ptr(), g["dL_dscale"].data_ptr(), g["dL_drot"].data_ptr()
+        a.debug = int(debug)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.gsr_backward(C.byref(a), stream), "gsr_backward")
+        return g
+
+    def param_grads(self) -> torch.Tensor:
+        """Flat view of the gradients of the optimised parameters (what a window all-reduces)."""
+        return self.grad_flat[:self.param_grad_floats]
+
+    # ------------------------------------------------------------------------------------------------
+    def stage_timing(self, on: bool) -> None:
+        self.lib.gsr_stage_timing_enable(int(on))
+
+    def stage_times(self) -> Dict[str, float]:
+        arr = (C.c_float * len(_lib.STAGES))()
+        _lib.check(self.lib.gsr_stage_times(arr, len(_lib.STAGES)), "gsr_stage_times")
+        return {n: float(arr[i]) for i, n in enumerate(_lib.STAGES)}

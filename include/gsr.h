@@ -153,6 +153,7 @@ typedef struct gsr_image_view {
   gsr_array_view n_contrib;   /* uint32 per pixel */
   gsr_array_view ranges;      /* uint2 per tile */
   gsr_array_view tile_last;   /* uint32 per tile: max n_contrib over the tile's pixels (ours) */
+  gsr_array_view tile_order;  /* uint32 per tile: launch order, longest lists first (ours) */
 } gsr_image_view;
 
 GSR_API int gsr_abi_version(void);
@@ -176,6 +177,22 @@ GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatri
 GSR_API int gsr_view_geom(char* geom_buffer, int P, gsr_geom_view* out);
 GSR_API int gsr_view_binning(char* binning_buffer, int R, gsr_binning_view* out);
 GSR_API int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* out);
+
+/* Optional per-stage device timing (CUDA events recorded on the launch stream around each stage of the
+ * last forward/backward on the calling thread); used by bench.py for the roofline figures. */
+enum gsr_stage {
+  GSR_STAGE_PREPROCESS = 0, /* preprocess_fwd            <- preprocessCUDA fwd        (forward.cu:179-286)   */
+  GSR_STAGE_SCAN = 1,       /* prefix sum                <- cub InclusiveSum          (rasterizer_impl.cu:270) */
+  GSR_STAGE_DUPLICATE = 2,  /* duplicate_with_keys       <- duplicateWithKeys         (rasterizer_impl.cu:64)  */
+  GSR_STAGE_SORT = 3,       /* (tile|depth) radix sort   <- cub SortPairs             (rasterizer_impl.cu:298) */
+  GSR_STAGE_FINALIZE = 4,   /* tile ranges + record gather <- identifyTileRanges      (rasterizer_impl.cu:106) */
+  GSR_STAGE_BLEND_FWD = 5,  /* blend_fwd                 <- renderCUDA fwd            (forward.cu:291-407)   */
+  GSR_STAGE_BLEND_BWD = 6,  /* blend_bwd                 <- renderCUDA bwd            (backward.cu:438-603)  */
+  GSR_STAGE_GEOM_BWD = 7,   /* fused per-Gaussian bwd    <- computeCov2DCUDA + preprocessCUDA bwd (backward.cu:140-435) */
+  GSR_NUM_STAGES = 8
+};
+GSR_API void gsr_stage_timing_enable(int on);
+GSR_API int gsr_stage_times(float* ms_out, int n); /* ms per stage, -1 where the stage did not run */
 
 /* Stream used by the C++ shim (CudaRasterizer::Rasterizer has no stream parameter). Default NULL =
  * legacy default stream, identical to the reference's launches. Thread-local. */
