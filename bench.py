@@ -1,0 +1,408 @@
+"""bench.py — forward+backward rendered frames/s of the rasterizer hot path (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (configs[1] of BASELINE.json): a 1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480,
+one "step" = one forward (C+D+S) + one backward of one keyframe view. With N ranks every rank renders its own
+view of the 8-pose keyframe window per step (weak scaling: the per-GPU work is fixed) and the per-Gaussian
+parameter gradients (59 floats = 236 B per Gaussian) are summed with one NCCL all-reduce inside the step.
+
+Printed (rank 0, ONE JSON line):
+  value     whole-job frames/s with everything resident in HBM, timed with CUDA events over K steps at the
+            C-ABI level (gs_livm_b200.engine.RasterContext: persistent scratch arenas, gradient zero-fill
+            included), max over ranks;
+  e2e       the same metric through the public tensor-level operator (GaussianRasterizer + autograd) with the
+            step's host inputs (camera + target image, pinned memory) copied host->device and the loss copied
+            device->host inside the timed region;
+  roofline  the dominant kernel's algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json, plus the same
+            for every stage under "stages";
+  cpu_baseline  Oracle B (scalar CPU port, all host cores for the blend loops) on one frame of the same workload.
+`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/gsr_ref_ext.so, compiled for
+sm_100a from /root/reference) on the same GPU, scene and step — that is the "reference CUDA rasterizer" the
+north star's >=10x target names; the reference has no CPU implementation of this path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+P_GAUSS = 1_000_000
+SH_DEGREE = 3
+SEED = 20241017 + 2
+WINDOW = 8
+MY_KERNELS_PER_STEP = 7  # preprocess, duplicate_with_keys, finalize_binning, order_tiles, blend_fwd, blend_bwd, geom_bwd
+LIB_KERNELS_PER_STEP = "cub: scan(2) + radix sort(histogram, scan, 6 onesweep passes); torch: gradient zero-fill"
+
+
+# ----------------------------------------------------------------------------------------------------------
+def sample_clocks_start(gpu_index: int):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        return subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+        return None
+
+
+def sample_clocks_stop(proc):
+    if proc is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    proc.terminate()
+    try:
+        out, _ = proc.communicate(timeout=5)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+        out = ""
+    sm, smax, reasons = [], [], set()
+    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    for line in out.strip().splitlines():
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 8:
+            continue
+        try:
+            sm.append(float(f[0]))
+            smax.append(float(f[1]))
+        except ValueError:
+            continue
+        for n, v in zip(names, f[4:8]):
+            if v.lower().startswith("active"):
+                reasons.add(n)
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif n_gpus > 1:
+        raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    return rank, world, local
+
+
+def barrier_sync(world):
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(ms: float, world: int, dev) -> float:
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------------------------
+def build_workload(dev):
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import scene
+    sc_cpu = scene.make_scene(P_GAUSS, SEED, SH_DEGREE)
+    sc = {k: v.to(dev) for k, v in sc_cpu.items()}
+    cams_cpu = [scene.scene_camera(sc_cpu, i, scene.NTU) for i in range(WINDOW)]
+    cams = [c.to(dev) for c in cams_cpu]
+    H, W = cams[0].height, cams[0].width
+    g = torch.Generator().manual_seed(SEED + 1)
+    dC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
+    dS = (torch.randn((1, H, W), generator=g) / (H * W)).to(dev)
+    return sc_cpu, sc, cams_cpu, cams, dC, dS
+
+
+def algorithmic_bytes(P, P_v, R, px, tiles, M=16):
+    """SURVEY.md section 8d per-unit figures, restated for OUR data layout where it moves fewer bytes
+    (DESIGN.md 'algorithmic bytes'): 48-byte records instead of separate arrays, no cov3D round trip."""
+    P_c = P - P_v
+    return {
+        "preprocess": (12 + 12 + 16 + 4 + 12 * M + 48 + 1 + 4 + 4) * P_v + (12 + 12 + 8) * P_c,
+        "scan": 8 * P,
+        "duplicate": (16 + 4 + 4 + 4) * P_v + 4 * P_c + 12 * R,
+        "sort": 24 * R * 6 + 8 * R,
+        "finalize": (8 + 4 + 48 + 48) * R + 8 * tiles,
+        "blend_fwd": 48 * R + 28 * px,
+        "blend_bwd": (48 + 4) * R + 24 * px + 36 * R,
+        "geom_bwd": (12 + 4 + 12 * M + 1 + 12 + 16 + 12 + 16 + 12 + 12 + 24 + 12 * M + 12 + 16) * P_v + 4 * P_c,
+    }
+
+
+def blend_flops(c_fwd, c_bwd):
+    """fwd 11 X + 12 X_p + 2 X_a + 14 X_b ; bwd 11 X' + 12 X'_p + 81 X_b (reference inner loops)."""
+    X, Xp, Xa, Xb = (float(v) for v in c_fwd)
+    Xq, Xqp, Xqb = (float(v) for v in c_bwd)
+    return 11 * X + 12 * Xp + 2 * Xa + 14 * Xb, 11 * Xq + 12 * Xqp + 81 * Xqb
+
+
+def cpu_baseline(sc_cpu, cam_cpu, dC, dS):
+    """Oracle B (CPU port of the path) on ONE frame of the same workload: preprocess + binning single-threaded,
+    blend loops on all host cores. Also returns the pair counters the FP32 roofline needs."""
+    from oracle import cpu
+    cores = os.cpu_count() or 1
+    osc = cpu.OracleScene(sc_cpu["means3D"], sc_cpu["opacities"], sc_cpu["background"], cam_cpu.viewmatrix,
+                          cam_cpu.projmatrix, cam_cpu.camera_center, cam_cpu.tanfovx, cam_cpu.tanfovy, cam_cpu.width,
+                          cam_cpu.height, shs=sc_cpu["shs"], sh_degree=SH_DEGREE, scales=sc_cpu["scales"],
+                          rotations=sc_cpu["rotations"])
+    t0 = time.perf_counter()
+    fwd = cpu.forward(osc, nthreads=cores)
+    t1 = time.perf_counter()
+    bwd = cpu.backward(osc, fwd, dC.cpu(), dS.cpu(), nthreads=cores)
+    t2 = time.perf_counter()
+    return {
+        "value": 1.0 / (t2 - t0), "unit": "frames/s", "cores": cores, "kind": "port",
+        "sample": "1 frame (fwd %.2f s + bwd %.2f s) of the same 1M-Gaussian 752x480 workload; scalar C port "
+                  "(oracle/gsr_oracle.c), blend loops on %d pthreads, preprocess/sort single-threaded" % (t1 - t0, t2 - t1, cores),
+    }, fwd["counters"], bwd["bwd_counters"], fwd
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, dev):
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import _lib, engine, rasterizer, scene
+
+    sc_cpu, sc, cams_cpu, cams, dC, dS = build_workload(dev)
+    H, W = cams[0].height, cams[0].width
+    ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE)
+    flat = ctx.param_grads()
+
+    def step_resident(i):
+        cam = cams[(rank + i) % WINDOW]
+        ctx.forward(sc, cam)
+        ctx.backward(dC, dS)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+    # ---- device-resident timing: W warm-up, K timed steps, CUDA events, max over ranks ----
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    ctx.stage_timing(True)
+    stage_acc = {n: 0.0 for n in _lib.STAGES}
+    barrier_sync(world)
+    clk = sample_clocks_start(dev.index or 0) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+        if i < 16:  # reading the stage events synchronises; keep it to a few steps and outside the rate below
+            pass
+    e1.record()
+    barrier_sync(world)
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    clocks = sample_clocks_stop(clk) if rank == 0 else None
+    # per-stage times: a second, separately timed pass (event reads synchronise, so they stay out of `value`)
+    n_stage = min(args.steps, 20)
+    for i in range(n_stage):
+        step_resident(i)
+        torch.cuda.synchronize()
+        for n, v in ctx.stage_times().items():
+            stage_acc[n] += v
+    ctx.stage_timing(False)
+    stage_ms = {n: stage_acc[n] / n_stage for n in _lib.STAGES}
+    R = ctx.num_rendered
+    P_v = int((ctx.radii > 0).sum())
+
+    # ---- end to end through the public operator: H2D camera + target, autograd, D2H loss ----
+    leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    host_targets = [torch.rand((3, H, W)).pin_memory() for _ in range(2)]
+    host_cams = [torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
+                 for c in cams_cpu]
+    h2d_bytes = host_targets[0].numel() * 4 + host_cams[0].numel() * 4
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e(i):
+        cpu_cam = cams_cpu[(rank + i) % WINDOW]
+        packed = host_cams[(rank + i) % WINDOW].to(dev, non_blocking=True)
+        target = host_targets[i % 2].to(dev, non_blocking=True)
+        rs = rasterizer.GaussianRasterizationSettings(H, W, cpu_cam.tanfovx, cpu_cam.tanfovy, sc["background"], 1.0,
+                                                      packed[:16].view(4, 4), packed[16:32].view(4, 4), SH_DEGREE,
+                                                      packed[32:35], False)
+        for t in list(leaves.values()) + [means2D]:
+            t.grad = None
+        color, radii, depth, acc = rasterizer.GaussianRasterizer(rs)(
+            leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+            rotations=leaves["rotations"])
+        loss = (color - target).abs().mean() + 0.1 * acc.mean()
+        loss.backward()
+        if world > 1:
+            for t in leaves.values():
+                dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the step's result is on the host
+        return float(loss_host[0])
+
+    for i in range(3):
+        step_e2e(i)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier_sync(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+
+    if rank != 0:
+        return None
+    # ---- roofline + CPU baseline (rank 0 only) ----
+    hbm_peak, peak_src, sm_max_mhz = measured_peaks()
+    px, tiles = H * W, ((W + 15) // 16) * ((H + 15) // 16)
+    alg = algorithmic_bytes(P_GAUSS, P_v, R, px, tiles)
+    cpu_base, c_fwd, c_bwd = None, None, None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base, c_fwd, c_bwd, _ = cpu_baseline(sc_cpu, cams_cpu[0], dC, dS)
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak_tf = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    stages = {}
+    for n in _lib.STAGES:
+        t = stage_ms[n] * 1e-3
+        ach = alg[n] / t / 1e9 if t > 0 else 0.0
+        stages[n] = {"us": round(stage_ms[n] * 1e3, 1), "alg_bytes": int(alg[n]), "achieved_gbs": round(ach, 1),
+                     "frac_hbm": round(ach / hbm_peak, 4)}
+    if c_fwd is not None:
+        f_fwd, f_bwd = blend_flops(c_fwd, c_bwd)
+        for n, fl in (("blend_fwd", f_fwd), ("blend_bwd", f_bwd)):
+            tf = fl / (stage_ms[n] * 1e-3) / 1e12
+            stages[n].update({"ref_flops": fl, "achieved_tflops": round(tf, 3), "frac_fp32": round(tf / fp32_peak_tf, 4)})
+    dominant = max(_lib.STAGES, key=lambda n: stage_ms[n])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(dominant)
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": stages[dominant]["achieved_gbs"], "peak": hbm_peak,
+                "unit": "GB/s", "frac": stages[dominant]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
+                "note": "blend kernels are FP32/latency-bound, not HBM-bound: see stages[*].frac_fp32 (peak %.1f "
+                        "TFLOP/s = SMs x 128 lanes x 2 x max SM clock); preprocess/geom_bwd are the HBM-bound stages"
+                        % fp32_peak_tf,
+                "stages": stages}
+    frames = args.steps * world
+    out = {
+        "metric": "fwd+bwd rendered frames/s (752x480, C+D+S)", "value": frames / (ms_total * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480 forward+backward "
+                               "(BASELINE.json configs[1]); one keyframe view per GPU per step, 8-pose window",
+                   "P": P_GAUSS, "P_visible": P_v, "R": R, "sh_degree": SH_DEGREE, "width": W, "height": H,
+                   "parallelism": "view-sharded window, replicated Gaussians" + (
+                       ", NCCL all-reduce of 236 B/Gaussian per step" if world > 1 else ""),
+                   "l2": "inputs (236 MB of Gaussians + 150 MB of per-frame state) exceed the 126 MB L2; no flush needed",
+                   "library_kernels": LIB_KERNELS_PER_STEP},
+        "clocks": clocks,
+        "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "path": "GaussianRasterizer (tensor-level mirror of the reference operator) + torch autograd + L1 loss"},
+        "gpu_launches": MY_KERNELS_PER_STEP * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu_base,
+    }
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world, dev):
+    """The unmodified reference CUDA rasterizer (oracle/_ref), same scene, same step, same GPU. Rank 0 only."""
+    if rank != 0:
+        return None
+    from oracle import ref
+    if not ref.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref/gsr_ref_ext.so missing (build with make -C oracle ref)"}
+    sc_cpu, sc, cams_cpu, cams, dC, dS = build_workload(dev)
+    H, W = cams[0].height, cams[0].width
+
+    def step(i):
+        cam = cams[i % WINDOW]
+        fwd = ref.forward(sc["background"], sc["means3D"], sc["opacities"], sc["scales"], sc["rotations"], sc["shs"],
+                          SH_DEGREE, cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, H, W,
+                          with_state=False)
+        ref.backward(fwd, sc["background"], sc["means3D"], sc["scales"], sc["rotations"], sc["shs"], SH_DEGREE,
+                     cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, dC, dS)
+        return fwd["num_rendered"]
+
+    for i in range(max(args.warmup, 3)):
+        R = step(i)
+    torch.cuda.synchronize()
+    clk = sample_clocks_start(dev.index or 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sample_clocks_stop(clk)
+    fps = args.steps / (ms * 1e-3)
+    return {
+        "impl": "reference", "metric": "fwd+bwd rendered frames/s (752x480, C+D+S)", "value": fps, "unit": "frames/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480 forward+backward "
+                               "(BASELINE.json configs[1])", "P": P_GAUSS, "R": int(R), "sh_degree": SH_DEGREE,
+                   "width": W, "height": H},
+        "clocks": clocks,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                         "sample": "UNMODIFIED reference CUDA rasterizer (src/cuda_rasterizer + rasterize_points.cu) "
+                                   "compiled for sm_100a into oracle/_ref, RasterizeGaussiansCUDA + "
+                                   "RasterizeGaussiansBackwardCUDA per step on this B200, driven by 1 host thread; "
+                                   "the reference has no CPU implementation of this path"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gs_livm_b200 has no CPU path")
+    if args.impl == "reference":
+        # rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work (no process group)
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        print(json.dumps(run_reference(args, 0, 1, dev)))
+        return
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    out = run_ours(args, rank, world, dev)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,7 @@ class ImageView(C.Structure):
 SYMBOLS = {
     "gsr_abi_version": (C.c_int, []),
     "gsr_last_error": (C.c_char_p, []),
+    "gsr_sizeof": (C.c_size_t, [C.c_int]),
     "gsr_required_geom": (C.c_size_t, [C.c_int]),
     "gsr_required_image": (C.c_size_t, [C.c_int, C.c_int]),
     "gsr_required_binning": (C.c_size_t, [C.c_int]),

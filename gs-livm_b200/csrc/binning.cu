@@ -112,13 +112,15 @@ __global__ void __launch_bounds__(256) finalize_binning_kernel(int R, const uint
 // Launch order of the blend CTAs: tiles bucketed by floor(log2(list length)) and emitted longest
 // bucket first (coarse LPT scheduling; the order inside a bucket is irrelevant). One CTA.
 __global__ void __launch_bounds__(1024) order_tiles_kernel(int tiles, const uint2* __restrict__ ranges,
-                                                          uint32_t* __restrict__ order) {
+                                                          uint32_t* __restrict__ order,
+                                                          uint32_t* __restrict__ tile_last) {
   __shared__ uint32_t s_count[33], s_base[33];
   if (threadIdx.x < 33) s_count[threadIdx.x] = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
     const uint2 r = ranges[t];
     atomicAdd(&s_count[32 - __clz(r.y - r.x)], 1u);
+    tile_last[t] = 0;  // blend_fwd accumulates the tile's last contributor with atomicMax
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -137,8 +139,9 @@ __global__ void __launch_bounds__(1024) order_tiles_kernel(int tiles, const uint
 
 }  // namespace
 
-cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s) {
-  order_tiles_kernel<<<1, 1024, 0, s>>>(tiles, ranges, tile_order);
+cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, uint32_t* tile_last,
+                               cudaStream_t s) {
+  order_tiles_kernel<<<1, 1024, 0, s>>>(tiles, ranges, tile_order, tile_last);
   return cudaGetLastError();
 }
 

@@ -6,11 +6,11 @@
 // silhouette channel and rasterizer.cu:77-80 drops grad_out_depth).
 //
 // Design ("blend_bwd"):
-//  * same tiling / warp-specialised TMA pipeline (producer warp + 8 decoupled consumer warps, full/empty
-//    mbarriers, no CTA-wide barrier in the loop) / sub-tile ballot culling as blend_fwd, traversed in
-//    reverse; whole batches behind the tile's last contributor (tile_last, written by the forward) are
-//    never loaded; survivors are processed two at a time so that the exp / alpha of the second overlaps
-//    the recurrence and warp reduction of the first;
+//  * same structure as blend_fwd, traversed in reverse: 8 fully independent warps per tile, each with a
+//    private TMA-fed ring (records + Gaussian ids) and private mbarriers, sub-tile ballot culling with
+//    survivor compaction; everything behind the warp's own last contributor (max n_contrib of its 32
+//    pixels) is never fetched; survivors are processed two at a time so that the exp / alpha of the
+//    second overlaps the recurrence and warp reduction of the first;
 //  * the reference issues 9 float atomics per blended (pixel, Gaussian) pair, all lanes of a warp
 //    hitting the same 9 addresses. Here the warp walks the same Gaussian in lock-step, the 9 partial
 //    sums are reduced across the 32 lanes with a transposing butterfly (14 shuffles for 9 values
@@ -24,8 +24,8 @@ namespace gsr {
 namespace {
 
 constexpr int kStages = 3;
-constexpr int kConsumerWarps = 8;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kWarps = 8;
+constexpr int kWB = 64;  // instances per per-warp batch
 constexpr int kIlp = 2;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kIdPad = 4;  // ids are bulk-copied from a 16-byte aligned-down start
@@ -60,59 +60,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-struct __align__(128) BwdSmem {
-  float4 rec[kStages][kBatch * 3];
-  uint32_t id[kStages][kBatch + kIdPad];
+struct __align__(128) WarpRing {
+  float4 rec[kStages][kWB * 3];
+  uint32_t id[kStages][kWB + kIdPad];
   uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint32_t list[kWB / 4];  // compacted survivor indices (descending), one byte each
 };
 
-__global__ void __launch_bounds__(kThreads) blend_bwd_kernel(
+__global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const SplatRecord* __restrict__ inst,
     const uint32_t* __restrict__ point_list, int W, int H, int grid_x, const float* __restrict__ bg,
-    const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_last,
+    const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpix, const float* __restrict__ dL_dacc, float* __restrict__ dL_dmean2D,
     float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpRing& ring = reinterpret_cast<WarpRing*>(smem_raw)[warp];
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
   const int tile = (int)tile_order[blockIdx.x];
-  const uint32_t t_last = tile_last[tile];
-  if (t_last == 0) return;  // nothing was blended in this tile (uniform for the CTA)
-
   const uint2 range = ranges[tile];
   const int total = (int)(range.y - range.x);
-  const int first_batch = (int)((t_last - 1) / kBatch);  // batch holding the tile's last contributor
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], kConsumerWarps);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == kConsumerWarps) {
-    // producer: batches first_batch, first_batch-1, ..., 0 (iteration `it` uses stage it % kStages)
-    if (lane == 0) {
-      for (int b = first_batch, it = 0; b >= 0; --b, ++it) {
-        const int stage = it % kStages;
-        if (it >= kStages) mbar_wait(&sm.empty[stage], (uint32_t)(it / kStages - 1) & 1u);
-        const int cnt = min(kBatch, total - b * kBatch);
-        const uint32_t rec_bytes = (uint32_t)cnt * (uint32_t)sizeof(SplatRecord);
-        const size_t start = (size_t)range.x + (size_t)b * kBatch;
-        const size_t a0 = start & ~(size_t)3;  // bulk copies need 16-byte aligned global addresses
-        const uint32_t id_bytes = (uint32_t)((((start - a0) + cnt) * 4 + 15) & ~(size_t)15);
-        mbar_expect_tx(&sm.full[stage], rec_bytes + id_bytes);
-        bulk_g2s(sm.rec[stage], inst + start, rec_bytes, &sm.full[stage]);
-        bulk_g2s(sm.id[stage], point_list + a0, id_bytes, &sm.full[stage]);
-      }
-    }
-    return;  // every issued batch is consumed (all consumers walk all batches), nothing left in flight
-  }
 
   const int tile_x = tile % grid_x, tile_y = tile / grid_x;
   const int wx = tile_x * kTile + (warp & 1) * 8, wy = tile_y * kTile + (warp >> 1) * 4;
@@ -123,15 +90,17 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(
 
   const size_t pix = (size_t)W * py + px;
   const size_t plane = (size_t)W * H;
-  const float T_final = inside ? final_T[pix] : 0.f;
   const uint32_t last_contributor = inside ? n_contrib[pix] : 0u;
+  const uint32_t warp_last = __reduce_max_sync(kFull, last_contributor);
+  if (warp_last == 0) return;  // nothing was blended into this warp's 32 pixels
+
+  const float T_final = inside ? final_T[pix] : 0.f;
   float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f, dacc = 0.f;
   if (inside) {
     dpx0 = dL_dpix[pix], dpx1 = dL_dpix[plane + pix], dpx2 = dL_dpix[2 * plane + pix];
     dacc = dL_dacc[pix];
   }
   const float bg_dot = __ldg(bg) * dpx0 + __ldg(bg + 1) * dpx1 + __ldg(bg + 2) * dpx2;
-  const uint32_t warp_last = __reduce_max_sync(kFull, last_contributor);
 
   float T = T_final;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_s = 0.f;  // accum_rec, accum_acc_rec
@@ -152,91 +121,119 @@ __global__ void __launch_bounds__(kThreads) blend_bwd_kernel(
     }
   }
 
+  // batches first_batch, first_batch-1, ..., 0; iteration `it` uses ring stage it % kStages
+  const int first_batch = (int)((warp_last - 1) / kWB);
+  auto issue = [&](int b, int it) {  // lane 0 only
+    const int stage = it % kStages;
+    const int cnt = min(kWB, total - b * kWB);
+    const uint32_t rec_bytes = (uint32_t)cnt * (uint32_t)sizeof(SplatRecord);
+    const size_t start = (size_t)range.x + (size_t)b * kWB;
+    const size_t a0 = start & ~(size_t)3;  // bulk copies need 16-byte aligned global addresses
+    const uint32_t id_bytes = (uint32_t)((((start - a0) + cnt) * 4 + 15) & ~(size_t)15);
+    mbar_expect_tx(&ring.full[stage], rec_bytes + id_bytes);
+    bulk_g2s(ring.rec[stage], inst + start, rec_bytes, &ring.full[stage]);
+    bulk_g2s(ring.id[stage], point_list + a0, id_bytes, &ring.full[stage]);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
+    mbar_fence_init();
+    for (int it = 0; it < kStages && first_batch - it >= 0; ++it) issue(first_batch - it, it);
+  }
+  __syncwarp();
+
   for (int b = first_batch, it = 0; b >= 0; --b, ++it) {
     const int stage = it % kStages;
-    mbar_wait(&sm.full[stage], (uint32_t)(it / kStages) & 1u);
-    const int cnt = min(kBatch, total - b * kBatch);
-    const float4* s = sm.rec[stage];
-    const uint32_t* ids = sm.id[stage] + (((size_t)range.x + (size_t)b * kBatch) & 3);
-    const uint32_t batch_base = (uint32_t)b * kBatch;
+    mbar_wait(&ring.full[stage], (uint32_t)(it / kStages) & 1u);
+    const int cnt = min(kWB, total - b * kWB);
+    const float4* s = ring.rec[stage];
+    const uint32_t* ids = ring.id[stage] + (((size_t)range.x + (size_t)b * kWB) & 3);
+    const uint32_t batch_base = (uint32_t)b * kWB;
 
-    if (batch_base < warp_last) {
-      for (int k = ((cnt - 1) >> 5) << 5; k >= 0; k -= 32) {
-        const int j = k + lane;
-        bool hit = false;
-        if (j < cnt && batch_base + (uint32_t)j < warp_last) {
-          const float4 c = s[3 * j];
-          hit = (c.x + c.z >= wx0) && (c.x - c.z <= wx1) && (c.y + c.w >= wy0) && (c.y - c.w <= wy1);
-        }
-        uint32_t m = __ballot_sync(kFull, hit);
-        while (m) {
-          // two survivors per step (back to front): alpha/G of both are independent of the recurrence
-          int jj[kIlp];
-          float G[kIlp], alpha[kIlp], dxs[kIlp], dys[kIlp];
+    // ---- cull + compact, highest index first ----
+    int nhit = 0;
+    uint8_t* list8 = reinterpret_cast<uint8_t*>(ring.list);
 #pragma unroll
-          for (int u = 0; u < kIlp; ++u) {
-            const bool valid = m != 0;
-            const int bit = valid ? 31 - __clz(m) : 0;
-            jj[u] = valid ? k + bit : jj[0];
-            m &= ~(valid ? (1u << bit) : 0u);
-            const float4 q0 = s[3 * jj[u]];
-            const float4 q1 = s[3 * jj[u] + 1];
-            const float dx = q0.x - pxf, dy = q0.y - pyf;
-            const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, q1.x), __fmul_rn(dy, __fmul_rn(dy, q1.z))),
-                                          -0.5f, -__fmul_rn(dy, __fmul_rn(dx, q1.y)));
-            const float g = expf(power);
-            const float a = fminf(0.99f, __fmul_rn(q1.w, g));
-            const bool on = valid && (batch_base + (uint32_t)jj[u] < last_contributor) && !(power > 0.0f) &&
-                            !(a < 1.0f / 255.0f);
-            G[u] = g, alpha[u] = on ? a : -1.0f, dxs[u] = dx, dys[u] = dy;
-          }
-#pragma unroll
-          for (int u = 0; u < kIlp; ++u) {
-            const bool active = alpha[u] >= 0.0f;
-            if (!__any_sync(kFull, active)) continue;
-            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float g_op = 0.f;
-            if (active) {
-              const float4 q1 = s[3 * jj[u] + 1];
-              const float4 q2 = s[3 * jj[u] + 2];
-              const float a = alpha[u], dx = dxs[u], dy = dys[u];
-              const float one_m_alpha = 1.f - a;
-              T = T / one_m_alpha;
-              const float dchannel_dcolor = a * T;
-              const float keep = 1.f - last_alpha;
-              acc0 = last_alpha * lc0 + keep * acc0;
-              acc1 = last_alpha * lc1 + keep * acc1;
-              acc2 = last_alpha * lc2 + keep * acc2;
-              acc_s = last_alpha * last_s + keep * acc_s;
-              lc0 = q2.x, lc1 = q2.y, lc2 = q2.z, last_s = 1.0f;
-              float dL_dalpha = (q2.x - acc0) * dpx0 + (q2.y - acc1) * dpx1 + (q2.z - acc2) * dpx2;
-              dL_dalpha += (1.0f - acc_s) * dacc;
-              dL_dalpha *= T;
-              last_alpha = a;
-              dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
-              const float dL_dG = q1.w * dL_dalpha;
-              const float gdx = G[u] * dx, gdy = G[u] * dy;
-              const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
-              const float dG_ddely = -gdy * q1.z - gdx * q1.y;
-              g[0] = dchannel_dcolor * dpx0;
-              g[1] = dchannel_dcolor * dpx1;
-              g[2] = dchannel_dcolor * dpx2;
-              g[3] = dL_dG * dG_ddelx * ddelx_dx;
-              g[4] = dL_dG * dG_ddely * ddely_dy;
-              g[5] = -0.5f * gdx * dx * dL_dG;
-              g[6] = -0.5f * gdx * dy * dL_dG;
-              g[7] = -0.5f * gdy * dy * dL_dG;
-              g_op = G[u] * dL_dalpha;
-            }
-            const float t = transpose_reduce8(g, lane);
-            const float o = warp_sum(g_op);
-            if (gptr) atomicAdd(gptr + (size_t)ids[jj[u]] * gstride, lane == 1 ? o : t);
-          }
-        }
+    for (int k = kWB - 32; k >= 0; k -= 32) {
+      const int j = k + lane;
+      bool hit = false;
+      if (j < cnt && batch_base + (uint32_t)j < warp_last) {
+        const float4 c = s[3 * j];
+        hit = (c.x + c.z >= wx0) && (c.x - c.z <= wx1) && (c.y + c.w >= wy0) && (c.y - c.w <= wy1);
       }
+      const uint32_t m = __ballot_sync(kFull, hit);
+      if (hit) list8[nhit + __popc(m & ~((2u << lane) - 1u))] = (uint8_t)j;  // rank among higher lanes
+      nhit += __popc(m);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[stage]);
+
+    for (int g = 0; g < nhit; g += kIlp) {
+      // kIlp survivors per step (back to front): G / alpha of all are independent of the recurrence
+      const uint32_t packed = ring.list[g >> 2] >> (8 * (g & 3));
+      int jj[kIlp];
+      float G[kIlp], alpha[kIlp], dxs[kIlp], dys[kIlp];
+#pragma unroll
+      for (int u = 0; u < kIlp; ++u) {
+        const bool valid = g + u < nhit;
+        jj[u] = valid ? (int)((packed >> (8 * u)) & 0xffu) : (int)(packed & 0xffu);
+        const float4 q0 = s[3 * jj[u]];
+        const float4 q1 = s[3 * jj[u] + 1];
+        const float dx = q0.x - pxf, dy = q0.y - pyf;
+        const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, q1.x), __fmul_rn(dy, __fmul_rn(dy, q1.z))), -0.5f,
+                                      -__fmul_rn(dy, __fmul_rn(dx, q1.y)));
+        const float gg = expf(power);
+        const float a = fminf(0.99f, __fmul_rn(q1.w, gg));
+        const bool on = valid && (batch_base + (uint32_t)jj[u] < last_contributor) && !(power > 0.0f) &&
+                        !(a < 1.0f / 255.0f);
+        G[u] = gg, alpha[u] = on ? a : -1.0f, dxs[u] = dx, dys[u] = dy;
+      }
+#pragma unroll
+      for (int u = 0; u < kIlp; ++u) {
+        const bool active = alpha[u] >= 0.0f;
+        if (!__any_sync(kFull, active)) continue;
+        float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float g_op = 0.f;
+        if (active) {
+          const float4 q1 = s[3 * jj[u] + 1];
+          const float4 q2 = s[3 * jj[u] + 2];
+          const float a = alpha[u], dx = dxs[u], dy = dys[u];
+          const float one_m_alpha = 1.f - a;
+          T = T / one_m_alpha;
+          const float dchannel_dcolor = a * T;
+          const float keep = 1.f - last_alpha;
+          acc0 = last_alpha * lc0 + keep * acc0;
+          acc1 = last_alpha * lc1 + keep * acc1;
+          acc2 = last_alpha * lc2 + keep * acc2;
+          acc_s = last_alpha * last_s + keep * acc_s;
+          lc0 = q2.x, lc1 = q2.y, lc2 = q2.z, last_s = 1.0f;
+          float dL_dalpha = (q2.x - acc0) * dpx0 + (q2.y - acc1) * dpx1 + (q2.z - acc2) * dpx2;
+          dL_dalpha += (1.0f - acc_s) * dacc;
+          dL_dalpha *= T;
+          last_alpha = a;
+          dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
+          const float dL_dG = q1.w * dL_dalpha;
+          const float gdx = G[u] * dx, gdy = G[u] * dy;
+          const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
+          const float dG_ddely = -gdy * q1.z - gdx * q1.y;
+          gr[0] = dchannel_dcolor * dpx0;
+          gr[1] = dchannel_dcolor * dpx1;
+          gr[2] = dchannel_dcolor * dpx2;
+          gr[3] = dL_dG * dG_ddelx * ddelx_dx;
+          gr[4] = dL_dG * dG_ddely * ddely_dy;
+          gr[5] = -0.5f * gdx * dx * dL_dG;
+          gr[6] = -0.5f * gdx * dy * dL_dG;
+          gr[7] = -0.5f * gdy * dy * dL_dG;
+          g_op = G[u] * dL_dalpha;
+        }
+        const float t = transpose_reduce8(gr, lane);
+        const float o = warp_sum(g_op);
+        if (gptr) atomicAdd(gptr + (size_t)ids[jj[u]] * gstride, lane == 1 ? o : t);
+      }
+    }
+    __syncwarp();  // all lanes are done with this stage before it is refilled
+    if (lane == 0 && b - kStages >= 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(b - kStages, it + kStages);
+    }
   }
 }
 
@@ -246,18 +243,18 @@ cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const
                              const float* background, const float* dL_dpix, const float* dL_dacc, float* dL_dmean2D,
                              float* dL_dconic, float* dL_dopacity, float* dL_dcolor, cudaStream_t s) {
   const int grid_x = (width + kTile - 1) / kTile, grid_y = (height + kTile - 1) / kTile;
+  constexpr int kSmem = (int)sizeof(WarpRing) * kWarps;
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(BwdSmem));
+    cudaError_t e = cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  blend_bwd_kernel<<<grid_x * grid_y, kThreads, sizeof(BwdSmem), s>>>(
+  blend_bwd_kernel<<<grid_x * grid_y, kWarps * 32, kSmem, s>>>(
       img.ranges, img.tile_order, b.inst, b.vals, width, height, grid_x, background, img.final_T, img.n_contrib,
-      img.tile_last, dL_dpix, dL_dacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+      dL_dpix, dL_dacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
   return cudaGetLastError();
 }
 

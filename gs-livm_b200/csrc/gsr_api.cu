@@ -131,6 +131,18 @@ extern "C" {
 int gsr_abi_version(void) { return GSR_ABI_VERSION; }
 const char* gsr_last_error(void) { return t_err; }
 
+size_t gsr_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(gsr_fwd_args);
+    case 1: return sizeof(gsr_bwd_args);
+    case 2: return sizeof(gsr_array_view);
+    case 3: return sizeof(gsr_geom_view);
+    case 4: return sizeof(gsr_binning_view);
+    case 5: return sizeof(gsr_image_view);
+    default: return 0;
+  }
+}
+
 void gsr_stage_timing_enable(int on) { t_timer.enabled = on != 0; }
 
 int gsr_stage_times(float* ms, int n) {
@@ -221,14 +233,17 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   BinningState bin = carve_binning(bin_chunk, R);
 
   if (R > 0) {
-    GSR_STAGE(GSR_STAGE_DUPLICATE, launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream), "duplicate_with_keys", debug,
-              stream);
+    GSR_STAGE(GSR_STAGE_DUPLICATE, launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream),
+              "duplicate_with_keys", debug, stream);
     const int bit = (int)higher_msb((uint32_t)tiles);
     GSR_STAGE(GSR_STAGE_SORT, run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
-    GSR_STAGE(GSR_STAGE_FINALIZE, launch_finalize_binning(R, bin, geom, a.colors_precomp, img.ranges, stream), "finalize_binning", debug,
-              stream);
   }
-  GSR_STAGE(GSR_STAGE_FINALIZE, launch_order_tiles(tiles, img.ranges, img.tile_order, stream), "order_tiles", debug, stream);
+  {
+    StageScope scope(GSR_STAGE_FINALIZE, stream);
+    GSR_CUDA(launch_finalize_binning(R, bin, geom, a.colors_precomp, img.ranges, stream), "finalize_binning");
+    GSR_CUDA(launch_order_tiles(tiles, img.ranges, img.tile_order, img.tile_last, stream), "order_tiles");
+  }
+  if (debug) GSR_CUDA(cudaStreamSynchronize(stream), "finalize_binning");
   GSR_STAGE(GSR_STAGE_BLEND_FWD, launch_blend_fwd(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream),
             "blend_fwd", debug, stream);
   *num_rendered = R;

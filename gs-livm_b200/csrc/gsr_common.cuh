@@ -87,7 +87,8 @@ cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* rad
 cudaError_t run_sort(const BinningState& b, int R, int end_bit, cudaStream_t s);
 cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomState& g, const float* colors_precomp,
                                     uint2* ranges, cudaStream_t s);
-cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, cudaStream_t s);
+cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, uint32_t* tile_last,
+                               cudaStream_t s);
 cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,
                              const float* background, float* out_color, float* out_depth, float* out_acc,
                              cudaStream_t s);

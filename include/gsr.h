@@ -157,6 +157,9 @@ typedef struct gsr_image_view {
 } gsr_image_view;
 
 GSR_API int gsr_abi_version(void);
+/* sizeof of an ABI struct as this library was compiled: 0 gsr_fwd_args, 1 gsr_bwd_args, 2 gsr_array_view,
+ * 3 gsr_geom_view, 4 gsr_binning_view, 5 gsr_image_view; 0 for an unknown index. Lets FFI bindings check layout. */
+GSR_API size_t gsr_sizeof(int which);
 GSR_API const char* gsr_last_error(void);
 
 GSR_API size_t gsr_required_geom(int P);

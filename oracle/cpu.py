@@ -143,14 +143,16 @@ def backward(sc: OracleScene, fwd: Dict[str, np.ndarray], dL_dpix, dL_dacc, nthr
              dL_dsh=np.zeros((P, max(M, 1), 3)), dL_dscale=np.zeros((P, 3)), dL_drot=np.zeros((P, 4)))
     feats = sc.colors_precomp if sc.colors_precomp is not None else fwd["rgb"]
     pl = fwd["point_list"] if fwd["num_rendered"] > 0 else np.zeros(1, np.uint32)
+    counters = np.zeros(3, np.uint64)
     lib.gsro_blend_bwd(W, H, _p(fwd["ranges"]), _p(pl), _p(fwd["means2D"]), _p(fwd["conic_opacity"]), _p(feats),
                        _p(sc.bg), _p(fwd["final_T"]), _p(fwd["n_contrib"]), _p(dpix), _p(dacc), _p(g["dL_dmean2D"]),
-                       _p(g["dL_dconic"]), _p(g["dL_dopacity"]), _p(g["dL_dcolor"]), int(nthreads))
+                       _p(g["dL_dconic"]), _p(g["dL_dopacity"]), _p(g["dL_dcolor"]), _p(counters), int(nthreads))
     inp = sc.c_inputs()
     lib.gsro_geom_bwd(C.byref(inp), _p(fwd["radii"]), _p(fwd["cov3D"]), _p(fwd["clamped"]), _p(g["dL_dmean2D"]),
                       _p(g["dL_dconic"]), _p(g["dL_dcolor"]), _p(g["dL_dmean3D"]), _p(g["dL_dcov3D"]), _p(g["dL_dsh"]),
                       _p(g["dL_dscale"]), _p(g["dL_drot"]))
     g["dL_dsh"] = g["dL_dsh"][:, :M, :]
+    g["bwd_counters"] = counters
     return g
 
 

@@ -406,10 +406,10 @@ typedef struct {
   const uint32_t* n_contrib;
   const float *dL_dpix, *dL_dacc;
   double *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor;
+  uint64_t (*cnt)[8]; /* per worker: X' (visited), X'_p (power <= 0), X_b (blended) */
 } bwd_ctx;
 
 static void blend_bwd_tile(int tile, void* vctx, int worker) {
-  (void)worker;
   bwd_ctx* cx = (bwd_ctx*)vctx;
   const int W = cx->W, H = cx->H, gx = cx->gx;
   const uint32_t *ranges = cx->ranges, *point_list = cx->point_list, *n_contrib = cx->n_contrib;
@@ -437,13 +437,16 @@ static void blend_bwd_tile(int tile, void* vctx, int worker) {
         double accum_rec[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, accum_acc = 0, last_acc = 0, last_alpha = 0;
         for (uint32_t k = r0 + last_contributor; k-- > r0;) { /* back to front; backward.cu:526-601 */
           const uint32_t id = point_list[k];
+          cx->cnt[worker][0]++;
           const float dxf = means2D[2 * (size_t)id] - pxf, dyf = means2D[2 * (size_t)id + 1] - pyf;
           const float* co = conic_opacity + 4 * (size_t)id;
           const float power = fmaf(fmaf(dxf, dxf * co[0], dyf * (dyf * co[2])), -0.5f, -(dyf * (dxf * co[1])));
           if (power > 0.0f) continue;
+          cx->cnt[worker][1]++;
           const float Gf = expf(power);
           const float alphaf = fminf(0.99f, co[3] * Gf);
           if (alphaf < 1.0f / 255.0f) continue;
+          cx->cnt[worker][2]++;
           const double G = Gf, alpha = alphaf, dx = dxf, dy = dyf;
           T = T / (1.0 - alpha);
           const double dchannel_dcolor = alpha * T;
@@ -478,11 +481,18 @@ static void blend_bwd_tile(int tile, void* vctx, int worker) {
 int gsro_blend_bwd(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
                    const float* conic_opacity, const float* features, const float* bg, const float* final_T,
                    const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dacc, double* dL_dmean2D,
-                   double* dL_dconic, double* dL_dopacity, double* dL_dcolor, int nthreads) {
+                   double* dL_dconic, double* dL_dopacity, double* dL_dcolor, uint64_t counters[3], int nthreads) {
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  static uint64_t cnt[GSRO_MAX_THREADS][8];
+  memset(cnt, 0, sizeof(cnt));
   bwd_ctx c = {W, H, gx, ranges, point_list, means2D, conic_opacity, features, bg, final_T, n_contrib,
-               dL_dpix, dL_dacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor};
+               dL_dpix, dL_dacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, cnt};
   parallel_tiles(gx * gy, nthreads, blend_bwd_tile, &c);
+  if (counters) {
+    for (int k = 0; k < 3; ++k) counters[k] = 0;
+    for (int w = 0; w < GSRO_MAX_THREADS; ++w)
+      for (int k = 0; k < 3; ++k) counters[k] += cnt[w][k];
+  }
   return 0;
 }
 

@@ -62,11 +62,12 @@ int gsro_blend_fwd(int W, int H, const uint32_t* ranges, const uint32_t* point_l
 
 /* renderCUDA backward, src/cuda_rasterizer/backward.cu:438-603: decisions in float exactly like the
  * forward, gradient arithmetic and accumulation in double (order-independent reference value for the
- * atomics). No depth gradient (backward.cu:567-571). */
+ * atomics). No depth gradient (backward.cu:567-571).
+ * counters = {X' pairs visited (contributor < n_contrib), X'_p with power <= 0, X_b blended}. */
 int gsro_blend_bwd(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
                    const float* conic_opacity, const float* features, const float* bg, const float* final_T,
                    const uint32_t* n_contrib, const float* dL_dpix, const float* dL_dacc, double* dL_dmean2D,
-                   double* dL_dconic, double* dL_dopacity, double* dL_dcolor, int nthreads);
+                   double* dL_dconic, double* dL_dopacity, double* dL_dcolor, uint64_t counters[3], int nthreads);
 
 /* computeCov2DCUDA (backward.cu:140-275) + preprocessCUDA backward (:371-435) with computeColorFromSH
  * backward (:20-135) and computeCov3D backward (:279-366); double arithmetic on the float forward state. */
