@@ -53,5 +53,6 @@ std::vector<torch::Tensor> render_and_backward(torch::Tensor means3D, torch::Ten
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "GS-LIVM's unchanged operator files linked against libgsr_b200.so (test infrastructure)";
-  m.def("render_and_backward", &render_and_backward);
+  // the LibTorch autograd engine must not be entered with the Python GIL held
+  m.def("render_and_backward", &render_and_backward, pybind11::call_guard<pybind11::gil_scoped_release>());
 }
