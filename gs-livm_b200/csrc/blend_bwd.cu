@@ -6,16 +6,22 @@
 // silhouette channel and rasterizer.cu:77-80 drops grad_out_depth).
 //
 // Design ("blend_bwd"):
-//  * same structure as blend_fwd, traversed in reverse: 8 fully independent warps per tile, each with a
-//    private TMA-fed ring (records + Gaussian ids) and private mbarriers, sub-tile ballot culling with
-//    survivor compaction; everything behind the warp's own last contributor (max n_contrib of its 32
-//    pixels) is never fetched; survivors are processed two at a time so that the exp / alpha of the
-//    second overlaps the recurrence and warp reduction of the first;
-//  * the reference issues 9 float atomics per blended (pixel, Gaussian) pair, all lanes of a warp
-//    hitting the same 9 addresses. Here the warp walks the same Gaussian in lock-step, the 9 partial
-//    sums are reduced across the 32 lanes with a transposing butterfly (14 shuffles for 9 values
-//    instead of 45) and leave through ONE predicated RED.ADD.F32 instruction in which 9 lanes each own
-//    a distinct address: 32x fewer L2 atomics and no same-address serialisation.
+//  * same structure as blend_fwd, traversed in reverse: every warp is independent, owns a small block of
+//    pixels of one tile and a private TMA-fed ring (records + Gaussian ids) with private mbarriers;
+//    sub-block ballot culling with survivor compaction; everything behind the warp's own last
+//    contributor (max n_contrib of its pixels) is never fetched;
+//  * the reference issues 9 float atomics per blended (pixel, Gaussian) pair, all lanes of a warp hitting
+//    the same 9 addresses. Here the lanes walk the same Gaussian in lock-step, the 9 partial sums are
+//    reduced across lanes with a transposing butterfly and leave through predicated RED.ADD.F32
+//    instructions in which every participating lane owns a distinct address;
+//  * two shapes of warp, as in blend_fwd. COARSE (short lists): 32 pixels (8x4) per warp, survivors two
+//    at a time, one 14-shuffle butterfly per survivor. FINE (lists >= kHeavy): 8 pixels (4x2) per warp,
+//    four lanes per pixel: the four lanes evaluate exp/alpha of four different survivors in parallel,
+//    all replay the cheap ordered recurrence, and each 8-lane group keeps the gradient terms of ONE of
+//    four consecutive survivors, so a single 10-shuffle butterfly (xor 4,2,1 stays inside a group)
+//    reduces four survivors at once and one RED instruction commits 32 sums. This removes the frame's
+//    longest serial chains (one warp walking ~2 400 survivors) and costs fewer instructions per
+//    survivor than the coarse shape.
 //  Summation order differs from the reference (as it does between two runs of the reference itself),
 //  so gradients are compared at 1e-4 relative, not bitwise.
 #include "gsr_common.cuh"
@@ -25,40 +31,10 @@ namespace {
 
 constexpr int kStages = 3;
 constexpr int kWarps = 8;
-constexpr int kWB = 64;  // instances per per-warp batch
-constexpr int kIlp = 2;
+constexpr int kWB = 64;       // instances per per-warp batch
+constexpr int kHeavy = 512;   // tiles with at least this many instances use the FINE shape
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kIdPad = 4;  // ids are bulk-copied from a 16-byte aligned-down start
-
-// Sum 8 per-lane values across the warp; afterwards every lane holds the total of value (lane >> 2) & 7.
-__device__ __forceinline__ float transpose_reduce8(const float v[8], int lane) {
-  float w[4], u[2];
-  bool up = lane & 16;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = up ? v[i] : v[i + 4];
-    const float keep = up ? v[i + 4] : v[i];
-    w[i] = keep + __shfl_xor_sync(kFull, send, 16);
-  }
-  up = lane & 8;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = up ? w[i] : w[i + 2];
-    const float keep = up ? w[i + 2] : w[i];
-    u[i] = keep + __shfl_xor_sync(kFull, send, 8);
-  }
-  up = lane & 4;
-  float t = (up ? u[1] : u[0]) + __shfl_xor_sync(kFull, up ? u[0] : u[1], 4);
-  t += __shfl_xor_sync(kFull, t, 2);
-  t += __shfl_xor_sync(kFull, t, 1);
-  return t;
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
+constexpr int kIdPad = 4;     // ids are bulk-copied from a 16-byte aligned-down start
 
 struct __align__(128) WarpRing {
   float4 rec[kStages][kWB * 3];
@@ -67,58 +43,140 @@ struct __align__(128) WarpRing {
   uint32_t list[kWB / 4];  // compacted survivor indices (descending), one byte each
 };
 
-__global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const SplatRecord* __restrict__ inst,
-    const uint32_t* __restrict__ point_list, int W, int H, int grid_x, const float* __restrict__ bg,
-    const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-    const float* __restrict__ dL_dpix, const float* __restrict__ dL_dacc, float* __restrict__ dL_dmean2D,
-    float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpRing& ring = reinterpret_cast<WarpRing*>(smem_raw)[warp];
+struct BwdArgs {
+  const uint2* ranges;
+  const uint32_t* tile_order;
+  const SplatRecord* inst;
+  const uint32_t* point_list;
+  int W, H, grid_x, tiles;
+  const float* bg;
+  const float* final_T;
+  const uint32_t* n_contrib;
+  const float *dL_dpix, *dL_dacc;
+  float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor;
+};
 
-  const int tile = (int)tile_order[blockIdx.x];
-  const uint2 range = ranges[tile];
+// Sum 8 per-lane values across 32 lanes; afterwards every lane holds the total of value (lane >> 2) & 7.
+__device__ __forceinline__ float transpose_reduce8_warp(const float v[8], int lane) {
+  float w[4], u[2];
+  bool up = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = (up ? v[i + 4] : v[i]) + __shfl_xor_sync(kFull, up ? v[i] : v[i + 4], 16);
+  up = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) u[i] = (up ? w[i + 2] : w[i]) + __shfl_xor_sync(kFull, up ? w[i] : w[i + 2], 8);
+  up = lane & 4;
+  float t = (up ? u[1] : u[0]) + __shfl_xor_sync(kFull, up ? u[0] : u[1], 4);
+  t += __shfl_xor_sync(kFull, t, 2);
+  t += __shfl_xor_sync(kFull, t, 1);
+  return t;
+}
+
+// Sum 8 per-lane values across each aligned group of 8 lanes; lane l ends with the total of value l & 7.
+__device__ __forceinline__ float transpose_reduce8_oct(const float v[8], int lane) {
+  float w[4], u[2];
+  bool up = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = (up ? v[i + 4] : v[i]) + __shfl_xor_sync(kFull, up ? v[i] : v[i + 4], 4);
+  up = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) u[i] = (up ? w[i + 2] : w[i]) + __shfl_xor_sync(kFull, up ? w[i] : w[i + 2], 2);
+  up = lane & 1;
+  return (up ? u[1] : u[0]) + __shfl_xor_sync(kFull, up ? u[0] : u[1], 1);
+}
+
+// pointer / stride of gradient word v (0..2 colour, 3..4 mean2D.xy, 5..7 conic.x,.y,.w)
+__device__ __forceinline__ void grad_slot(const BwdArgs& a, int v, float*& ptr, int& stride) {
+  if (v < 3) ptr = a.dL_dcolor + v, stride = 3;
+  else if (v < 5) ptr = a.dL_dmean2D + (v - 3), stride = 3;
+  else ptr = a.dL_dconic + (v == 7 ? 3 : v - 5), stride = 4;
+}
+
+// Per-pixel state of the reverse traversal (reference backward.cu:480-501).
+struct PixelState {
+  float T, T_final, acc0, acc1, acc2, acc_s, lc0, lc1, lc2, last_s, last_alpha;
+  float dpx0, dpx1, dpx2, dacc, bg_dot;
+};
+
+// One blended (pixel, Gaussian) pair: advance the recurrence and emit the 9 gradient terms
+// (reference backward.cu:546-600). q1 = {conic, opacity}, q2 = {rgb, depth}.
+__device__ __forceinline__ void pair_backward(PixelState& s, float alpha, float G, float dx, float dy,
+                                              const float4& q1, const float4& q2, float ddelx_dx, float ddely_dy,
+                                              float g[8], float& g_op) {
+  const float one_m_alpha = 1.f - alpha;
+  s.T = s.T / one_m_alpha;
+  const float dchannel_dcolor = alpha * s.T;
+  const float keep = 1.f - s.last_alpha;
+  s.acc0 = s.last_alpha * s.lc0 + keep * s.acc0;
+  s.acc1 = s.last_alpha * s.lc1 + keep * s.acc1;
+  s.acc2 = s.last_alpha * s.lc2 + keep * s.acc2;
+  s.acc_s = s.last_alpha * s.last_s + keep * s.acc_s;
+  s.lc0 = q2.x, s.lc1 = q2.y, s.lc2 = q2.z, s.last_s = 1.0f;
+  float dL_dalpha = (q2.x - s.acc0) * s.dpx0 + (q2.y - s.acc1) * s.dpx1 + (q2.z - s.acc2) * s.dpx2;
+  dL_dalpha += (1.0f - s.acc_s) * s.dacc;
+  dL_dalpha *= s.T;
+  s.last_alpha = alpha;
+  dL_dalpha += (-s.T_final / one_m_alpha) * s.bg_dot;
+  const float dL_dG = q1.w * dL_dalpha;
+  const float gdx = G * dx, gdy = G * dy;
+  const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
+  const float dG_ddely = -gdy * q1.z - gdx * q1.y;
+  g[0] = dchannel_dcolor * s.dpx0;
+  g[1] = dchannel_dcolor * s.dpx1;
+  g[2] = dchannel_dcolor * s.dpx2;
+  g[3] = dL_dG * dG_ddelx * ddelx_dx;
+  g[4] = dL_dG * dG_ddely * ddely_dy;
+  g[5] = -0.5f * gdx * dx * dL_dG;
+  g[6] = -0.5f * gdx * dy * dL_dG;
+  g[7] = -0.5f * gdy * dy * dL_dG;
+  g_op = G * dL_dalpha;
+}
+
+template <int SLOTS>
+__device__ __forceinline__ void blend_bwd_warp(const BwdArgs& a, WarpRing& ring, int tile, int block_in_tile,
+                                               int lane) {
+  constexpr int PIX = 32 / SLOTS;
+  constexpr int BW = SLOTS == 1 ? 8 : 4, BH = PIX / BW;
+  constexpr int ILP = 2;              // exp/alpha evaluations per lane per step
+  constexpr int GROUP = ILP * SLOTS;  // survivors per step: 2 (coarse) or 8 (fine)
+
+  const uint2 range = a.ranges[tile];
   const int total = (int)(range.y - range.x);
-
-  const int tile_x = tile % grid_x, tile_y = tile / grid_x;
-  const int wx = tile_x * kTile + (warp & 1) * 8, wy = tile_y * kTile + (warp >> 1) * 4;
-  const int px = wx + (lane & 7), py = wy + (lane >> 3);
-  const bool inside = px < W && py < H;
+  const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+  const int wx = tile_x * kTile + (block_in_tile % (kTile / BW)) * BW;
+  const int wy = tile_y * kTile + (block_in_tile / (kTile / BW)) * BH;
+  const int pix = lane % PIX, slot = lane / PIX;
+  const int px = wx + pix % BW, py = wy + pix / BW;
+  const bool inside = px < a.W && py < a.H;
   const float pxf = (float)px, pyf = (float)py;
-  const float wx0 = (float)wx, wx1 = (float)(wx + 7), wy0 = (float)wy, wy1 = (float)(wy + 3);
+  const float wx0 = (float)wx, wx1 = (float)(wx + BW - 1), wy0 = (float)wy, wy1 = (float)(wy + BH - 1);
 
-  const size_t pix = (size_t)W * py + px;
-  const size_t plane = (size_t)W * H;
-  const uint32_t last_contributor = inside ? n_contrib[pix] : 0u;
+  const size_t p = (size_t)a.W * py + px;
+  const size_t plane = (size_t)a.W * a.H;
+  const uint32_t last_contributor = inside ? a.n_contrib[p] : 0u;
   const uint32_t warp_last = __reduce_max_sync(kFull, last_contributor);
-  if (warp_last == 0) return;  // nothing was blended into this warp's 32 pixels
+  if (warp_last == 0) return;  // nothing was blended into this warp's pixels
 
-  const float T_final = inside ? final_T[pix] : 0.f;
-  float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f, dacc = 0.f;
+  PixelState st;
+  st.T_final = inside ? a.final_T[p] : 0.f;
+  st.T = st.T_final;
+  st.acc0 = st.acc1 = st.acc2 = st.acc_s = st.lc0 = st.lc1 = st.lc2 = st.last_s = st.last_alpha = 0.f;
+  st.dpx0 = st.dpx1 = st.dpx2 = st.dacc = 0.f;
   if (inside) {
-    dpx0 = dL_dpix[pix], dpx1 = dL_dpix[plane + pix], dpx2 = dL_dpix[2 * plane + pix];
-    dacc = dL_dacc[pix];
+    st.dpx0 = a.dL_dpix[p], st.dpx1 = a.dL_dpix[plane + p], st.dpx2 = a.dL_dpix[2 * plane + p];
+    st.dacc = a.dL_dacc[p];
   }
-  const float bg_dot = __ldg(bg) * dpx0 + __ldg(bg + 1) * dpx1 + __ldg(bg + 2) * dpx2;
+  st.bg_dot = __ldg(a.bg) * st.dpx0 + __ldg(a.bg + 1) * st.dpx1 + __ldg(a.bg + 2) * st.dpx2;
+  const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
-  float T = T_final;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_s = 0.f;  // accum_rec, accum_acc_rec
-  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_s = 0.f, last_alpha = 0.f;
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-
-  // which of the 9 gradient words this lane commits after the warp reduction
+  // which gradient word this lane commits after a reduction
   float* gptr = nullptr;
   int gstride = 0;
-  {
-    const int v = lane >> 2;
-    if ((lane & 3) == 0) {
-      if (v < 3) gptr = dL_dcolor + v, gstride = 3;
-      else if (v < 5) gptr = dL_dmean2D + (v - 3), gstride = 3;
-      else gptr = dL_dconic + (v == 7 ? 3 : v - 5), gstride = 4;
-    } else if (lane == 1) {
-      gptr = dL_dopacity, gstride = 1;
-    }
+  if (SLOTS == 1) {
+    if ((lane & 3) == 0) grad_slot(a, lane >> 2, gptr, gstride);
+    else if (lane == 1) gptr = a.dL_dopacity, gstride = 1;
+  } else {
+    grad_slot(a, pix, gptr, gstride);  // lane (slot, pix) commits word `pix` of the survivor its group kept
   }
 
   // batches first_batch, first_batch-1, ..., 0; iteration `it` uses ring stage it % kStages
@@ -131,8 +189,8 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(
     const size_t a0 = start & ~(size_t)3;  // bulk copies need 16-byte aligned global addresses
     const uint32_t id_bytes = (uint32_t)((((start - a0) + cnt) * 4 + 15) & ~(size_t)15);
     mbar_expect_tx(&ring.full[stage], rec_bytes + id_bytes);
-    bulk_g2s(ring.rec[stage], inst + start, rec_bytes, &ring.full[stage]);
-    bulk_g2s(ring.id[stage], point_list + a0, id_bytes, &ring.full[stage]);
+    bulk_g2s(ring.rec[stage], a.inst + start, rec_bytes, &ring.full[stage]);
+    bulk_g2s(ring.id[stage], a.point_list + a0, id_bytes, &ring.full[stage]);
   };
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&ring.full[s], 1);
@@ -166,67 +224,89 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(
     }
     __syncwarp();
 
-    for (int g = 0; g < nhit; g += kIlp) {
-      // kIlp survivors per step (back to front): G / alpha of all are independent of the recurrence
-      const uint32_t packed = ring.list[g >> 2] >> (8 * (g & 3));
-      int jj[kIlp];
-      float G[kIlp], alpha[kIlp], dxs[kIlp], dys[kIlp];
+    for (int g = 0; g < nhit; g += GROUP) {
+      // ---- exp / alpha of this lane's ILP survivors (independent of the recurrence) ----
+      float G_mine[ILP], a_mine[ILP];
 #pragma unroll
-      for (int u = 0; u < kIlp; ++u) {
-        const bool valid = g + u < nhit;
-        jj[u] = valid ? (int)((packed >> (8 * u)) & 0xffu) : (int)(packed & 0xffu);
-        const float4 q0 = s[3 * jj[u]];
-        const float4 q1 = s[3 * jj[u] + 1];
+      for (int u = 0; u < ILP; ++u) {
+        const int h = g + u * SLOTS + slot;
+        const bool valid = h < nhit;
+        const int jj = (int)list8[valid ? h : g];
+        const float4 q0 = s[3 * jj];
+        const float4 q1 = s[3 * jj + 1];
         const float dx = q0.x - pxf, dy = q0.y - pyf;
         const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, q1.x), __fmul_rn(dy, __fmul_rn(dy, q1.z))), -0.5f,
                                       -__fmul_rn(dy, __fmul_rn(dx, q1.y)));
         const float gg = expf(power);
-        const float a = fminf(0.99f, __fmul_rn(q1.w, gg));
-        const bool on = valid && (batch_base + (uint32_t)jj[u] < last_contributor) && !(power > 0.0f) &&
-                        !(a < 1.0f / 255.0f);
-        G[u] = gg, alpha[u] = on ? a : -1.0f, dxs[u] = dx, dys[u] = dy;
+        const float al = fminf(0.99f, __fmul_rn(q1.w, gg));
+        const bool on = valid && (batch_base + (uint32_t)jj < last_contributor) && !(power > 0.0f) &&
+                        !(al < 1.0f / 255.0f);
+        G_mine[u] = gg, a_mine[u] = on ? al : -1.0f;
       }
+
+      if (SLOTS == 1) {
+        // ---- COARSE: one 32-lane butterfly per survivor ----
 #pragma unroll
-      for (int u = 0; u < kIlp; ++u) {
-        const bool active = alpha[u] >= 0.0f;
-        if (!__any_sync(kFull, active)) continue;
-        float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        float g_op = 0.f;
-        if (active) {
-          const float4 q1 = s[3 * jj[u] + 1];
-          const float4 q2 = s[3 * jj[u] + 2];
-          const float a = alpha[u], dx = dxs[u], dy = dys[u];
-          const float one_m_alpha = 1.f - a;
-          T = T / one_m_alpha;
-          const float dchannel_dcolor = a * T;
-          const float keep = 1.f - last_alpha;
-          acc0 = last_alpha * lc0 + keep * acc0;
-          acc1 = last_alpha * lc1 + keep * acc1;
-          acc2 = last_alpha * lc2 + keep * acc2;
-          acc_s = last_alpha * last_s + keep * acc_s;
-          lc0 = q2.x, lc1 = q2.y, lc2 = q2.z, last_s = 1.0f;
-          float dL_dalpha = (q2.x - acc0) * dpx0 + (q2.y - acc1) * dpx1 + (q2.z - acc2) * dpx2;
-          dL_dalpha += (1.0f - acc_s) * dacc;
-          dL_dalpha *= T;
-          last_alpha = a;
-          dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
-          const float dL_dG = q1.w * dL_dalpha;
-          const float gdx = G[u] * dx, gdy = G[u] * dy;
-          const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
-          const float dG_ddely = -gdy * q1.z - gdx * q1.y;
-          gr[0] = dchannel_dcolor * dpx0;
-          gr[1] = dchannel_dcolor * dpx1;
-          gr[2] = dchannel_dcolor * dpx2;
-          gr[3] = dL_dG * dG_ddelx * ddelx_dx;
-          gr[4] = dL_dG * dG_ddely * ddely_dy;
-          gr[5] = -0.5f * gdx * dx * dL_dG;
-          gr[6] = -0.5f * gdx * dy * dL_dG;
-          gr[7] = -0.5f * gdy * dy * dL_dG;
-          g_op = G[u] * dL_dalpha;
+        for (int t = 0; t < GROUP; ++t) {
+          const float al = a_mine[t];
+          const bool active = al >= 0.0f;
+          if (!__any_sync(kFull, active)) continue;
+          const int jj = (int)list8[min(g + t, nhit - 1)];
+          float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float g_op = 0.f;
+          if (active) {
+            const float4 q0 = s[3 * jj];
+            pair_backward(st, al, G_mine[t], q0.x - pxf, q0.y - pyf, s[3 * jj + 1], s[3 * jj + 2], ddelx_dx, ddely_dy,
+                          gr, g_op);
+          }
+          const float tsum = transpose_reduce8_warp(gr, lane);
+          float o = g_op;
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) o += __shfl_xor_sync(kFull, o, sh);
+          if (gptr) atomicAdd(gptr + (size_t)ids[jj] * gstride, lane == 1 ? o : tsum);
         }
-        const float t = transpose_reduce8(gr, lane);
-        const float o = warp_sum(g_op);
-        if (gptr) atomicAdd(gptr + (size_t)ids[jj[u]] * gstride, lane == 1 ? o : t);
+      } else {
+        // ---- FINE: all lanes replay the recurrence; each 8-lane group keeps one of 4 consecutive survivors ----
+#pragma unroll
+        for (int half = 0; half < GROUP / SLOTS; ++half) {
+          float keep_g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float keep_op = 0.f;
+          uint32_t any_bits = 0;
+#pragma unroll
+          for (int q = 0; q < SLOTS; ++q) {
+            const int t = half * SLOTS + q;
+            const float al = __shfl_sync(kFull, a_mine[half], q * PIX + pix);
+            const float gg = __shfl_sync(kFull, G_mine[half], q * PIX + pix);
+            const bool active = al >= 0.0f;
+            if (!__any_sync(kFull, active)) continue;
+            any_bits |= 1u << q;
+            const int jj = (int)list8[min(g + t, nhit - 1)];
+            float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float g_op = 0.f;
+            if (active) {
+              const float4 q0 = s[3 * jj];
+              pair_backward(st, al, gg, q0.x - pxf, q0.y - pyf, s[3 * jj + 1], s[3 * jj + 2], ddelx_dx, ddely_dy, gr,
+                            g_op);
+            }
+            if (slot == q) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) keep_g[k] = gr[k];
+              keep_op = g_op;
+            }
+          }
+          if (any_bits == 0) continue;
+          const float tsum = transpose_reduce8_oct(keep_g, lane);
+          float o = keep_op;
+          o += __shfl_xor_sync(kFull, o, 4);
+          o += __shfl_xor_sync(kFull, o, 2);
+          o += __shfl_xor_sync(kFull, o, 1);
+          if ((any_bits >> slot) & 1u) {
+            const int jj = (int)list8[min(g + half * SLOTS + slot, nhit - 1)];
+            const size_t id = ids[jj];
+            atomicAdd(gptr + id * gstride, tsum);
+            if (pix == 0) atomicAdd(a.dL_dopacity + id, o);
+          }
+        }
       }
     }
     __syncwarp();  // all lanes are done with this stage before it is refilled
@@ -234,6 +314,25 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(b - kStages, it + kStages);
     }
+  }
+}
+
+// grid = 4*tiles FINE candidates (tile_order[b/4], quarter b%4) followed by tiles COARSE candidates.
+__global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(const BwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpRing& ring = reinterpret_cast<WarpRing*>(smem_raw)[warp];
+  const int b = (int)blockIdx.x;
+  if (b < 4 * a.tiles) {
+    const int tile = (int)a.tile_order[b >> 2];
+    const uint2 r = a.ranges[tile];
+    if ((int)(r.y - r.x) < kHeavy) return;
+    blend_bwd_warp<4>(a, ring, tile, (b & 3) * kWarps + warp, lane);
+  } else {
+    const int tile = (int)a.tile_order[b - 4 * a.tiles];
+    const uint2 r = a.ranges[tile];
+    if ((int)(r.y - r.x) >= kHeavy) return;
+    blend_bwd_warp<1>(a, ring, tile, warp, lane);
   }
 }
 
@@ -252,9 +351,13 @@ cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  blend_bwd_kernel<<<grid_x * grid_y, kWarps * 32, kSmem, s>>>(
-      img.ranges, img.tile_order, b.inst, b.vals, width, height, grid_x, background, img.final_T, img.n_contrib,
-      dL_dpix, dL_dacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+  BwdArgs a;
+  a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
+  a.W = width, a.H = height, a.grid_x = grid_x, a.tiles = grid_x * grid_y;
+  a.bg = background, a.final_T = img.final_T, a.n_contrib = img.n_contrib;
+  a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;
+  a.dL_dmean2D = dL_dmean2D, a.dL_dconic = dL_dconic, a.dL_dopacity = dL_dopacity, a.dL_dcolor = dL_dcolor;
+  blend_bwd_kernel<<<5 * a.tiles, kWarps * 32, kSmem, s>>>(a);
   return cudaGetLastError();
 }
 
