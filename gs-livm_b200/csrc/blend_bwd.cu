@@ -17,13 +17,16 @@
 //  * two shapes of warp, as in blend_fwd. COARSE (short lists): 32 pixels (8x4) per warp, survivors two
 //    at a time, one 14-shuffle butterfly per survivor. FINE (lists >= kHeavy): 8 pixels (4x2) per warp,
 //    four lanes per pixel: the four lanes evaluate exp/alpha of four different survivors in parallel,
-//    all replay the cheap ordered recurrence, and each 8-lane group keeps the gradient terms of ONE of
-//    four consecutive survivors, so a single 10-shuffle butterfly (xor 4,2,1 stays inside a group)
-//    reduces four survivors at once and one RED instruction commits 32 sums. This removes the frame's
-//    longest serial chains (one warp walking ~2 400 survivors) and costs fewer instructions per
-//    survivor than the coarse shape.
+//    all replay the cheap ordered recurrence (T, accumulated colour) and snapshot the state in front of
+//    their own survivor, then each 8-lane group computes the gradient terms of ONE of four consecutive
+//    survivors, so the expensive part runs 4-wide and a single 10-shuffle butterfly (xor 4,2,1 stays
+//    inside a group) reduces four survivors at once; one RED instruction commits 32 sums. This removes
+//    the frame's longest serial chains (one warp walking ~2 400 survivors) and costs fewer
+//    instructions per survivor than the coarse shape.
 //  Summation order differs from the reference (as it does between two runs of the reference itself),
 //  so gradients are compared at 1e-4 relative, not bitwise.
+#include <cstdlib>
+
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -32,7 +35,8 @@ namespace {
 constexpr int kStages = 3;
 constexpr int kWarps = 8;
 constexpr int kWB = 64;       // instances per per-warp batch
-constexpr int kHeavy = 512;   // tiles with at least this many instances use the FINE shape
+constexpr int kHeavy = 3072;   // tiles with at least this many instances use the FINE shape
+constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kIdPad = 4;     // ids are bulk-copied from a 16-byte aligned-down start
 
@@ -48,7 +52,7 @@ struct BwdArgs {
   const uint32_t* tile_order;
   const SplatRecord* inst;
   const uint32_t* point_list;
-  int W, H, grid_x, tiles;
+  int W, H, grid_x, tiles, heavy, fine_tiles;
   const float* bg;
   const float* final_T;
   const uint32_t* n_contrib;
@@ -266,43 +270,68 @@ __device__ __forceinline__ void blend_bwd_warp(const BwdArgs& a, WarpRing& ring,
           if (gptr) atomicAdd(gptr + (size_t)ids[jj] * gstride, lane == 1 ? o : tsum);
         }
       } else {
-        // ---- FINE: all lanes replay the recurrence; each 8-lane group keeps one of 4 consecutive survivors ----
+        // ---- FINE: every lane replays the cheap ordered recurrence of 4 consecutive survivors and snapshots the
+        // state in front of ITS survivor (the one its 8-lane group evaluated above); the expensive gradient
+        // terms are then computed once, for four survivors in parallel, and reduced by one butterfly ----
 #pragma unroll
         for (int half = 0; half < GROUP / SLOTS; ++half) {
-          float keep_g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          float keep_op = 0.f;
+          const int h_mine = g + half * SLOTS + slot;
+          const int jj_mine = (int)list8[min(h_mine, nhit - 1)];
+          float snap_T = 0.f, snap_a0 = 0.f, snap_a1 = 0.f, snap_a2 = 0.f, snap_as = 0.f;
           uint32_t any_bits = 0;
 #pragma unroll
           for (int q = 0; q < SLOTS; ++q) {
-            const int t = half * SLOTS + q;
             const float al = __shfl_sync(kFull, a_mine[half], q * PIX + pix);
-            const float gg = __shfl_sync(kFull, G_mine[half], q * PIX + pix);
             const bool active = al >= 0.0f;
             if (!__any_sync(kFull, active)) continue;
             any_bits |= 1u << q;
-            const int jj = (int)list8[min(g + t, nhit - 1)];
-            float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float g_op = 0.f;
             if (active) {
-              const float4 q0 = s[3 * jj];
-              pair_backward(st, al, gg, q0.x - pxf, q0.y - pyf, s[3 * jj + 1], s[3 * jj + 2], ddelx_dx, ddely_dy, gr,
-                            g_op);
-            }
-            if (slot == q) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) keep_g[k] = gr[k];
-              keep_op = g_op;
+              const int jj = (int)list8[min(g + half * SLOTS + q, nhit - 1)];
+              const float4 q2 = s[3 * jj + 2];
+              st.T = st.T / (1.f - al);
+              const float keep = 1.f - st.last_alpha;
+              st.acc0 = st.last_alpha * st.lc0 + keep * st.acc0;
+              st.acc1 = st.last_alpha * st.lc1 + keep * st.acc1;
+              st.acc2 = st.last_alpha * st.lc2 + keep * st.acc2;
+              st.acc_s = st.last_alpha * st.last_s + keep * st.acc_s;
+              st.lc0 = q2.x, st.lc1 = q2.y, st.lc2 = q2.z, st.last_s = 1.0f;
+              st.last_alpha = al;
+              if (slot == q) snap_T = st.T, snap_a0 = st.acc0, snap_a1 = st.acc1, snap_a2 = st.acc2, snap_as = st.acc_s;
             }
           }
           if (any_bits == 0) continue;
-          const float tsum = transpose_reduce8_oct(keep_g, lane);
-          float o = keep_op;
+          float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float g_op = 0.f;
+          const float al = a_mine[half];
+          if (al >= 0.0f) {  // gradient terms of this lane's own survivor (reference backward.cu:547-600)
+            const float4 q0 = s[3 * jj_mine], q1 = s[3 * jj_mine + 1], q2 = s[3 * jj_mine + 2];
+            const float dx = q0.x - pxf, dy = q0.y - pyf, G = G_mine[half];
+            const float dchannel_dcolor = al * snap_T;
+            float dL_dalpha = (q2.x - snap_a0) * st.dpx0 + (q2.y - snap_a1) * st.dpx1 + (q2.z - snap_a2) * st.dpx2;
+            dL_dalpha += (1.0f - snap_as) * st.dacc;
+            dL_dalpha *= snap_T;
+            dL_dalpha += (-st.T_final / (1.f - al)) * st.bg_dot;
+            const float dL_dG = q1.w * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
+            const float dG_ddely = -gdy * q1.z - gdx * q1.y;
+            gr[0] = dchannel_dcolor * st.dpx0;
+            gr[1] = dchannel_dcolor * st.dpx1;
+            gr[2] = dchannel_dcolor * st.dpx2;
+            gr[3] = dL_dG * dG_ddelx * ddelx_dx;
+            gr[4] = dL_dG * dG_ddely * ddely_dy;
+            gr[5] = -0.5f * gdx * dx * dL_dG;
+            gr[6] = -0.5f * gdx * dy * dL_dG;
+            gr[7] = -0.5f * gdy * dy * dL_dG;
+            g_op = G * dL_dalpha;
+          }
+          const float tsum = transpose_reduce8_oct(gr, lane);
+          float o = g_op;
           o += __shfl_xor_sync(kFull, o, 4);
           o += __shfl_xor_sync(kFull, o, 2);
           o += __shfl_xor_sync(kFull, o, 1);
           if ((any_bits >> slot) & 1u) {
-            const int jj = (int)list8[min(g + half * SLOTS + slot, nhit - 1)];
-            const size_t id = ids[jj];
+            const size_t id = ids[jj_mine];
             atomicAdd(gptr + id * gstride, tsum);
             if (pix == 0) atomicAdd(a.dL_dopacity + id, o);
           }
@@ -317,21 +346,21 @@ __device__ __forceinline__ void blend_bwd_warp(const BwdArgs& a, WarpRing& ring,
   }
 }
 
-// grid = 4*tiles FINE candidates (tile_order[b/4], quarter b%4) followed by tiles COARSE candidates.
+// grid = 4*fine_tiles FINE candidates (tile_order[b/4], quarter b%4) followed by tiles COARSE candidates.
 __global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpRing& ring = reinterpret_cast<WarpRing*>(smem_raw)[warp];
   const int b = (int)blockIdx.x;
-  if (b < 4 * a.tiles) {
+  if (b < 4 * a.fine_tiles) {
     const int tile = (int)a.tile_order[b >> 2];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) < kHeavy) return;
+    if ((int)(r.y - r.x) < a.heavy) return;
     blend_bwd_warp<4>(a, ring, tile, (b & 3) * kWarps + warp, lane);
   } else {
-    const int tile = (int)a.tile_order[b - 4 * a.tiles];
+    const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) >= kHeavy) return;
+    if ((int)(r.y - r.x) >= a.heavy) return;
     blend_bwd_warp<1>(a, ring, tile, warp, lane);
   }
 }
@@ -354,10 +383,16 @@ cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const
   BwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
   a.W = width, a.H = height, a.grid_x = grid_x, a.tiles = grid_x * grid_y;
+  static const int heavy = [] {
+    const char* e = getenv("GSR_BWD_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
+    return e ? atoi(e) : kHeavy;
+  }();
+  a.heavy = heavy;
+  a.fine_tiles = a.tiles < kFineCap ? a.tiles : kFineCap;  // only the longest kFineCap lists can be FINE
   a.bg = background, a.final_T = img.final_T, a.n_contrib = img.n_contrib;
   a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;
   a.dL_dmean2D = dL_dmean2D, a.dL_dconic = dL_dconic, a.dL_dopacity = dL_dopacity, a.dL_dcolor = dL_dcolor;
-  blend_bwd_kernel<<<5 * a.tiles, kWarps * 32, kSmem, s>>>(a);
+  blend_bwd_kernel<<<4 * a.fine_tiles + a.tiles, kWarps * 32, kSmem, s>>>(a);
   return cudaGetLastError();
 }
 

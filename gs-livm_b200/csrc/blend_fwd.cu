@@ -29,6 +29,8 @@
 // Numerics: the per-pair operation DAG (which product is fused, order of accumulation) mirrors the
 // reference's sm_100a SASS through explicit _rn intrinsics; exp is the
 // same precise expf. With identical inputs C, D, S, final_T and n_contrib come out bit-identical.
+#include <cstdlib>
+
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -37,7 +39,8 @@ namespace {
 constexpr int kStages = 3;
 constexpr int kWarps = 8;
 constexpr int kWB = 64;        // instances per per-warp batch
-constexpr int kHeavy = 1536;   // tiles with at least this many instances use the FINE shape
+constexpr int kHeavy = 4096;   // tiles with at least this many instances use the FINE shape
+constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct __align__(128) WarpRing {
@@ -50,7 +53,7 @@ struct FwdArgs {
   const uint2* ranges;
   const uint32_t* tile_order;
   const SplatRecord* inst;
-  int W, H, grid_x, tiles;
+  int W, H, grid_x, tiles, heavy, fine_tiles;
   const float* bg;
   float *out_color, *out_depth, *out_acc, *final_T;
   uint32_t *n_contrib, *tile_last;
@@ -191,22 +194,22 @@ __device__ __forceinline__ void blend_warp(const FwdArgs& a, WarpRing& ring, int
   if (lane == 0 && wmax) atomicMax(&a.tile_last[tile], wmax);  // tile_last is zeroed by order_tiles
 }
 
-// grid = 4*tiles FINE candidates (tile_order[b/4], quarter b%4) followed by tiles COARSE candidates; a CTA
+// grid = 4*fine_tiles FINE candidates (tile_order[b/4], quarter b%4) followed by tiles COARSE candidates; a CTA
 // whose tile belongs to the other shape exits at once. Heavy tiles therefore start first.
 __global__ void __launch_bounds__(kWarps * 32) blend_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpRing& ring = reinterpret_cast<WarpRing*>(smem_raw)[warp];
   const int b = (int)blockIdx.x;
-  if (b < 4 * a.tiles) {
+  if (b < 4 * a.fine_tiles) {
     const int tile = (int)a.tile_order[b >> 2];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) < kHeavy) return;
+    if ((int)(r.y - r.x) < a.heavy) return;
     blend_warp<4>(a, ring, tile, (b & 3) * kWarps + warp, lane);
   } else {
-    const int tile = (int)a.tile_order[b - 4 * a.tiles];
+    const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) >= kHeavy) return;
+    if ((int)(r.y - r.x) >= a.heavy) return;
     blend_warp<1>(a, ring, tile, warp, lane);
   }
 }
@@ -229,9 +232,15 @@ cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const
   FwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst;
   a.W = width, a.H = height, a.grid_x = grid_x, a.tiles = grid_x * grid_y;
+  static const int heavy = [] {
+    const char* e = getenv("GSR_FWD_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
+    return e ? atoi(e) : kHeavy;
+  }();
+  a.heavy = heavy;
+  a.fine_tiles = a.tiles < kFineCap ? a.tiles : kFineCap;  // only the longest kFineCap lists can be FINE
   a.bg = background, a.out_color = out_color, a.out_depth = out_depth, a.out_acc = out_acc;
   a.final_T = img.final_T, a.n_contrib = img.n_contrib, a.tile_last = img.tile_last;
-  blend_fwd_kernel<<<5 * a.tiles, kWarps * 32, kSmem, s>>>(a);
+  blend_fwd_kernel<<<4 * a.fine_tiles + a.tiles, kWarps * 32, kSmem, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -90,9 +90,16 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
   bx[15] = kC3[6] * 3.f * (xx - yy), by[15] = kC3[6] * -6.f * xy;
 }
 
+constexpr int kShRow = 13;  // float4 per staged SH row: 12 used + 1 pad -> conflict-free lane-strided LDS/STS.128
+
+// kVec16: M == 16 and shs / dL_dsh 16-byte aligned. SH rows of the block's visible Gaussians are staged into
+// shared memory with coalesced 16-byte cp.async transfers (issued first, so they overlap the covariance
+// math), and the dL_dsh rows leave the same way: written row-wise into shared memory, stored coalesced.
 template <bool kVec16>
 __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   __shared__ float s_view[16], s_proj[16], s_cam[3];
+  __shared__ uint8_t s_active[256];
+  extern __shared__ __align__(16) float4 s_sh[];  // [256][kShRow] when kVec16
   const int tid = threadIdx.x;
   if (tid < 16) {
     s_view[tid] = __ldg(a.viewmatrix + tid);
@@ -101,21 +108,38 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   } else if (tid < 35) {
     s_cam[tid - 32] = __ldg(a.cam_pos + tid - 32);
   }
+  const int base = blockIdx.x * 256;
+  const int n = min(256, a.P - base);
+  const int idx = base + tid;
+  const bool active = tid < n && a.radii[idx] > 0;
+  s_active[tid] = active;
   __syncthreads();
-  const int idx = blockIdx.x * 256 + tid;
-  if (idx >= a.P) return;
-  if (!(a.radii[idx] > 0)) return;
-
-  const float* V = s_view;
-  const float* PM = s_proj;
-  const float mx = __ldg(a.means3D + 3 * (size_t)idx), my = __ldg(a.means3D + 3 * (size_t)idx + 1),
-              mz = __ldg(a.means3D + 3 * (size_t)idx + 2);
-
-  // ---- forward recomputation: 3D covariance (same DAG as preprocess.cu) --------------------------
-  float c0, c1, c2, c3, c4, c5;
+  if (kVec16) {
+    const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
+    for (int q = tid; q < n * 12; q += 256) {
+      const int row = q / 12;
+      if (s_active[row]) {
+        const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  float gmx = 0.f, gmy = 0.f, gmz = 0.f;
+  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float sx = 0.f, sy = 0.f, sz = 0.f, qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
   float A0 = 0, A1 = 0, A2 = 0, B0 = 0, B1 = 0, B2 = 0, C0 = 0, C1 = 0, C2 = 0;  // rows of M = S*R
   float R00 = 0, R01 = 0, R02 = 0, R10 = 0, R11 = 0, R12 = 0, R20 = 0, R21 = 0, R22 = 0;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  if (active) {
+
+  const float* V = s_view;
+  const float* PM = s_proj;
+  mx = __ldg(a.means3D + 3 * (size_t)idx), my = __ldg(a.means3D + 3 * (size_t)idx + 1),
+  mz = __ldg(a.means3D + 3 * (size_t)idx + 2);
+
+  // ---- forward recomputation: 3D covariance (same DAG as preprocess.cu) --------------------------
+  float c0, c1, c2, c3, c4, c5;
   if (a.cov3D_precomp) {
     const float* cp = a.cov3D_precomp + (size_t)idx * 6;
     c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2), c3 = __ldg(cp + 3), c4 = __ldg(cp + 4), c5 = __ldg(cp + 5);
@@ -173,7 +197,6 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   const float denom = ca * cc - cb * cb;
   const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
   float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
-  float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (denom2inv != 0.f) {
     dL_da = denom2inv * (-cc * cc * dcon.x + 2.f * cb * cc * dcon.y + (denom - ca * cc) * dcon.w);
     dL_dc = denom2inv * (-ca * ca * dcon.w + 2.f * ca * cb * dcon.y + (denom - ca * cc) * dcon.x);
@@ -204,9 +227,9 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   const float dty = y_grad_mul * -a.focal_y * itz2 * dJ12;
   const float dtz = -a.focal_x * itz2 * dJ00 - a.focal_y * itz2 * dJ11 + (2.f * a.focal_x * tx) * itz3 * dJ02 +
                     (2.f * a.focal_y * ty) * itz3 * dJ12;
-  float gmx = V[0] * dtx + V[1] * dty + V[2] * dtz;
-  float gmy = V[4] * dtx + V[5] * dty + V[6] * dtz;
-  float gmz = V[8] * dtx + V[9] * dty + V[10] * dtz;
+  gmx = V[0] * dtx + V[1] * dty + V[2] * dtz;
+  gmy = V[4] * dtx + V[5] * dty + V[6] * dtz;
+  gmz = V[8] * dtx + V[9] * dty + V[10] * dtz;
 
   // ---- projection backward: dL/dmean2D -> dL/dmean3D (reference preprocessCUDA, backward.cu:399-416) ----
   {
@@ -220,8 +243,14 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
     gmz += (PM[8] * m_w - PM[11] * mul1) * d2x + (PM[9] * m_w - PM[11] * mul2) * d2y;
   }
 
+  }  // if (active): covariance + projection part
+
   // ---- SH backward (reference computeColorFromSH backward) -------------------------------------
-  if (a.shs) {
+  if (kVec16) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // every thread's part of the staged rows has landed
+  }
+  if (active && a.shs) {
     const float ox = mx - s_cam[0], oy = my - s_cam[1], oz = mz - s_cam[2];
     const float len = sqrtf(ox * ox + oy * oy + oz * oz);
     const float x = ox / len, y = oy / len, z = oz / len;
@@ -235,9 +264,8 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;  // dL/d(dir)
     if (kVec16) {
       float4 in4[12], out4[12];
-      const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)idx * 12;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) in4[i] = __ldg(g4 + i);
+      for (int i = 0; i < 12; ++i) in4[i] = s_sh[tid * kShRow + i];
       const float* sh = reinterpret_cast<const float*>(in4);
       float* o = reinterpret_cast<float*>(out4);
 #pragma unroll
@@ -252,9 +280,8 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
           }
         }
       }
-      float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)idx * 12;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) d4[i] = out4[i];
+      for (int i = 0; i < 12; ++i) s_sh[tid * kShRow + i] = out4[i];  // own row only: no hazard
     } else {
       const float* sh = a.shs + (size_t)idx * a.M * 3;
       float* o = a.dL_dsh + (size_t)idx * a.M * 3;
@@ -275,6 +302,15 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
     gmy += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * inv32;
     gmz += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * inv32;
   }
+  if (kVec16) {  // coalesced store of the visible Gaussians' dL_dsh rows (culled rows stay at the caller's zeros)
+    __syncthreads();
+    float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)base * 12;
+    for (int q = tid; q < n * 12; q += 256) {
+      const int row = q / 12;
+      if (s_active[row]) d4[q] = s_sh[row * kShRow + (q - row * 12)];
+    }
+  }
+  if (!active) return;
   a.dL_dmean3D[3 * (size_t)idx] = gmx;
   a.dL_dmean3D[3 * (size_t)idx + 1] = gmy;
   a.dL_dmean3D[3 * (size_t)idx + 2] = gmz;
@@ -325,10 +361,20 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
     return cudaErrorMisalignedAddress;
   a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && al16(f.dL_dsh);
   const int blocks = (f.P + 255) / 256;
-  if (a.vec_sh)
-    geom_bwd_kernel<true><<<blocks, 256, 0, s>>>(a);
-  else
+  if (a.vec_sh) {
+    constexpr int kSmem = 256 * kShRow * (int)sizeof(float4);  // 53 248 B: needs the opt-in above 48 KB
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(geom_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    geom_bwd_kernel<true><<<blocks, 256, kSmem, s>>>(a);
+  } else {
     geom_bwd_kernel<false><<<blocks, 256, 0, s>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -97,11 +97,18 @@ __device__ __forceinline__ void eval_sh(int deg, float3 dir, Load sh, float out[
   }
 }
 
-template <bool kVec16>  // kVec16: M == 16 and shs 16-byte aligned -> 12 x LDG.128 per Gaussian
+constexpr int kShRow = 13;  // float4 per staged SH row: 12 used + 1 pad, so lane-strided LDS.128 are conflict-free
+
+// kVec16: M == 16 and shs 16-byte aligned. The 192-byte SH rows of the block's SURVIVING Gaussians are staged
+// into shared memory with coalesced 16-byte cp.async (LDGSTS) transfers and read back row-wise; rows of culled
+// Gaussians (behind the camera, oversized, off-screen) are never fetched.
+template <bool kVec16>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
   __shared__ float s_view[16], s_proj[16], s_cam[3];
   __shared__ __align__(16) float s_means[256 * 3];
   __shared__ __align__(16) float s_scales[256 * 3];
+  __shared__ uint8_t s_survive[256];
+  extern __shared__ __align__(16) float4 s_sh[];  // [256][kShRow] when kVec16
 
   const int tid = threadIdx.x;
   const int base = blockIdx.x * 256;
@@ -116,14 +123,17 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
   stage_floats(s_means, a.means3D + (size_t)base * 3, n * 3, a.vec_ok);
   if (a.scales) stage_floats(s_scales, a.scales + (size_t)base * 3, n * 3, a.vec_ok);
   __syncthreads();
-  if (tid >= n) return;
   const int idx = base + tid;
 
   int out_radius = 0;
   uint32_t out_tiles = 0;
+  bool survive = false;
+  float4 rq0 = make_float4(0.f, 0.f, 0.f, 0.f), rq1 = rq0;
+  float rdepth = 0.f;
+  const float px = tid < n ? s_means[3 * tid] : 0.f, py = tid < n ? s_means[3 * tid + 1] : 0.f,
+              pz = tid < n ? s_means[3 * tid + 2] : 0.f;
 
-  do {  // single-pass block; `break` == the reference's early `return` with radius/tiles left at 0
-    const float px = s_means[3 * tid], py = s_means[3 * tid + 1], pz = s_means[3 * tid + 2];
+  if (tid < n) do {  // single-pass block; `break` == the reference's early `return` with radius/tiles left at 0
     const float* V = s_view;
     const float* PM = s_proj;
 
@@ -245,34 +255,6 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
     const uint32_t tiles = (uint32_t)(rmaxx - rminx) * (uint32_t)(rmaxy - rminy);
     if (tiles == 0) break;
 
-    // colour: precomputed, or SH evaluated towards the camera (forward.cu:272-277)
-    float rgb[3];
-    uint32_t clamp_bits = 0;
-    if (a.colors_precomp) {
-      const float* cp = a.colors_precomp + (size_t)idx * 3;
-      rgb[0] = __ldg(cp), rgb[1] = __ldg(cp + 1), rgb[2] = __ldg(cp + 2);
-    } else {
-      float3 dir = {px - s_cam[0], py - s_cam[1], pz - s_cam[2]};
-      const float len = __fsqrt_rn(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.x, dir.x, __fmul_rn(dir.y, dir.y))));
-      dir.x = __fdiv_rn(dir.x, len), dir.y = __fdiv_rn(dir.y, len), dir.z = __fdiv_rn(dir.z, len);
-      if (kVec16) {
-        float4 c4v[12];
-        const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)idx * 12;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) c4v[i] = __ldg(g4 + i);
-        const float* cf = reinterpret_cast<const float*>(c4v);
-        eval_sh(a.D, dir, [&](int k, int c) { return cf[k * 3 + c]; }, rgb);
-      } else {
-        const float* sh = a.shs + (size_t)idx * a.M * 3;
-        eval_sh(a.D, dir, [&](int k, int c) { return __ldg(sh + k * 3 + c); }, rgb);
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (rgb[c] < 0.f) clamp_bits |= 1u << c;
-        rgb[c] = fmaxf(rgb[c], 0.0f);
-      }
-    }
-
     // Conservative extent of {pixels where the reference can reach alpha >= 1/255} (ours).
     // power = -q(d), q = 1/2 d^T Q d, Q = conic, Q^-1 = cov2D  =>  |dx| <= sqrt(2 tau cov_x).
     const float op = __ldg(a.opacities + idx);
@@ -291,19 +273,67 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
         if (!(ex >= 0.f) || !(ey >= 0.f)) ex = ey = INFINITY;
       }
     }
-
-    SplatRecord rec;
-    rec.q0 = make_float4(pix_x, pix_y, ex, ey);
-    rec.q1 = make_float4(con_x, con_y, con_z, op);
-    rec.q2 = make_float4(rgb[0], rgb[1], rgb[2], depth);
-    a.rec[idx] = rec;
-    a.clamped[idx] = (uint8_t)clamp_bits;
+    rq0 = make_float4(pix_x, pix_y, ex, ey);
+    rq1 = make_float4(con_x, con_y, con_z, op);
+    rdepth = depth;
     out_radius = radius;
     out_tiles = tiles;
+    survive = true;
   } while (false);
 
-  a.radii[idx] = out_radius;
-  a.tiles_touched[idx] = out_tiles;
+  if (kVec16) {  // cooperative, coalesced staging of the survivors' SH rows (uniform control flow)
+    s_survive[tid] = survive;
+    __syncthreads();
+    const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
+    for (int q = tid; q < n * 12; q += 256) {
+      const int row = q / 12;
+      if (s_survive[row]) {
+        const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+
+  if (survive) {
+    // colour: precomputed, or SH evaluated towards the camera (forward.cu:272-277)
+    float rgb[3];
+    uint32_t clamp_bits = 0;
+    if (a.colors_precomp) {
+      const float* cp = a.colors_precomp + (size_t)idx * 3;
+      rgb[0] = __ldg(cp), rgb[1] = __ldg(cp + 1), rgb[2] = __ldg(cp + 2);
+    } else {
+      float3 dir = {px - s_cam[0], py - s_cam[1], pz - s_cam[2]};
+      const float len = __fsqrt_rn(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.x, dir.x, __fmul_rn(dir.y, dir.y))));
+      dir.x = __fdiv_rn(dir.x, len), dir.y = __fdiv_rn(dir.y, len), dir.z = __fdiv_rn(dir.z, len);
+      if (kVec16) {
+        float4 c4v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) c4v[i] = s_sh[tid * kShRow + i];
+        const float* cf = reinterpret_cast<const float*>(c4v);
+        eval_sh(a.D, dir, [&](int k, int c) { return cf[k * 3 + c]; }, rgb);
+      } else {
+        const float* sh = a.shs + (size_t)idx * a.M * 3;
+        eval_sh(a.D, dir, [&](int k, int c) { return __ldg(sh + k * 3 + c); }, rgb);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (rgb[c] < 0.f) clamp_bits |= 1u << c;
+        rgb[c] = fmaxf(rgb[c], 0.0f);
+      }
+    }
+    SplatRecord rec;
+    rec.q0 = rq0;
+    rec.q1 = rq1;
+    rec.q2 = make_float4(rgb[0], rgb[1], rgb[2], rdepth);
+    a.rec[idx] = rec;
+    a.clamped[idx] = (uint8_t)clamp_bits;
+  }
+  if (tid < n) {
+    a.radii[idx] = out_radius;
+    a.tiles_touched[idx] = out_tiles;
+  }
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -338,10 +368,20 @@ cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int
   if (!rot_ok) return cudaErrorMisalignedAddress;
   const int blocks = (f.P + 255) / 256;
   const bool vec16 = !f.colors_precomp && f.M == 16 && al16(f.shs);
-  if (vec16)
-    preprocess_fwd_kernel<true><<<blocks, 256, 0, s>>>(a);
-  else
+  if (vec16) {
+    constexpr int kSmem = 256 * kShRow * (int)sizeof(float4);  // 53 248 B: needs the opt-in above 48 KB
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    preprocess_fwd_kernel<true><<<blocks, 256, kSmem, s>>>(a);
+  } else {
     preprocess_fwd_kernel<false><<<blocks, 256, 0, s>>>(a);
+  }
   return cudaGetLastError();
 }
 
