@@ -4,6 +4,7 @@
 // with our kernels; nothing here touches the CPU oracle and there is no fallback path.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -96,6 +97,7 @@ BinningState carve_binning(char* chunk, int R) {
   BinningState b;
   const size_t n = (size_t)R;
   carve(chunk, b.inst, n);
+  carve(chunk, b.aux, n);
   carve(chunk, b.keys_unsorted, n);
   carve(chunk, b.keys, n);
   carve(chunk, b.vals_unsorted, n);
@@ -240,11 +242,14 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   }
   {
     StageScope scope(GSR_STAGE_FINALIZE, stream);
-    GSR_CUDA(launch_finalize_binning(R, bin, geom, a.colors_precomp, img.ranges, stream), "finalize_binning");
+    GSR_CUDA(launch_finalize_binning(R, bin, geom, grid_x, img.ranges, stream), "finalize_binning");
     GSR_CUDA(launch_order_tiles(tiles, img.ranges, img.tile_order, img.tile_last, stream), "order_tiles");
   }
   if (debug) GSR_CUDA(cudaStreamSynchronize(stream), "finalize_binning");
-  GSR_STAGE(GSR_STAGE_BLEND_FWD, launch_blend_fwd(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream),
+  static const bool fwd_warp = [] { const char* e = getenv("GSR_FWD_IMPL"); return !(e && !strcmp(e, "mask")); }();
+  GSR_STAGE(GSR_STAGE_BLEND_FWD,
+            (fwd_warp ? launch_blend_fwd : launch_blend_fwd_mask)(a.width, a.height, img, bin, a.background, a.out_color,
+                                                                  a.out_depth, a.out_acc, stream),
             "blend_fwd", debug, stream);
   *num_rendered = R;
   return GSR_OK;
@@ -320,6 +325,7 @@ int gsr_view_binning(char* binning_buffer, int R, gsr_binning_view* out) {
   out->point_list_keys = view_of(b.keys, 8, n);
   out->point_list = view_of(b.vals, 4, n);
   out->instance_records = view_of(b.inst, sizeof(SplatRecord), n);
+  out->instance_aux = view_of(b.aux, sizeof(InstAux), n);
   return GSR_OK;
 }
 
