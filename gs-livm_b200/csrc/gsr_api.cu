@@ -90,6 +90,8 @@ ImageState carve_image(char* chunk, int width, int height) {
   carve(chunk, s.ranges, tiles);
   carve(chunk, s.tile_last, tiles);
   carve(chunk, s.tile_order, tiles);
+  carve(chunk, s.tile_count, tiles);
+  carve(chunk, s.summary, 4);
   return s;
 }
 
@@ -114,12 +116,12 @@ static size_t required_bytes(F carve_fn) {
   return carve_fn() + kAlign;
 }
 
-// One pinned int per host thread for the R read-back (reference: blocking cudaMemcpy D2H,
+// Four pinned words per host thread for the {R, longest list, #large lists} read-back (reference: blocking cudaMemcpy D2H,
 // rasterizer_impl.cu:277).
-static int* pinned_counter() {
-  static thread_local int* p = nullptr;
+static uint32_t* pinned_summary() {
+  static thread_local uint32_t* p = nullptr;
   if (!p) {
-    if (cudaMallocHost(reinterpret_cast<void**>(&p), sizeof(int)) != cudaSuccess) p = nullptr;
+    if (cudaMallocHost(reinterpret_cast<void**>(&p), 4 * sizeof(uint32_t)) != cudaSuccess) p = nullptr;
   }
   return p;
 }
@@ -173,8 +175,7 @@ size_t gsr_required_image(int width, int height) {
   if (width < 0 || height < 0) return 0;
   return required_bytes([&] {
     ImageState s = carve_image(nullptr, width, height);
-    const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    return (size_t)(reinterpret_cast<uintptr_t>(s.tile_order + tiles));
+    return (size_t)(reinterpret_cast<uintptr_t>(s.summary + 4));
   });
 }
 
@@ -218,34 +219,51 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   if (!img_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: image allocator returned NULL");
   ImageState img = carve_image(img_chunk, a.width, a.height);
 
-  GSR_STAGE(GSR_STAGE_PREPROCESS, launch_preprocess_fwd(a, geom, radii, focal_x, focal_y, stream), "preprocess_fwd", debug, stream);
-  GSR_STAGE(GSR_STAGE_SCAN, run_scan(geom, a.P, stream), "scan", debug, stream);
+  // instances per tile are counted by preprocess; one small kernel turns them into the tile ranges, the
+  // scatter cursors, the launch order of the per-tile CTAs and {R, longest list, #large lists}
+  GSR_CUDA(cudaMemsetAsync(img.tile_count, 0, (size_t)tiles * sizeof(uint32_t), stream), "clear tile counts");
+  GSR_STAGE(GSR_STAGE_PREPROCESS, launch_preprocess_fwd(a, geom, radii, img.tile_count, focal_x, focal_y, stream),
+            "preprocess_fwd", debug, stream);
+  GSR_STAGE(GSR_STAGE_SCAN, launch_tile_scan(tiles, img, stream), "tile_scan", debug, stream);
 
-  int* h_count = pinned_counter();
-  if (!h_count) return fail(GSR_ERR_CUDA, "gsr_forward: cudaMallocHost failed");
-  GSR_CUDA(cudaMemcpyAsync(h_count, geom.point_offsets + (a.P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream),
+  // R has to reach the host: the binning allocator is a host callback (reference: blocking cudaMemcpy D2H,
+  // rasterizer_impl.cu:277)
+  uint32_t* h_summary = pinned_summary();
+  if (!h_summary) return fail(GSR_ERR_CUDA, "gsr_forward: cudaMallocHost failed");
+  GSR_CUDA(cudaMemcpyAsync(h_summary, img.summary, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream),
            "read num_rendered");
-  GSR_CUDA(cudaMemsetAsync(img.ranges, 0, (size_t)tiles * sizeof(uint2), stream), "clear ranges");
   GSR_CUDA(cudaStreamSynchronize(stream), "read num_rendered");
-  const int R = *h_count;
-  if (R < 0) return fail(GSR_ERR_INVALID, "gsr_forward: instance count overflows int32");
+  if (h_summary[0] > 0x7fffffffu) return fail(GSR_ERR_INVALID, "gsr_forward: instance count overflows int32");
+  const int R = (int)h_summary[0];
+  const uint32_t longest = h_summary[1];
+  const int n_large = (int)h_summary[2];
 
   char* bin_chunk = binning_alloc(binning_ctx, gsr_required_binning(R));
   if (!bin_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: binning allocator returned NULL");
   BinningState bin = carve_binning(bin_chunk, R);
 
   if (R > 0) {
-    GSR_STAGE(GSR_STAGE_DUPLICATE, launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream),
-              "duplicate_with_keys", debug, stream);
-    const int bit = (int)higher_msb((uint32_t)tiles);
-    GSR_STAGE(GSR_STAGE_SORT, run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
+    const char* force = getenv("GSR_SORT");  // "device": always take the device-wide path (parity tests)
+    if (longest <= (uint32_t)kLargeCap && !(force && !strcmp(force, "device"))) {
+      // per-tile path: bucket by tile, sort every tile's segment inside one CTA (tile_sort.cu)
+      GSR_STAGE(GSR_STAGE_DUPLICATE, launch_scatter_instances(a.P, geom, radii, img, bin, grid_x, grid_y, stream),
+                "scatter_instances", debug, stream);
+      GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, n_large, img, bin, geom, grid_x, stream), "tile_sort", debug,
+                stream);
+    } else {
+      // device-wide path, the reference's own sequence: scan -> duplicateWithKeys -> radix sort -> ranges
+      GSR_STAGE(GSR_STAGE_DUPLICATE,
+                [&] {
+                  cudaError_t e = run_scan(geom, a.P, stream);
+                  return e != cudaSuccess ? e : launch_duplicate_with_keys(a.P, geom, radii, bin, grid_x, grid_y, stream);
+                }(),
+                "duplicate_with_keys", debug, stream);
+      const int bit = (int)higher_msb((uint32_t)tiles);
+      GSR_STAGE(GSR_STAGE_SORT, run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
+      GSR_STAGE(GSR_STAGE_FINALIZE, launch_finalize_binning(R, bin, geom, grid_x, img.ranges, stream), "finalize_binning",
+                debug, stream);
+    }
   }
-  {
-    StageScope scope(GSR_STAGE_FINALIZE, stream);
-    GSR_CUDA(launch_finalize_binning(R, bin, geom, grid_x, img.ranges, stream), "finalize_binning");
-    GSR_CUDA(launch_order_tiles(tiles, img.ranges, img.tile_order, img.tile_last, stream), "order_tiles");
-  }
-  if (debug) GSR_CUDA(cudaStreamSynchronize(stream), "finalize_binning");
   static const bool fwd_warp = [] { const char* e = getenv("GSR_FWD_IMPL"); return !(e && !strcmp(e, "mask")); }();
   GSR_STAGE(GSR_STAGE_BLEND_FWD,
             (fwd_warp ? launch_blend_fwd : launch_blend_fwd_mask)(a.width, a.height, img, bin, a.background, a.out_color,

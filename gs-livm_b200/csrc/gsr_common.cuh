@@ -59,7 +59,14 @@ struct ImageState {
   uint2* ranges;        // [tiles]
   uint32_t* tile_last;  // [tiles] max n_contrib in the tile: where the backward starts
   uint32_t* tile_order; // [tiles] tile ids, longest instance lists first (launch order of the blend CTAs)
+  uint32_t* tile_count; // [tiles] instances per tile (preprocess), then the tile's scatter cursor (tile_sort.cu)
+  uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, 0}
 };
+
+// tile_sort.cu: lists up to kSmallMax instances are sorted by a 256-thread CTA (kSmallCap slots of shared
+// memory), lists up to kLargeCap by a 1024-thread CTA; a frame with a longer list takes the device-wide sort.
+constexpr int kSmallCap = 2048, kSmallMax = kSmallCap - 1;  // kSmallMax + 1 is a power of two: see tile_order
+constexpr int kLargeCap = 12032;  // 12032 x 16 B of keys/values + 32 warps x 1 KB of histograms = 220 KB
 
 struct BinningState {
   uint64_t* keys_unsorted;  // [R]
@@ -92,8 +99,8 @@ struct Camera {
 };
 
 // ---- kernel launchers (each returns the cudaError_t of the launch) ----------------------------
-cudaError_t launch_preprocess_fwd(const gsr_fwd_args& a, const GeomState& g, int* radii, float focal_x, float focal_y,
-                                  cudaStream_t s);
+cudaError_t launch_preprocess_fwd(const gsr_fwd_args& a, const GeomState& g, int* radii, uint32_t* tile_count,
+                                  float focal_x, float focal_y, cudaStream_t s);
 cudaError_t launch_mark_visible(int P, const float* means3D, const float* viewmatrix, unsigned char* present,
                                 cudaStream_t s);
 cudaError_t run_scan(const GeomState& g, int P, cudaStream_t s);
@@ -102,6 +109,11 @@ cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* rad
 cudaError_t run_sort(const BinningState& b, int R, int end_bit, cudaStream_t s);
 cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomState& g, int grid_x, uint2* ranges,
                                     cudaStream_t s);
+cudaError_t launch_tile_scan(int tiles, const ImageState& img, cudaStream_t s);
+cudaError_t launch_scatter_instances(int P, const GeomState& g, const int* radii, const ImageState& img,
+                                     const BinningState& b, int grid_x, int grid_y, cudaStream_t s);
+cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, const BinningState& b, const GeomState& g,
+                             int grid_x, cudaStream_t s);
 cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, uint32_t* tile_last,
                                cudaStream_t s);
 cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,

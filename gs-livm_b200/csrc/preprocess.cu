@@ -42,6 +42,7 @@ struct PreArgs {
   SplatRecord* rec;
   uint32_t* tiles_touched;
   uint8_t* clamped;
+  uint32_t* tile_count;  // [tiles] instances per tile, accumulated here (tile_sort.cu)
   int vec_ok;  // means3D/scales/shs 16-byte aligned -> float4 staging
 };
 
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
   const int idx = base + tid;
 
   int out_radius = 0;
+  int rect_x0 = 0, rect_y0 = 0, rect_w = 1;
   uint32_t out_tiles = 0;
   bool survive = false;
   float4 rq0 = make_float4(0.f, 0.f, 0.f, 0.f), rq1 = rq0;
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
         a.grid_y, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(pix_y, rf), 16.0f), -1.0f), 0.0625f))));
     const uint32_t tiles = (uint32_t)(rmaxx - rminx) * (uint32_t)(rmaxy - rminy);
     if (tiles == 0) break;
+    rect_x0 = rminx, rect_y0 = rminy, rect_w = rmaxx - rminx;
 
     // Conservative extent of {pixels where the reference can reach alpha >= 1/255} (ours).
     // power = -q(d), q = 1/2 d^T Q d, Q = conic, Q^-1 = cov2D  =>  |dx| <= sqrt(2 tau cov_x).
@@ -280,6 +283,22 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
     out_tiles = tiles;
     survive = true;
   } while (false);
+
+  // Instances per tile (tile_sort.cu). Neighbouring Gaussians mostly fall into the same tile, and L2 serialises
+  // atomics to one address (~15 ns each across warps): lanes that hit the same tile are merged with match_any
+  // and only their leader issues the RED.
+  {
+    const uint32_t most = __reduce_max_sync(0xffffffffu, out_tiles);
+    for (uint32_t k = 0; k < most; ++k) {
+      uint32_t t = 0xffffffffu;
+      if (k < out_tiles) {
+        const int ry = (int)k / rect_w;
+        t = (uint32_t)((rect_y0 + ry) * a.grid_x + rect_x0 + ((int)k - ry * rect_w));
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, t);
+      if (t != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&a.tile_count[t], (uint32_t)__popc(peers));
+    }
+  }
 
   if (kVec16) {  // cooperative, coalesced staging of the survivors' SH rows (uniform control flow)
     s_survive[tid] = survive;
@@ -351,8 +370,8 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 }  // namespace
 
-cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int* radii, float focal_x, float focal_y,
-                                  cudaStream_t s) {
+cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int* radii, uint32_t* tile_count,
+                                  float focal_x, float focal_y, cudaStream_t s) {
   PreArgs a;
   a.P = f.P, a.D = f.D, a.M = f.M, a.W = f.width, a.H = f.height;
   a.grid_x = (f.width + kTile - 1) / kTile, a.grid_y = (f.height + kTile - 1) / kTile;
@@ -362,6 +381,7 @@ cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int
   a.cov3D_precomp = f.cov3D_precomp, a.colors_precomp = f.colors_precomp;
   a.viewmatrix = f.viewmatrix, a.projmatrix = f.projmatrix, a.cam_pos = f.cam_pos;
   a.radii = radii, a.rec = g.rec, a.tiles_touched = g.tiles_touched, a.clamped = g.clamped;
+  a.tile_count = tile_count;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   a.vec_ok = al16(f.means3D) && (!f.scales || al16(f.scales));
   const bool rot_ok = f.cov3D_precomp || al16(f.rotations);

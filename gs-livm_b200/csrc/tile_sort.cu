@@ -1,0 +1,438 @@
+// Tile-bucketed binning for sm_100a: the (tile | depth) sort of the reference done as an exact bucketing by
+// tile followed by an in-shared-memory radix sort of every tile's segment.
+//
+// Replaces, on the fast path, cub InclusiveSum + duplicateWithKeys + cub SortPairs + cudaMemset +
+// identifyTileRanges (reference src/cuda_rasterizer/rasterizer_impl.cu:270-316, 64-125) with
+//
+//   preprocess              counts instances per tile (RED.ADD into tile_count)            [preprocess.cu]
+//   tile_scan_kernel        one CTA: exclusive scan of the counts -> ranges (== identifyTileRanges' result),
+//                           scatter cursors, launch order of the blend CTAs, {R, longest list, #large lists}
+//   scatter_instances       one thread per Gaussian: (depth bits, id) appended to each touched tile's segment
+//                           through the tile's cursor (order inside a segment is arbitrary here)
+//   tile_sort_kernel        one CTA per tile: LSD radix sort of the segment by depth bits in shared memory
+//                           (only over the bits that differ inside the segment), ties put in ascending-id
+//                           order, then the outputs in final order: point_list_keys (tile << 32 | depth),
+//                           point_list, the gathered 48-byte records and the 16-byte aux records.
+//
+// Why this is bit-exact. The reference sorts instances by (tile, depth bits) with a STABLE radix sort of a
+// list written in Gaussian-id order (rows of a Gaussian's rectangle are different tiles), so its result is
+// the unique ascending order of the triple (tile, depth bits, id). Any correct sort of that triple gives the
+// same arrays; stability and the unsorted intermediate order are artefacts. Why it is faster at frame scale:
+// a device-wide onesweep pass over ~1 M pairs is bound by its decoupled look-back chain (~20 us per pass,
+// 6 passes + 2 set-up kernels for 43 key bits, ncu in profiles/); here no pass crosses a CTA boundary.
+//
+// Lists longer than kLargeCap do not fit one CTA's shared memory: gsr_forward then takes the device-wide
+// path (binning.cu), which is the bandwidth-efficient choice at those sizes anyway.
+#include "gsr_common.cuh"
+
+namespace gsr {
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------------------
+// One CTA: ranges, cursors, launch order, summary.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __restrict__ tile_count,
+                                                        uint2* __restrict__ ranges, uint32_t* __restrict__ order,
+                                                        uint32_t* __restrict__ tile_last,
+                                                        uint32_t* __restrict__ summary, uint32_t small_cap) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_count[33], s_base[33];
+  __shared__ uint32_t s_carry, s_max, s_large;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 33) s_count[tid] = 0;
+  if (tid == 0) s_carry = 0, s_max = 0, s_large = 0;
+  __syncthreads();
+  for (int base = 0; base < tiles; base += 1024) {
+    const int t = base + tid;
+    const uint32_t c = t < tiles ? tile_count[t] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, w, d);
+        if (lane >= d) w += v;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t off = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - c;
+    if (t < tiles) {
+      ranges[t] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);  // untouched tiles stay (0,0): memset at :311
+      tile_count[t] = off;                                            // from here on: the tile's scatter cursor
+      tile_last[t] = 0;  // blend_fwd accumulates the tile's last contributor with atomicMax
+      atomicAdd(&s_count[32 - __clz(c)], 1u);
+      if (c > small_cap) atomicAdd(&s_large, 1u);
+      atomicMax(&s_max, c);
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += s_warp[31];
+    __syncthreads();
+  }
+  // launch order of the per-tile CTAs: bucketed by floor(log2(length)), longest bucket first
+  if (tid == 0) {
+    uint32_t acc = 0;
+    for (int b = 32; b >= 0; --b) {
+      s_base[b] = acc;
+      acc += s_count[b];
+    }
+    summary[0] = s_carry, summary[1] = s_max, summary[2] = s_large, summary[3] = 0;
+  }
+  __syncthreads();
+  for (int t = tid; t < tiles; t += 1024) {
+    const uint2 r = ranges[t];
+    order[atomicAdd(&s_base[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One thread per Gaussian: append (depth bits, id) to every touched tile's segment. The rectangle is
+// recomputed from the stored pixel mean and the integer radius with the same float ops as in preprocess
+// (getRect, auxiliary.h:39-46), exactly like duplicate_with_keys_kernel.
+__global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const SplatRecord* __restrict__ rec,
+                                                               const int* __restrict__ radii,
+                                                               uint32_t* __restrict__ cursor,
+                                                               uint32_t* __restrict__ seg_keys,
+                                                               uint32_t* __restrict__ seg_vals, int grid_x,
+                                                               int grid_y) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int radius = idx < P ? radii[idx] : 0;
+  int rminx = 0, rminy = 0, rw = 1;
+  uint32_t ntiles = 0, depth_bits = 0;
+  if (radius > 0) {
+    const float4 q0 = rec[idx].q0;
+    depth_bits = __float_as_uint(rec[idx].q2.w);
+    const float rf = (float)radius;
+    rminx = min(grid_x, max(0, __float2int_rz(__fmul_rn(__fadd_rn(q0.x, -rf), 0.0625f))));
+    rminy = min(grid_y, max(0, __float2int_rz(__fmul_rn(__fadd_rn(q0.y, -rf), 0.0625f))));
+    const int rmaxx =
+        min(grid_x, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q0.x, rf), 16.0f), -1.0f), 0.0625f))));
+    const int rmaxy =
+        min(grid_y, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(q0.y, rf), 16.0f), -1.0f), 0.0625f))));
+    rw = rmaxx - rminx;
+    ntiles = (uint32_t)rw * (uint32_t)(rmaxy - rminy);
+  }
+  // lanes that append to the same tile share one atomicAdd on its cursor (see preprocess.cu)
+  const uint32_t most = __reduce_max_sync(kFull, ntiles);
+  for (uint32_t k = 0; k < most; ++k) {
+    uint32_t t = 0xffffffffu;
+    if (k < ntiles) {
+      const int ry = (int)k / rw;
+      t = (uint32_t)((rminy + ry) * grid_x + rminx + ((int)k - ry * rw));
+    }
+    const uint32_t peers = __match_any_sync(kFull, t);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (t != 0xffffffffu && lane == leader) base = atomicAdd(&cursor[t], (uint32_t)__popc(peers));
+    base = __shfl_sync(kFull, base, leader);
+    if (t != 0xffffffffu) {
+      const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+      seg_keys[pos] = depth_bits;
+      seg_vals[pos] = (uint32_t)idx;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Same box as finalize_binning_kernel (binning.cu).
+__device__ __forceinline__ uint32_t clipped_box(float x, float y, float ex, float ey, float tx0, float ty0) {
+  const float lx = x - ex - tx0, hx = x + ex - tx0;
+  const float ly = y - ey - ty0, hy = y + ey - ty0;
+  const int x0 = (lx > 0.0f) ? (int)ceilf(fminf(lx, 16.0f)) : 0;
+  const int x1 = (hx < 15.0f) ? (int)floorf(fmaxf(hx, -1.0f)) : 15;
+  const int y0 = (ly > 0.0f) ? (int)ceilf(fminf(ly, 16.0f)) : 0;
+  const int y1 = (hy < 15.0f) ? (int)floorf(fmaxf(hy, -1.0f)) : 15;
+  if (x1 < x0 || y1 < y0) return 0u;
+  return kBoxValid | (uint32_t)x0 | ((uint32_t)x1 << 4) | ((uint32_t)y0 << 8) | ((uint32_t)y1 << 12);
+}
+
+struct TileSortArgs {
+  const uint2* ranges;
+  const uint32_t* order;
+  const uint32_t* seg_keys;
+  const uint32_t* seg_vals;
+  const SplatRecord* rec;
+  uint64_t* keys_out;
+  uint32_t* vals_out;
+  SplatRecord* inst;
+  InstAux* aux;
+  int grid_x;
+  uint32_t min_len, max_len;  // this launch handles lists with min_len < length <= max_len
+};
+
+// Stable LSD pass over bits [lo, lo + nbits) of `kin` (nbits <= 8): (kin, vin) -> (kout, vout).
+// Every warp owns a contiguous chunk; ranks inside a chunk come from match_any peers, ranks across chunks
+// from the digit-major scan of the per-warp histograms.
+template <int kWarps>
+__device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
+                                           int n, int lo, int nbits, bool by_val, uint32_t (*hist)[256],
+                                           uint32_t* s_scan) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t dmask = (1u << nbits) - 1u;
+  const int chunk = (((n + kWarps - 1) / kWarps) + 31) & ~31;
+  const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
+  const uint32_t* src = by_val ? vin : kin;
+  for (int i = tid; i < kWarps * 256; i += kWarps * 32) hist[0][i] = 0;
+  __syncthreads();
+  // count
+  for (int i = beg + lane; i - lane < end; i += 32) {
+    const bool valid = i < end;
+    const uint32_t d = valid ? ((src[i] >> lo) & dmask) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(kFull, d);
+    if (valid && lane == __ffs(peers) - 1) hist[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // digit-major exclusive scan: thread d walks the warps of digit d, then the digit totals are scanned
+  if (tid < 256) {
+    uint32_t s = 0;
+#pragma unroll 4
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t c = hist[w][tid];
+      hist[w][tid] = s;
+      s += c;
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    s_scan[32 + tid] = incl - s;  // exclusive inside the warp
+  }
+  __syncthreads();
+  if (tid < 256) {
+    uint32_t base = s_scan[32 + tid];
+    for (int w = 0; w < warp; ++w) base += s_scan[w];  // warp < 8
+#pragma unroll 4
+    for (int w = 0; w < kWarps; ++w) hist[w][tid] += base;
+  }
+  __syncthreads();
+  // scatter
+  for (int i = beg + lane; i - lane < end; i += 32) {
+    const bool valid = i < end;
+    const uint32_t k = valid ? kin[i] : 0u, v = valid ? vin[i] : 0u;
+    const uint32_t d = valid ? (((by_val ? v : k) >> lo) & dmask) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(kFull, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) {
+      base = hist[warp][d];
+      hist[warp][d] = base + __popc(peers);
+    }
+    base = __shfl_sync(kFull, base, leader);
+    if (valid) {
+      const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+      kout[pos] = k;
+      vout[pos] = v;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+template <int kCap, int kThreads>
+__global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs a) {
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* k0 = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* v0 = k0 + kCap;
+  uint32_t* k1 = v0 + kCap;
+  uint32_t* v1 = k1 + kCap;
+  uint32_t(*hist)[256] = reinterpret_cast<uint32_t(*)[256]>(v1 + kCap);
+  __shared__ uint32_t s_scan[32 + 256];
+  __shared__ uint32_t s_or_k, s_or_v, s_flag;
+
+  const int tid = threadIdx.x;
+  const uint32_t tile = a.order[blockIdx.x];
+  const uint2 range = a.ranges[tile];
+  const int n = (int)(range.y - range.x);
+  if ((uint32_t)n <= a.min_len || (uint32_t)n > a.max_len) return;
+
+  if (tid == 0) s_or_k = 0, s_or_v = 0, s_flag = 0;
+  __syncthreads();
+  {
+    const uint32_t kf = a.seg_keys[range.x], vf = a.seg_vals[range.x];
+    uint32_t ok = 0, ov = 0;
+    for (int i = tid; i < n; i += kThreads) {
+      const uint32_t k = a.seg_keys[range.x + i], v = a.seg_vals[range.x + i];
+      k0[i] = k, v0[i] = v;
+      ok |= k ^ kf, ov |= v ^ vf;
+    }
+    ok = __reduce_or_sync(kFull, ok), ov = __reduce_or_sync(kFull, ov);
+    if ((tid & 31) == 0) {
+      if (ok) atomicOr(&s_or_k, ok);
+      if (ov) atomicOr(&s_or_v, ov);
+    }
+  }
+  __syncthreads();
+  const uint32_t diff_k = s_or_k, diff_v = s_or_v;
+
+  uint32_t *kc = k0, *vc = v0, *kn = k1, *vn = v1;
+  auto sort_bits = [&](uint32_t diff, bool by_val) {  // LSD over the bits that differ inside the segment
+    if (diff == 0) return;
+    const int lo0 = __ffs(diff) - 1, hi = 32 - __clz(diff);
+    const int passes = (hi - lo0 + 7) / 8;
+    const int width = (hi - lo0 + passes - 1) / passes;
+    for (int p = 0, lo = lo0; p < passes; ++p, lo += width) {
+      radix_pass<kWarps>(kc, vc, kn, vn, n, lo, min(width, hi - lo), by_val, hist, s_scan);
+      uint32_t* t = kc;
+      kc = kn, kn = t;
+      t = vc, vc = vn, vn = t;
+    }
+  };
+  sort_bits(diff_k, false);
+  // Equal depths must come out in ascending id order (the reference's stable sort of an id-ordered list);
+  // the scatter order inside a segment is arbitrary. Runs of equal depth are short (lattice rows at the same
+  // view depth): the thread at the start of a run insertion-sorts the run's ids in place. A run longer than
+  // kRunMax makes the CTA redo the segment as a two-key LSD sort (ids first).
+  constexpr int kRunMax = 48;
+  for (int i = tid; i + 1 < n; i += kThreads) {
+    const uint32_t k = kc[i];
+    if (k != kc[i + 1] || (i > 0 && kc[i - 1] == k)) continue;  // not the first element of a run
+    int hi = i + 2;
+    while (hi < n && hi - i <= kRunMax && kc[hi] == k) ++hi;
+    if (hi - i > kRunMax) {
+      s_flag = 1;
+      continue;
+    }
+    for (int p = i + 1; p < hi; ++p) {
+      const uint32_t v = vc[p];
+      int q = p;
+      while (q > i && vc[q - 1] > v) {
+        vc[q] = vc[q - 1];
+        --q;
+      }
+      vc[q] = v;
+    }
+  }
+  __syncthreads();
+  if (s_flag) {
+    sort_bits(diff_v, true);
+    sort_bits(diff_k, false);
+  }
+
+  // outputs in final order
+  const float tx0 = (float)((tile % (uint32_t)a.grid_x) * kTile), ty0 = (float)((tile / (uint32_t)a.grid_x) * kTile);
+  const uint64_t hi_key = (uint64_t)tile << 32;
+  for (int i = tid; i < n; i += kThreads) {
+    const size_t g = (size_t)range.x + i;
+    a.keys_out[g] = hi_key | kc[i];
+    a.vals_out[g] = vc[i];
+  }
+  auto emit = [&](int i, uint32_t id, const float4& q0, const float4& q1, const float4& q2) {
+    const size_t g = (size_t)range.x + i;
+    float4* dst = reinterpret_cast<float4*>(a.inst + g);
+    dst[0] = q0, dst[1] = q1, dst[2] = q2;
+    InstAux x;
+    x.box = clipped_box(q0.x, q0.y, q0.z, q0.w, tx0, ty0);
+    x.pmin = -(logf(255.0f * q1.w) + 1.0e-4f);
+    x.id = id;
+    x.pad = 0;
+    a.aux[g] = x;
+  };
+  for (int i = tid; i < n; i += 2 * kThreads) {  // two independent record gathers in flight per thread
+    const int i2 = i + kThreads;
+    const uint32_t id = vc[i], id2 = i2 < n ? vc[i2] : id;
+    const float4* src = reinterpret_cast<const float4*>(a.rec + id);
+    const float4* src2 = reinterpret_cast<const float4*>(a.rec + id2);
+    const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+    const float4 r0 = __ldg(src2), r1 = __ldg(src2 + 1), r2 = __ldg(src2 + 2);
+    emit(i, id, q0, q1, q2);
+    if (i2 < n) emit(i2, id2, r0, r1, r2);
+  }
+}
+
+constexpr int kSmallThreads = 256, kLargeThreads = 1024;
+constexpr size_t sort_smem(int cap, int threads) { return (size_t)cap * 16 + (size_t)(threads / 32) * 256 * 4; }
+
+}  // namespace
+
+cudaError_t launch_tile_scan(int tiles, const ImageState& img, cudaStream_t s) {
+  tile_scan_kernel<<<1, 1024, 0, s>>>(tiles, img.tile_count, img.ranges, img.tile_order, img.tile_last, img.summary,
+                                      (uint32_t)kSmallMax);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_instances(int P, const GeomState& g, const int* radii, const ImageState& img,
+                                     const BinningState& b, int grid_x, int grid_y, cudaStream_t s) {
+  uint32_t* seg_keys = reinterpret_cast<uint32_t*>(b.keys_unsorted);
+  scatter_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, radii, img.tile_count, seg_keys, b.vals_unsorted,
+                                                          grid_x, grid_y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, const BinningState& b, const GeomState& g,
+                             int grid_x, cudaStream_t s) {
+  constexpr size_t kSmemSmall = sort_smem(kSmallCap, kSmallThreads), kSmemLarge = sort_smem(kLargeCap, kLargeThreads);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<kSmallCap, kSmallThreads>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSmall);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tile_sort_kernel<kLargeCap, kLargeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kSmemLarge);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  TileSortArgs a;
+  a.ranges = img.ranges, a.order = img.tile_order;
+  a.seg_keys = reinterpret_cast<const uint32_t*>(b.keys_unsorted), a.seg_vals = b.vals_unsorted;
+  a.rec = g.rec, a.keys_out = b.keys, a.vals_out = b.vals, a.inst = b.inst, a.aux = b.aux, a.grid_x = grid_x;
+  // The few long lists (one 1024-thread CTA each, all of an SM's shared memory) and the many short ones are
+  // independent: the short-list kernel runs on a side stream so it fills the SMs the long lists leave free.
+  struct Side {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+  };
+  static thread_local Side side[64];
+  Side* sd = nullptr;
+  if (n_large > 0 && dev >= 0 && dev < 64) {
+    sd = &side[dev];
+    if (!sd->stream) {
+      if (cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&sd->join, cudaEventDisableTiming) != cudaSuccess) {
+        sd->stream = nullptr;
+        sd = nullptr;
+        (void)cudaGetLastError();
+      }
+    }
+  }
+  cudaStream_t small_stream = s;
+  if (sd) {
+    cudaError_t e = cudaEventRecord(sd->fork, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(sd->stream, sd->fork, 0);
+    if (e != cudaSuccess) return e;
+    small_stream = sd->stream;
+  }
+  if (n_large > 0) {  // the longest lists come first in tile_order
+    a.min_len = (uint32_t)kSmallMax, a.max_len = (uint32_t)kLargeCap;
+    tile_sort_kernel<kLargeCap, kLargeThreads><<<n_large, kLargeThreads, kSmemLarge, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  a.min_len = 0, a.max_len = (uint32_t)kSmallMax;
+  tile_sort_kernel<kSmallCap, kSmallThreads><<<tiles, kSmallThreads, kSmemSmall, small_stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (sd) {
+    e = cudaEventRecord(sd->join, sd->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, sd->join, 0);
+  }
+  return e;
+}
+
+}  // namespace gsr

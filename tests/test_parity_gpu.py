@@ -52,10 +52,11 @@ def check_backward(ours, ref, case):
 
 
 # ------------------------------------------------------------------------------------------ (1) golden vectors
+@pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
 @pytest.mark.parametrize("name", helpers.GOLDEN_CASES)
-def test_golden_vectors(name, built_library, cuda_device):
+def test_golden_vectors(name, sort_path, built_library, cuda_device):
     case, ref = helpers.load_golden(name)
-    ours = helpers.run_ours(case, cuda_device)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
     check_forward_exact(ours, ref, case, vs_cuda_reference=True)
     check_backward(ours, ref, case)
 
@@ -70,10 +71,11 @@ def test_golden_vectors(name, built_library, cuda_device):
     (1, 106, 3, SMALL, False, False),                                            # single Gaussian
     (37, 107, 3, dict(width=17, height=9, fx=10.0, fy=10.0), True, False),       # image smaller than two tiles
 ])
-def test_against_cpu_oracle(P, seed, deg, intr, heavy, close, built_library, cuda_device):
+@pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
+def test_against_cpu_oracle(P, seed, deg, intr, heavy, close, sort_path, built_library, cuda_device):
     case = helpers.scene_case(P, seed, deg, intr=intr, heavy=heavy, close_up=close)
     ref = helpers.run_oracle_cpu(case)
-    ours = helpers.run_ours(case, cuda_device)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
     check_forward_exact(ours, ref, case, vs_cuda_reference=False)
     if not (ref["fragile"] != 0).any():
         check_backward(ours, ref, case)
@@ -106,6 +108,48 @@ def test_colors_precomp_and_sh_paths_agree_on_geometry(built_library, cuda_devic
         check_backward(b, ref, case)
 
 
+def _replicated(case, copies):
+    """Every Gaussian `copies` times: exact depth ties everywhere, so the order of equal keys (ascending Gaussian
+    id, what the reference's stable sort produces) is exercised."""
+    rep = lambda t: None if t is None else torch.cat([t] * copies, dim=0).contiguous()  # noqa: E731
+    c = helpers.Case(rep(case.means3D), rep(case.scales), rep(case.rotations), rep(case.opacities) * 0.3, rep(case.shs),
+                     case.background, case.viewmatrix, case.projmatrix, case.camera_center, case.tanfovx, case.tanfovy,
+                     case.width, case.height, case.sh_degree)
+    return c.with_upstream(11)
+
+
+@pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
+def test_depth_ties_keep_id_order(sort_path, built_library, cuda_device):
+    case = _replicated(helpers.scene_case(2500, 131, 1, intr=SMALL, heavy=True), 3)
+    ref = helpers.run_oracle_cpu(case)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
+    keys = np.asarray(ours["point_list_keys"]).astype(np.uint64)
+    assert (keys[1:] == keys[:-1]).mean() > 0.5, "the case must contain equal keys"
+    check_forward_exact(ours, ref, case, vs_cuda_reference=False)
+
+
+def test_list_longer_than_one_cta_takes_the_device_path(built_library, cuda_device):
+    """A tile with more instances than tile_sort.cu's shared-memory capacity (kLargeCap = 12032): gsr_forward
+    must switch to the device-wide sort by itself and still match the oracle bit for bit."""
+    case = helpers.scene_case(2000, 141, 0, intr=SMALL)
+    fwd = helpers.run_oracle_cpu(case, backward=False)
+    m2 = np.asarray(fwd["means2D"])
+    central = (np.asarray(fwd["radii"]) > 0) & (np.abs(m2[:, 0] - 80) < 40) & (np.abs(m2[:, 1] - 48) < 24)
+    k = int(np.argmax(central))
+    g = torch.Generator().manual_seed(3)
+    n = 20_000
+    pick = lambda t: t[k:k + 1].repeat(n, *([1] * (t.dim() - 1)))  # noqa: E731
+    means = pick(case.means3D) + 1e-3 * torch.randn((n, 3), generator=g)
+    c = helpers.Case(means, pick(case.scales) * 0.2, pick(case.rotations), torch.full((n, 1), 0.01), pick(case.shs),
+                     case.background, case.viewmatrix, case.projmatrix, case.camera_center, case.tanfovx, case.tanfovy,
+                     case.width, case.height, case.sh_degree).with_upstream(5)
+    ref = helpers.run_oracle_cpu(c)
+    lengths = np.diff(np.asarray(ref["ranges"]).astype(np.int64), axis=1)
+    assert lengths.max() > 12032
+    ours = helpers.run_ours(c, cuda_device)
+    check_forward_exact(ours, ref, c, vs_cuda_reference=False)
+
+
 # ------------------------------------------------------------------------------------------ (3) reference CUDA
 needs_ref = pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref/gsr_ref_ext.so not built")
 
@@ -116,10 +160,11 @@ needs_ref = pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref/
     (100_000, 402, 0, HALF_NTU, False, False),
     (200_000, 403, 3, None, True, True),
 ])
-def test_against_reference_cuda(P, seed, deg, intr, heavy, close, built_library, cuda_device):
+@pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
+def test_against_reference_cuda(P, seed, deg, intr, heavy, close, sort_path, built_library, cuda_device):
     case = helpers.scene_case(P, seed, deg, intr=intr, heavy=heavy, close_up=close)
     ref = helpers.run_ref_cuda(case, cuda_device)
-    ours = helpers.run_ours(case, cuda_device)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
     check_forward_exact(ours, ref, case, vs_cuda_reference=True)
     check_backward(ours, ref, case)
 
@@ -161,6 +206,13 @@ def test_full_size_keys_sorted_and_ranges_partition(full_size):
     np.testing.assert_array_equal(counts, lens)
     nz = lens > 0
     np.testing.assert_array_equal(tiles[r[nz, 0]], np.nonzero(nz)[0])
+    # the per-tile path (default) and the device-wide path must agree bit for bit
+    d = helpers.run_ours(case, torch.device("cuda:0"), backward=False, sort_path="device")
+    np.testing.assert_array_equal(d["point_list_keys"].astype(np.uint64), keys)
+    np.testing.assert_array_equal(d["point_list"], o["point_list"])
+    np.testing.assert_array_equal(d["ranges"], o["ranges"])
+    np.testing.assert_array_equal(helpers.bits(d["out_color"]), helpers.bits(o["out_color"]))
+    o = d  # the device-wide path also leaves the reference's intermediates behind
     # multiset preserved by the sort: order-independent checksum of (key, value) pairs
     ku, vu = o["point_list_keys_unsorted"].astype(np.uint64), o["point_list_unsorted"].astype(np.uint64)
     mix = lambda k, v: (k * np.uint64(0x9E3779B97F4A7C15) + v * np.uint64(0xC2B2AE3D27D4EB4F))  # noqa: E731
