@@ -293,33 +293,71 @@ __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs 
   };
   sort_bits(diff_k, false);
   // Equal depths must come out in ascending id order (the reference's stable sort of an id-ordered list);
-  // the scatter order inside a segment is arbitrary. Runs of equal depth are short (lattice rows at the same
-  // view depth): the thread at the start of a run insertion-sorts the run's ids in place. A run longer than
-  // kRunMax makes the CTA redo the segment as a two-key LSD sort (ids first).
-  constexpr int kRunMax = 48;
-  for (int i = tid; i + 1 < n; i += kThreads) {
-    const uint32_t k = kc[i];
-    if (k != kc[i + 1] || (i > 0 && kc[i - 1] == k)) continue;  // not the first element of a run
-    int hi = i + 2;
-    while (hi < n && hi - i <= kRunMax && kc[hi] == k) ++hi;
-    if (hi - i > kRunMax) {
-      s_flag = 1;
-      continue;
-    }
-    for (int p = i + 1; p < hi; ++p) {
-      const uint32_t v = vc[p];
-      int q = p;
-      while (q > i && vc[q - 1] > v) {
-        vc[q] = vc[q - 1];
-        --q;
+  // the scatter order inside a segment is arbitrary. Lattice rows at the same view depth make such runs
+  // common on voxelised maps, so this is done in parallel: every warp finds the run bounds of its contiguous
+  // share with ballots, then every element ranks its id inside its run. A run longer than kRunMax makes the
+  // CTA redo the segment as a two-key LSD sort (ids first).
+  constexpr int kRunMax = 256;
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int chunk = (((n + kWarps - 1) / kWarps) + 31) & ~31;
+    const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
+    uint32_t* run_lo = kn;  // the spare key/value buffers hold the bounds
+    uint32_t* run_hi = vn;
+    if (beg < end) {
+      int carry = beg;  // start of the run that contains element beg
+      {
+        const uint32_t k = kc[beg];
+        while (carry > 0 && beg - carry <= kRunMax && kc[carry - 1] == k) --carry;
       }
-      vc[q] = v;
+      for (int c = beg; c < end; c += 32) {
+        const int i = c + lane;
+        const bool valid = i < end;
+        const bool is_start = valid && (i == 0 || kc[i - 1] != kc[i]);
+        const uint32_t b = __ballot_sync(kFull, is_start);
+        const uint32_t mine = b & (kFull >> (31 - lane));
+        if (valid) run_lo[i] = (uint32_t)(mine ? c + 31 - __clz(mine) : carry);
+        if (b) carry = c + 31 - __clz(b);
+      }
+      int carry_hi = end;  // one past the run that contains element end - 1
+      {
+        const uint32_t k = kc[end - 1];
+        while (carry_hi < n && carry_hi - end <= kRunMax && kc[carry_hi] == k) ++carry_hi;
+      }
+      for (int c = beg + ((end - beg - 1) & ~31); c >= beg; c -= 32) {
+        const int i = c + lane;
+        const bool valid = i < end;
+        const bool is_last = valid && (i == n - 1 || kc[i + 1] != kc[i]);
+        const uint32_t b = __ballot_sync(kFull, is_last);
+        const uint32_t mine = b & (kFull << lane);
+        if (valid) run_hi[i] = (uint32_t)(mine ? c + __ffs(mine) : carry_hi);
+        if (b) carry_hi = c + __ffs(b);
+      }
     }
-  }
-  __syncthreads();
-  if (s_flag) {
-    sort_bits(diff_v, true);
-    sort_bits(diff_k, false);
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) {
+      const int lo = (int)run_lo[i], hi = (int)run_hi[i];
+      int pos = i;
+      if (hi - lo > kRunMax) {
+        s_flag = 1;
+      } else if (hi - lo > 1) {
+        const uint32_t v = vc[i];
+        int rank = 0;
+        for (int j = lo; j < hi; ++j) rank += vc[j] < v;
+        pos = lo + rank;
+      }
+      run_lo[i] = (uint32_t)pos;
+    }
+    __syncthreads();
+    if (!s_flag) {
+      for (int i = tid; i < n; i += kThreads) run_hi[run_lo[i]] = vc[i];
+      __syncthreads();
+      uint32_t* t = vc;  // ids now live in the spare value buffer; keys are unchanged (equal inside a run)
+      vc = vn, vn = t;
+    } else {
+      sort_bits(diff_v, true);
+      sort_bits(diff_k, false);
+    }
   }
 
   // outputs in final order

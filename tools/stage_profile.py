@@ -41,7 +41,7 @@ def main():
             torch.cuda.synchronize()
             if it >= 3:
                 for n, v in ctx.stage_times().items():
-                    acc[n] += v
+                    acc[n] += max(v, 0.0)  # -1: the stage did not run on this path
                 tot += e0.elapsed_time(e1)
         print(f"ours P={P} {W}x{H} R={ctx.num_rendered} visible={int((ctx.radii > 0).sum())}")
         for n in _lib.STAGES:
