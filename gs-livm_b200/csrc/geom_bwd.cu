@@ -46,6 +46,7 @@ struct GeomBwdArgs {
   float* dL_dscale;
   float* dL_drot;
   int vec_sh;  // M == 16 and shs / dL_dsh 16-byte aligned
+  int assign_all;  // GSR_BWD_OUTPUTS_UNINITIALIZED: also write the zeros of Gaussians with radii <= 0
 };
 
 __device__ __forceinline__ float dot3_ref(float a, float b, float c, float d, float e, float f) {
@@ -294,6 +295,8 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
           }
         }
       }
+      if (a.assign_all)  // coefficients above the active degree
+        for (int k = ncoef * 3; k < a.M * 3; ++k) o[k] = 0.f;
     }
     // through the normalisation dir = o/|o| (reference dnormvdv, auxiliary.h:93-103)
     const float sum2 = ox * ox + oy * oy + oz * oz;
@@ -308,9 +311,24 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
     for (int q = tid; q < n * 12; q += 256) {
       const int row = q / 12;
       if (s_active[row]) d4[q] = s_sh[row * kShRow + (q - row * 12)];
+      else if (a.assign_all) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  if (!active) return;
+  if (!active) {
+    if (a.assign_all && tid < n) {  // the caller did not zero the outputs: culled Gaussians get their zeros here
+      const size_t i = (size_t)idx;
+      a.dL_dmean3D[3 * i] = 0.f, a.dL_dmean3D[3 * i + 1] = 0.f, a.dL_dmean3D[3 * i + 2] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * i + k] = 0.f;
+      if (a.scales && !a.cov3D_precomp) {
+        a.dL_dscale[3 * i] = 0.f, a.dL_dscale[3 * i + 1] = 0.f, a.dL_dscale[3 * i + 2] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (!kVec16 && a.shs)
+        for (int k = 0; k < a.M * 3; ++k) a.dL_dsh[i * a.M * 3 + k] = 0.f;
+    }
+    return;
+  }
   a.dL_dmean3D[3 * (size_t)idx] = gmx;
   a.dL_dmean3D[3 * (size_t)idx + 1] = gmy;
   a.dL_dmean3D[3 * (size_t)idx + 2] = gmz;
@@ -360,6 +378,7 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
   if (!al16(f.dL_dconic) || (!f.cov3D_precomp && (!al16(f.rotations) || !al16(f.dL_drot))))
     return cudaErrorMisalignedAddress;
   a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && al16(f.dL_dsh);
+  a.assign_all = (f.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) ? 1 : 0;
   const int blocks = (f.P + 255) / 256;
   if (a.vec_sh) {
     constexpr int kSmem = 256 * kShRow * (int)sizeof(float4);  // 53 248 B: needs the opt-in above 48 KB

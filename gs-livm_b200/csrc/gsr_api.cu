@@ -294,8 +294,17 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   const float focal_y = a.height / (2.0f * a.tan_fovy);
   const float focal_x = a.width / (2.0f * a.tan_fovx);
 
+  if (a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) {  // the four accumulated outputs start from zero
+    const size_t n = (size_t)a.P * sizeof(float);
+    GSR_CUDA(cudaMemsetAsync(a.dL_dmean2D, 0, 3 * n, stream), "zero dL_dmean2D");
+    GSR_CUDA(cudaMemsetAsync(a.dL_dconic, 0, 4 * n, stream), "zero dL_dconic");
+    GSR_CUDA(cudaMemsetAsync(a.dL_dopacity, 0, n, stream), "zero dL_dopacity");
+    GSR_CUDA(cudaMemsetAsync(a.dL_dcolor, 0, 3 * n, stream), "zero dL_dcolor");
+  }
   if (a.R > 0) {
-    GSR_STAGE(GSR_STAGE_BLEND_BWD, launch_blend_bwd(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
+    const char* impl = getenv("GSR_BWD_IMPL");
+    const bool bwd_mask = impl && !strcmp(impl, "mask");
+    GSR_STAGE(GSR_STAGE_BLEND_BWD, (bwd_mask ? launch_blend_bwd_mask : launch_blend_bwd)(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
                                a.dL_dconic, a.dL_dopacity, a.dL_dcolor, stream),
               "blend_bwd", debug, stream);
   }

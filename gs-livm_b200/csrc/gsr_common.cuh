@@ -125,6 +125,10 @@ cudaError_t launch_blend_fwd_mask(int width, int height, const ImageState& img, 
 cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const BinningState& b,
                              const float* background, const float* dL_dpix, const float* dL_dacc, float* dL_dmean2D,
                              float* dL_dconic, float* dL_dopacity, float* dL_dcolor, cudaStream_t s);
+cudaError_t launch_blend_bwd_mask(int width, int height, const ImageState& img, const BinningState& b,
+                                  const float* background, const float* dL_dpix, const float* dL_dacc,
+                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                                  cudaStream_t s);
 cudaError_t launch_geom_bwd(const gsr_bwd_args& a, const GeomState& g, const int* radii, float focal_x, float focal_y,
                             cudaStream_t s);
 

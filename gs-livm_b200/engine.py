@@ -86,12 +86,13 @@ class RasterContext:
         return self.out_color, self.out_depth, self.out_acc
 
     def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False) -> Dict[str, torch.Tensor]:
-        """Gradients of the last forward. Outputs are zero-filled here (the contract of the reference's
-        backward: rasterize_points.cu:173-181) inside whatever region the caller is timing."""
+        """Gradients of the last forward. The reference's caller zero-fills all nine outputs before every
+        backward (rasterize_points.cu:173-181); here the library is told they are uninitialised
+        (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element itself, inside whatever region the caller is
+        timing."""
         f = self._fwd_args
         if f is None:
             raise RuntimeError("backward() before forward()")
-        self.grad_flat.zero_()
         g = self.grads
         a = _lib.BwdArgs()
         a.P, a.D, a.M, a.R, a.width, a.height = self.P, self.D, self.M, self.num_rendered, self.W, self.H
@@ -105,7 +106,7 @@ class RasterContext:
         a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = g["dL_dmean2D"].data_ptr(), g["dL_dconic"].data_ptr(), g["dL_dopacity"].data_ptr()
         a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D = g["dL_dcolor"].data_ptr(), g["dL_dmean3D"].data_ptr(), g["dL_dcov3D"].data_ptr()
         a.dL_dsh, a.dL_dscale, a.dL_drot = g["dL_dsh"].data_ptr(), g["dL_dscale"].data_ptr(), g["dL_drot"].data_ptr()
-        a.debug = int(debug)
+        a.debug, a.flags = int(debug), _lib.BWD_OUTPUTS_UNINITIALIZED
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.gsr_backward(C.byref(a), stream), "gsr_backward")
         return g

@@ -56,16 +56,26 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 class _ScratchAllocator:
-    """resizeFunctional (rasterize_points.cu:36-44): a byte tensor the C ABI sizes through a callback."""
+    """resizeFunctional (rasterize_points.cu:36-44): a byte tensor the C ABI sizes through a callback.
+
+    The ctypes callback closes over a one-element list, not over `self`: a bound method would put the buffer
+    into a reference cycle (object -> callback -> method -> object) and hand its lifetime to Python's cyclic
+    collector, i.e. hundreds of MB of scratch per render would pile up until the next collection and the
+    caching allocator would answer with cudaMalloc instead of reusing the previous render's blocks."""
 
     def __init__(self, device: torch.device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.fn = _lib.ALLOC_FN(self._alloc)
+        cell = [torch.empty(0, dtype=torch.uint8, device=device)]
 
-    def _alloc(self, _ctx, nbytes):
-        self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self.tensor.data_ptr()
+        def _alloc(_ctx, nbytes, _cell=cell, _device=device):
+            _cell[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=_device)
+            return _cell[0].data_ptr()
+
+        self._cell = cell
+        self.fn = _lib.ALLOC_FN(_alloc)
+
+    @property
+    def tensor(self) -> torch.Tensor:
+        return self._cell[0]
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -125,15 +135,20 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
     P, H, W = means3D.size(0), dL_dout_color.size(1), dL_dout_color.size(2)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
     opts = dict(dtype=torch.float32, device=dev)
-    dL_dmeans3D = torch.zeros((P, 3), **opts)
-    dL_dmeans2D = torch.zeros((P, 3), **opts)
-    dL_dcolors = torch.zeros((P, NUM_CHANNELS), **opts)
-    dL_dconic = torch.zeros((P, 2, 2), **opts)
-    dL_dopacity = torch.zeros((P, 1), **opts)
-    dL_dcov3D = torch.zeros((P, 6), **opts)
-    dL_dsh = torch.zeros((P, M, 3), **opts)
-    dL_dscales = torch.zeros((P, 3), **opts)
-    dL_drotations = torch.zeros((P, 4), **opts)
+    # The reference zero-fills all nine tensors here (rasterize_points.cu:173-181). The library is told the
+    # outputs are uninitialised instead (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element of what it
+    # computes; only what it does not touch on this argument combination is zeroed here.
+    have_cov = cov3D_precomp is not None and cov3D_precomp.numel() != 0
+    fresh = torch.empty if P != 0 else torch.zeros
+    dL_dmeans3D = fresh((P, 3), **opts)
+    dL_dmeans2D = fresh((P, 3), **opts)
+    dL_dcolors = fresh((P, NUM_CHANNELS), **opts)
+    dL_dconic = fresh((P, 2, 2), **opts)
+    dL_dopacity = fresh((P, 1), **opts)
+    dL_dcov3D = fresh((P, 6), **opts)
+    dL_dsh = fresh((P, M, 3), **opts)
+    dL_dscales = (torch.zeros if have_cov else fresh)((P, 3), **opts)
+    dL_drotations = (torch.zeros if have_cov else fresh)((P, 4), **opts)
 
     if P != 0:
         keep = [_f32c(t) for t in (background, means3D, sh, colors, scales, rotations, cov3D_precomp, viewmatrix,
@@ -152,7 +167,7 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
         a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = dL_dmeans2D.data_ptr(), dL_dconic.data_ptr(), dL_dopacity.data_ptr()
         a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D = dL_dcolors.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr()
         a.dL_dsh, a.dL_dscale, a.dL_drot = _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr()
-        a.debug = int(bool(debug))
+        a.debug, a.flags = int(bool(debug)), _lib.BWD_OUTPUTS_UNINITIALIZED
         with torch.cuda.device(dev):
             st = lib.gsr_backward(C.byref(a), _stream_ptr(dev))
         _lib.check(st, "gsr_backward")
