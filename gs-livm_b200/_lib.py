@@ -70,6 +70,11 @@ class ImageView(C.Structure):
     _fields_ = [(n, ArrayView) for n in ("accum_alpha", "n_contrib", "ranges", "tile_last", "tile_order")]
 
 
+class AsyncStatus(C.Structure):
+    _fields_ = [("num_rendered", C.c_uint32), ("longest_list", C.c_uint32), ("long_lists", C.c_uint32),
+                ("overflow", C.c_uint32)]
+
+
 # every symbol include/gsr.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "gsr_abi_version": (C.c_int, []),
@@ -80,6 +85,8 @@ SYMBOLS = {
     "gsr_required_binning": (C.c_size_t, [C.c_int]),
     "gsr_forward": (C.c_int, [C.POINTER(FwdArgs), ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
                               C.c_void_p, c_int_p]),
+    "gsr_forward_presized": (C.c_int, [C.POINTER(FwdArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "gsr_backward": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
     "gsr_mark_visible": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_view_geom": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GeomView)]),

@@ -107,8 +107,9 @@ struct PixelState {
 __device__ __forceinline__ void pair_backward(PixelState& s, float alpha, float G, float dx, float dy,
                                               const float4& q1, const float4& q2, float ddelx_dx, float ddely_dy,
                                               float g[8], float& g_op) {
-  const float one_m_alpha = 1.f - alpha;
-  s.T = s.T / one_m_alpha;
+  // one correctly rounded reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581)
+  const float inv = __frcp_rn(1.f - alpha);
+  s.T = s.T * inv;
   const float dchannel_dcolor = alpha * s.T;
   const float keep = 1.f - s.last_alpha;
   s.acc0 = s.last_alpha * s.lc0 + keep * s.acc0;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void pair_backward(PixelState& s, float alpha, float 
   dL_dalpha += (1.0f - s.acc_s) * s.dacc;
   dL_dalpha *= s.T;
   s.last_alpha = alpha;
-  dL_dalpha += (-s.T_final / one_m_alpha) * s.bg_dot;
+  dL_dalpha += (-s.T_final * inv) * s.bg_dot;
   const float dL_dG = q1.w * dL_dalpha;
   const float gdx = G * dx, gdy = G * dy;
   const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
@@ -288,7 +289,7 @@ __device__ __forceinline__ void blend_bwd_warp(const BwdArgs& a, WarpRing& ring,
             if (active) {
               const int jj = (int)list8[min(g + half * SLOTS + q, nhit - 1)];
               const float4 q2 = s[3 * jj + 2];
-              st.T = st.T / (1.f - al);
+              st.T = st.T * __frcp_rn(1.f - al);
               const float keep = 1.f - st.last_alpha;
               st.acc0 = st.last_alpha * st.lc0 + keep * st.acc0;
               st.acc1 = st.last_alpha * st.lc1 + keep * st.acc1;
@@ -310,7 +311,7 @@ __device__ __forceinline__ void blend_bwd_warp(const BwdArgs& a, WarpRing& ring,
             float dL_dalpha = (q2.x - snap_a0) * st.dpx0 + (q2.y - snap_a1) * st.dpx1 + (q2.z - snap_a2) * st.dpx2;
             dL_dalpha += (1.0f - snap_as) * st.dacc;
             dL_dalpha *= snap_T;
-            dL_dalpha += (-st.T_final / (1.f - al)) * st.bg_dot;
+            dL_dalpha += (-st.T_final * __frcp_rn(1.f - al)) * st.bg_dot;
             const float dL_dG = q1.w * dL_dalpha;
             const float gdx = G * dx, gdy = G * dy;
             const float dG_ddelx = -gdx * q1.x - gdy * q1.y;

@@ -187,21 +187,36 @@ size_t gsr_required_binning(int R) {
   });
 }
 
+static int validate_fwd(const gsr_fwd_args& a, const char* who) {
+  if (a.P <= 0 || a.width <= 0 || a.height <= 0) return fail(GSR_ERR_INVALID, "%s: P, width, height must be > 0", who);
+  if (!a.means3D || !a.opacities || !a.viewmatrix || !a.projmatrix || !a.cam_pos || !a.background || !a.out_color ||
+      !a.out_depth || !a.out_acc)
+    return fail(GSR_ERR_INVALID, "%s: null input/output pointer", who);
+  if (!a.colors_precomp && (!a.shs || a.M <= 0)) return fail(GSR_ERR_INVALID, "%s: need shs or colors_precomp", who);
+  if (!a.colors_precomp && (a.D < 0 || a.D > 3 || (a.D + 1) * (a.D + 1) > a.M))
+    return fail(GSR_ERR_INVALID, "%s: SH degree %d needs %d coefficients, M = %d", who, a.D, (a.D + 1) * (a.D + 1), a.M);
+  if (!a.cov3D_precomp && (!a.scales || !a.rotations))
+    return fail(GSR_ERR_INVALID, "%s: need scales+rotations or cov3D_precomp", who);
+  return GSR_OK;
+}
+
+static int launch_blend_forward(const gsr_fwd_args& a, const ImageState& img, const BinningState& bin, int debug,
+                                cudaStream_t stream) {
+  static const bool fwd_warp = [] { const char* e = getenv("GSR_FWD_IMPL"); return !(e && !strcmp(e, "mask")); }();
+  GSR_STAGE(GSR_STAGE_BLEND_FWD,
+            (fwd_warp ? launch_blend_fwd : launch_blend_fwd_mask)(a.width, a.height, img, bin, a.background, a.out_color,
+                                                                  a.out_depth, a.out_acc, stream),
+            "blend_fwd", debug, stream);
+  return GSR_OK;
+}
+
 int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ctx, gsr_alloc_fn binning_alloc,
                 void* binning_ctx, gsr_alloc_fn image_alloc, void* image_ctx, void* stream_v, int* num_rendered) {
   if (!args || !geom_alloc || !binning_alloc || !image_alloc || !num_rendered)
     return fail(GSR_ERR_INVALID, "gsr_forward: null argument");
   const gsr_fwd_args& a = *args;
   *num_rendered = 0;
-  if (a.P <= 0 || a.width <= 0 || a.height <= 0) return fail(GSR_ERR_INVALID, "gsr_forward: P, width, height must be > 0");
-  if (!a.means3D || !a.opacities || !a.viewmatrix || !a.projmatrix || !a.cam_pos || !a.background || !a.out_color ||
-      !a.out_depth || !a.out_acc)
-    return fail(GSR_ERR_INVALID, "gsr_forward: null input/output pointer");
-  if (!a.colors_precomp && (!a.shs || a.M <= 0)) return fail(GSR_ERR_INVALID, "gsr_forward: need shs or colors_precomp");
-  if (!a.colors_precomp && (a.D < 0 || a.D > 3 || (a.D + 1) * (a.D + 1) > a.M))
-    return fail(GSR_ERR_INVALID, "gsr_forward: SH degree %d needs %d coefficients, M = %d", a.D, (a.D + 1) * (a.D + 1), a.M);
-  if (!a.cov3D_precomp && (!a.scales || !a.rotations))
-    return fail(GSR_ERR_INVALID, "gsr_forward: need scales+rotations or cov3D_precomp");
+  if (int st = validate_fwd(a, "gsr_forward")) return st;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int debug = a.debug;
 
@@ -220,11 +235,11 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   ImageState img = carve_image(img_chunk, a.width, a.height);
 
   // instances per tile are counted by preprocess; one small kernel turns them into the tile ranges, the
-  // scatter cursors, the launch order of the per-tile CTAs and {R, longest list, #large lists}
+  // scatter cursors, the launch order of the per-tile CTAs and {R, longest list, #long lists}
   GSR_CUDA(cudaMemsetAsync(img.tile_count, 0, (size_t)tiles * sizeof(uint32_t), stream), "clear tile counts");
   GSR_STAGE(GSR_STAGE_PREPROCESS, launch_preprocess_fwd(a, geom, radii, img.tile_count, focal_x, focal_y, stream),
             "preprocess_fwd", debug, stream);
-  GSR_STAGE(GSR_STAGE_SCAN, launch_tile_scan(tiles, img, stream), "tile_scan", debug, stream);
+  GSR_STAGE(GSR_STAGE_SCAN, launch_tile_scan(tiles, img, 0xffffffffu, stream), "tile_scan", debug, stream);
 
   // R has to reach the host: the binning allocator is a host callback (reference: blocking cudaMemcpy D2H,
   // rasterizer_impl.cu:277)
@@ -264,13 +279,40 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
                 debug, stream);
     }
   }
-  static const bool fwd_warp = [] { const char* e = getenv("GSR_FWD_IMPL"); return !(e && !strcmp(e, "mask")); }();
-  GSR_STAGE(GSR_STAGE_BLEND_FWD,
-            (fwd_warp ? launch_blend_fwd : launch_blend_fwd_mask)(a.width, a.height, img, bin, a.background, a.out_color,
-                                                                  a.out_depth, a.out_acc, stream),
-            "blend_fwd", debug, stream);
+  if (int st = launch_blend_forward(a, img, bin, debug, stream)) return st;
   *num_rendered = R;
   return GSR_OK;
+}
+
+int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, char* binning_buffer, int R_capacity,
+                         char* image_buffer, void* stream_v, gsr_async_status* status) {
+  if (!args || !geom_buffer || !binning_buffer || !image_buffer || R_capacity <= 0)
+    return fail(GSR_ERR_INVALID, "gsr_forward_presized: null buffer or non-positive capacity");
+  const gsr_fwd_args& a = *args;
+  if (int st = validate_fwd(a, "gsr_forward_presized")) return st;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int debug = a.debug;
+  const float focal_y = a.height / (2.0f * a.tan_fovy);
+  const float focal_x = a.width / (2.0f * a.tan_fovx);
+  const int grid_x = (a.width + kTile - 1) / kTile, grid_y = (a.height + kTile - 1) / kTile;
+  const int tiles = grid_x * grid_y;
+  GeomState geom = carve_geom(geom_buffer, a.P);
+  int* radii = a.radii ? a.radii : geom.internal_radii;
+  ImageState img = carve_image(image_buffer, a.width, a.height);
+  BinningState bin = carve_binning(binning_buffer, R_capacity);
+
+  GSR_CUDA(cudaMemsetAsync(img.tile_count, 0, (size_t)tiles * sizeof(uint32_t), stream), "clear tile counts");
+  GSR_STAGE(GSR_STAGE_PREPROCESS, launch_preprocess_fwd(a, geom, radii, img.tile_count, focal_x, focal_y, stream),
+            "preprocess_fwd", debug, stream);
+  // tile_scan empties every range if the frame does not fit, so the stages below then find nothing to do
+  GSR_STAGE(GSR_STAGE_SCAN, launch_tile_scan(tiles, img, (uint32_t)R_capacity, stream), "tile_scan", debug, stream);
+  if (status)
+    GSR_CUDA(cudaMemcpyAsync(status, img.summary, sizeof(gsr_async_status), cudaMemcpyDeviceToHost, stream),
+             "copy status");
+  GSR_STAGE(GSR_STAGE_DUPLICATE, launch_scatter_instances(a.P, geom, radii, img, bin, grid_x, grid_y, stream),
+            "scatter_instances", debug, stream);
+  GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, -1, img, bin, geom, grid_x, stream), "tile_sort", debug, stream);
+  return launch_blend_forward(a, img, bin, debug, stream);
 }
 
 int gsr_backward(const gsr_bwd_args* args, void* stream_v) {

@@ -60,7 +60,7 @@ struct ImageState {
   uint32_t* tile_last;  // [tiles] max n_contrib in the tile: where the backward starts
   uint32_t* tile_order; // [tiles] tile ids, longest instance lists first (launch order of the blend CTAs)
   uint32_t* tile_count; // [tiles] instances per tile (preprocess), then the tile's scatter cursor (tile_sort.cu)
-  uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, 0}
+  uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, overflow code (sync-free forward)}
 };
 
 // tile_sort.cu: lists up to kSmallMax instances are sorted by a 256-thread CTA (kSmallCap slots of shared
@@ -109,7 +109,7 @@ cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* rad
 cudaError_t run_sort(const BinningState& b, int R, int end_bit, cudaStream_t s);
 cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomState& g, int grid_x, uint2* ranges,
                                     cudaStream_t s);
-cudaError_t launch_tile_scan(int tiles, const ImageState& img, cudaStream_t s);
+cudaError_t launch_tile_scan(int tiles, const ImageState& img, uint32_t r_cap, cudaStream_t s);
 cudaError_t launch_scatter_instances(int P, const GeomState& g, const int* radii, const ImageState& img,
                                      const BinningState& b, int grid_x, int grid_y, cudaStream_t s);
 cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, const BinningState& b, const GeomState& g,

@@ -35,7 +35,8 @@ constexpr uint32_t kFull = 0xffffffffu;
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __restrict__ tile_count,
                                                         uint2* __restrict__ ranges, uint32_t* __restrict__ order,
                                                         uint32_t* __restrict__ tile_last,
-                                                        uint32_t* __restrict__ summary, uint32_t small_cap) {
+                                                        uint32_t* __restrict__ summary, uint32_t small_cap,
+                                                        uint32_t r_cap, uint32_t list_cap) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_count[33], s_base[33];
   __shared__ uint32_t s_carry, s_max, s_large;
@@ -84,9 +85,18 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, uint32_t* __
       s_base[b] = acc;
       acc += s_count[b];
     }
-    summary[0] = s_carry, summary[1] = s_max, summary[2] = s_large, summary[3] = 0;
+    // r_cap != ~0: sync-free forward into a presized binning buffer. If the frame does not fit (more instances
+    // than the buffer holds, or a list too long for the per-tile sort) every range is emptied, so all later
+    // stages find nothing to do, and the overflow is reported to the host with the other counters.
+    const uint32_t overflow = r_cap == 0xffffffffu ? 0u : (s_carry > r_cap ? 1u : (s_max > list_cap ? 2u : 0u));
+    summary[0] = s_carry, summary[1] = s_max, summary[2] = overflow ? 0u : s_large, summary[3] = overflow;
+    s_large = overflow;
   }
   __syncthreads();
+  if (s_large != 0 && r_cap != 0xffffffffu) {  // (s_large now holds the overflow code)
+    for (int t = tid; t < tiles; t += 1024) ranges[t] = make_uint2(0u, 0u);
+    __syncthreads();
+  }
   for (int t = tid; t < tiles; t += 1024) {
     const uint2 r = ranges[t];
     order[atomicAdd(&s_base[32 - __clz(r.y - r.x)], 1u)] = (uint32_t)t;
@@ -102,7 +112,8 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
                                                                uint32_t* __restrict__ cursor,
                                                                uint32_t* __restrict__ seg_keys,
                                                                uint32_t* __restrict__ seg_vals, int grid_x,
-                                                               int grid_y) {
+                                                               int grid_y, const uint32_t* __restrict__ summary) {
+  if (summary[3]) return;  // presized binning buffer too small for this frame: nothing may be written
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int radius = idx < P ? radii[idx] : 0;
@@ -158,6 +169,7 @@ __device__ __forceinline__ uint32_t clipped_box(float x, float y, float ex, floa
 struct TileSortArgs {
   const uint2* ranges;
   const uint32_t* order;
+  const uint32_t* summary;  // [2] = number of long lists (they come first in `order`)
   const uint32_t* seg_keys;
   const uint32_t* seg_vals;
   const SplatRecord* rec;
@@ -242,9 +254,8 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 }
 
 template <int kCap, int kThreads>
-__global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs a) {
+__device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t tile, unsigned char* smem_raw) {
   constexpr int kWarps = kThreads / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* k0 = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* v0 = k0 + kCap;
   uint32_t* k1 = v0 + kCap;
@@ -254,11 +265,11 @@ __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs 
   __shared__ uint32_t s_or_k, s_or_v, s_flag;
 
   const int tid = threadIdx.x;
-  const uint32_t tile = a.order[blockIdx.x];
   const uint2 range = a.ranges[tile];
   const int n = (int)(range.y - range.x);
   if ((uint32_t)n <= a.min_len || (uint32_t)n > a.max_len) return;
 
+  __syncthreads();  // the previous tile of this CTA is completely written out
   if (tid == 0) s_or_k = 0, s_or_v = 0, s_flag = 0;
   __syncthreads();
   {
@@ -391,14 +402,27 @@ __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs 
   }
 }
 
+// Short lists: one CTA per tile. Long lists: a few persistent CTAs (each takes a whole SM's shared memory) walk
+// the first summary[2] entries of the launch order.
+template <int kCap, int kThreads, bool kPersistent>
+__global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (kPersistent) {
+    const uint32_t n_long = a.summary[2];
+    for (uint32_t t = blockIdx.x; t < n_long; t += gridDim.x) sort_one_tile<kCap, kThreads>(a, a.order[t], smem_raw);
+  } else {
+    sort_one_tile<kCap, kThreads>(a, a.order[blockIdx.x], smem_raw);
+  }
+}
+
 constexpr int kSmallThreads = 256, kLargeThreads = 1024;
 constexpr size_t sort_smem(int cap, int threads) { return (size_t)cap * 16 + (size_t)(threads / 32) * 256 * 4; }
 
 }  // namespace
 
-cudaError_t launch_tile_scan(int tiles, const ImageState& img, cudaStream_t s) {
+cudaError_t launch_tile_scan(int tiles, const ImageState& img, uint32_t r_cap, cudaStream_t s) {
   tile_scan_kernel<<<1, 1024, 0, s>>>(tiles, img.tile_count, img.ranges, img.tile_order, img.tile_last, img.summary,
-                                      (uint32_t)kSmallMax);
+                                      (uint32_t)kSmallMax, r_cap, (uint32_t)kLargeCap);
   return cudaGetLastError();
 }
 
@@ -406,7 +430,7 @@ cudaError_t launch_scatter_instances(int P, const GeomState& g, const int* radii
                                      const BinningState& b, int grid_x, int grid_y, cudaStream_t s) {
   uint32_t* seg_keys = reinterpret_cast<uint32_t*>(b.keys_unsorted);
   scatter_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, radii, img.tile_count, seg_keys, b.vals_unsorted,
-                                                          grid_x, grid_y);
+                                                          grid_x, grid_y, img.summary);
   return cudaGetLastError();
 }
 
@@ -417,16 +441,23 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<kSmallCap, kSmallThreads>,
+    cudaError_t e = cudaFuncSetAttribute(tile_sort_kernel<kSmallCap, kSmallThreads, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSmall);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tile_sort_kernel<kLargeCap, kLargeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)kSmemLarge);
+    e = cudaFuncSetAttribute(tile_sort_kernel<kLargeCap, kLargeThreads, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLarge);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
+  static int sm_count[64] = {};
+  int sms = 148;
+  if (dev >= 0 && dev < 64) {
+    if (!sm_count[dev] && cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sm_count[dev] = 148;
+    sms = sm_count[dev];
+  }
   TileSortArgs a;
-  a.ranges = img.ranges, a.order = img.tile_order;
+  a.ranges = img.ranges, a.order = img.tile_order, a.summary = img.summary;
   a.seg_keys = reinterpret_cast<const uint32_t*>(b.keys_unsorted), a.seg_vals = b.vals_unsorted;
   a.rec = g.rec, a.keys_out = b.keys, a.vals_out = b.vals, a.inst = b.inst, a.aux = b.aux, a.grid_x = grid_x;
   // The few long lists (one 1024-thread CTA each, all of an SM's shared memory) and the many short ones are
@@ -437,7 +468,7 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
   };
   static thread_local Side side[64];
   Side* sd = nullptr;
-  if (n_large > 0 && dev >= 0 && dev < 64) {
+  if (n_large != 0 && dev >= 0 && dev < 64) {  // n_large < 0: not known on the host (sync-free forward)
     sd = &side[dev];
     if (!sd->stream) {
       if (cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -456,14 +487,15 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
     if (e != cudaSuccess) return e;
     small_stream = sd->stream;
   }
-  if (n_large > 0) {  // the longest lists come first in tile_order
+  if (n_large != 0) {  // the longest lists come first in tile_order; the kernel reads their number on the device
     a.min_len = (uint32_t)kSmallMax, a.max_len = (uint32_t)kLargeCap;
-    tile_sort_kernel<kLargeCap, kLargeThreads><<<n_large, kLargeThreads, kSmemLarge, s>>>(a);
+    const int grid = n_large > 0 ? (n_large < sms ? n_large : sms) : (tiles < sms ? tiles : sms);
+    tile_sort_kernel<kLargeCap, kLargeThreads, true><<<grid, kLargeThreads, kSmemLarge, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   a.min_len = 0, a.max_len = (uint32_t)kSmallMax;
-  tile_sort_kernel<kSmallCap, kSmallThreads><<<tiles, kSmallThreads, kSmemSmall, small_stream>>>(a);
+  tile_sort_kernel<kSmallCap, kSmallThreads, false><<<tiles, kSmallThreads, kSmemSmall, small_stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (sd) {

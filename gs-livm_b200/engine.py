@@ -40,7 +40,12 @@ class _Arena:
 class RasterContext:
     """One (Gaussian set, image size) rasterization context on one device."""
 
-    def __init__(self, P: int, M: int, width: int, height: int, device, sh_degree: int = 3):
+    def __init__(self, P: int, M: int, width: int, height: int, device, sh_degree: int = 3, sync_free: bool = True):
+        """sync_free: after a first frame has told how many (Gaussian, tile) instances the scene produces, later
+        forwards go through gsr_forward_presized — the binning arena is kept 30 % larger than the largest R seen
+        and the host never waits for the GPU inside a forward. `check()` (any time after a synchronisation the
+        caller does anyway) tells whether every frame since the last check fitted; a frame that did not is
+        redone through the synchronous path by `forward(..., redo=True)`."""
         self.lib = _lib.load()
         self.P, self.M, self.W, self.H, self.D = int(P), int(M), int(width), int(height), int(sh_degree)
         self.device = torch.device(device)
@@ -64,9 +69,15 @@ class RasterContext:
         self.num_rendered = 0
         self._fwd_args: Optional[_lib.FwdArgs] = None
         self._keep = None
+        self.sync_free = bool(sync_free)
+        self._capacity = 0  # instances the binning arena is carved for (0: not known yet)
+        self._status = torch.zeros((16, 4), dtype=torch.int32).pin_memory()  # ring of gsr_async_status
+        self._status_head = 0
+        self._unchecked = []  # ring slots written since the last check()
 
     # ------------------------------------------------------------------------------------------------
-    def forward(self, scene: Dict[str, torch.Tensor], cam: Camera, scale_modifier: float = 1.0, debug: bool = False):
+    def forward(self, scene: Dict[str, torch.Tensor], cam: Camera, scale_modifier: float = 1.0, debug: bool = False,
+                redo: bool = False):
         a = _lib.FwdArgs()
         a.P, a.D, a.M, a.width, a.height = self.P, self.D, self.M, self.W, self.H
         a.background, a.means3D, a.shs = scene["background"].data_ptr(), scene["means3D"].data_ptr(), scene["shs"].data_ptr()
@@ -76,14 +87,46 @@ class RasterContext:
         a.tan_fovx, a.tan_fovy, a.prefiltered = float(cam.tanfovx), float(cam.tanfovy), 0
         a.out_color, a.out_depth, a.out_acc = self.out_color.data_ptr(), self.out_depth.data_ptr(), self.out_acc.data_ptr()
         a.radii, a.debug = self.radii.data_ptr(), int(debug)
-        n = C.c_int(0)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._fwd_args, self._keep = a, (scene, cam)
+        if self.sync_free and self._capacity > 0 and not redo:
+            slot = self._status_head % self._status.shape[0]
+            self._status_head += 1
+            if len(self._unchecked) >= self._status.shape[0] - 1:
+                self.check()  # the ring is about to wrap: look at what is pending (synchronises)
+            self._unchecked.append(slot)
+            need = self.lib.gsr_required_binning(self._capacity)
+            if self.binning.buf.numel() < need:  # (the previous frame's backward is over: same stream)
+                self.binning._alloc(None, need)
+            st = self.lib.gsr_forward_presized(C.byref(a), self.geom.buf.data_ptr(), self.binning.buf.data_ptr(),
+                                               self._capacity, self.image.buf.data_ptr(), stream,
+                                               self._status[slot].data_ptr())
+            _lib.check(st, "gsr_forward_presized")
+            self.num_rendered = self._capacity  # what the matching backward carves the binning arena with
+            return self.out_color, self.out_depth, self.out_acc
+        n = C.c_int(0)
         st = self.lib.gsr_forward(C.byref(a), self.geom.fn, None, self.binning.fn, None, self.image.fn, None, stream,
                                   C.byref(n))
         _lib.check(st, "gsr_forward")
         self.num_rendered = n.value
-        self._fwd_args, self._keep = a, (scene, cam)
+        if self.sync_free:  # the frames to come get a binning arena with 30 % head-room over this R
+            self._capacity = max(self._capacity, int(n.value * 1.3) + 65536)
         return self.out_color, self.out_depth, self.out_acc
+
+    def check(self) -> bool:
+        """True if every sync-free forward since the last call fitted its presized binning arena. Synchronises
+        the current stream. After a False the arena is re-learned by the next forward (synchronous path)."""
+        if not self._unchecked:
+            return True
+        torch.cuda.current_stream(self.device).synchronize()
+        st = self._status[self._unchecked]
+        self._unchecked = []
+        ok = bool((st[:, 3] == 0).all())
+        if ok:
+            self.last_rendered = int(st[-1, 0])
+        else:
+            self._capacity = 0 if bool((st[:, 3] == 2).any()) else int(st[:, 0].max().item() * 1.3) + 65536
+        return ok
 
     def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False) -> Dict[str, torch.Tensor]:
         """Gradients of the last forward. The reference's caller zero-fills all nine outputs before every

@@ -181,6 +181,24 @@ GSR_API int gsr_forward(const gsr_fwd_args* args,
                 gsr_alloc_fn image_alloc, void* image_ctx,
                 void* stream, int* num_rendered);
 
+/* Sync-free forward. The reference reads the number of instances R back to the host in the
+ * middle of every forward (blocking cudaMemcpy, rasterizer_impl.cu:277) because its binning buffer is sized from
+ * it. Here the caller provides all three buffers up front — geometry and image of gsr_required_geom/_image bytes,
+ * binning of gsr_required_binning(R_capacity) bytes — and nothing waits for the GPU: every kernel reads what it
+ * needs from device memory. `status` (pinned host memory, may be NULL) receives the counters through an
+ * asynchronous copy on `stream`; it is valid once the caller has synchronised with the stream for its own
+ * reasons (e.g. to read the loss). If status->overflow != 0 the frame did not fit (1: R > R_capacity, 2: a tile
+ * list longer than the per-tile sort handles) and the outputs are those of an EMPTY scene: redo the frame with
+ * gsr_forward. The matching gsr_backward takes R = R_capacity and the same three buffers. */
+typedef struct gsr_async_status {
+  uint32_t num_rendered; /* R */
+  uint32_t longest_list;
+  uint32_t long_lists;
+  uint32_t overflow;
+} gsr_async_status;
+GSR_API int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, char* binning_buffer, int R_capacity,
+                                 char* image_buffer, void* stream, gsr_async_status* status);
+
 GSR_API int gsr_backward(const gsr_bwd_args* args, void* stream);
 
 GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -71,12 +71,13 @@ def test_raster_context_matches_operator_and_reuses_memory(built_library, cuda_d
     ctx = engine.RasterContext(case.P, 16, case.width, case.height, dev, 3)
     raw = helpers.run_ours(case, dev)
     ptrs = None
-    for _ in range(3):
+    for it in range(4):  # the first forward is synchronous and sizes the binning arena; the others never wait
         color, depth, acc = ctx.forward(sc, cam)
         g = ctx.backward(case.dL_dcolor.to(dev), case.dL_dacc.to(dev))
         torch.cuda.synchronize()
+        assert ctx.check(), "the frame must fit the presized binning arena"
         now = (ctx.geom.buf.data_ptr(), ctx.binning.buf.data_ptr(), ctx.image.buf.data_ptr())
-        assert ptrs is None or ptrs == now, "scratch arenas must be reused, not re-allocated"
+        assert it < 2 or ptrs == now, "scratch arenas must be reused, not re-allocated"
         ptrs = now
         np.testing.assert_array_equal(helpers.bits(color.cpu().numpy()), helpers.bits(raw["out_color"]))
         np.testing.assert_array_equal(helpers.bits(depth.cpu().numpy()), helpers.bits(raw["out_depth"]))
@@ -90,6 +91,34 @@ def test_raster_context_matches_operator_and_reuses_memory(built_library, cuda_d
     times = ctx.stage_times()
     ctx.stage_timing(False)
     assert all(times[k] > 0 for k in ("preprocess", "sort", "blend_fwd", "blend_bwd", "geom_bwd"))
+
+
+def test_sync_free_forward_reports_a_frame_that_does_not_fit(built_library, cuda_device):
+    """gsr_forward_presized with a binning capacity below R: nothing is written out of bounds, the outputs are
+    those of an empty scene, the status says so, and redoing the frame synchronously gives the right image."""
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import engine, scene
+    case = helpers.scene_case(20_000, 504, 3, intr=SMALL, heavy=True)
+    dev = cuda_device
+    sc = dict(means3D=case.means3D.to(dev), scales=case.scales.to(dev), rotations=case.rotations.to(dev),
+              opacities=case.opacities.to(dev), shs=case.shs.to(dev), background=case.background.to(dev))
+    cam = scene.Camera(case.width, case.height, case.tanfovx, case.tanfovy, case.viewmatrix, case.projmatrix,
+                       case.camera_center).to(dev)
+    raw = helpers.run_ours(case, dev, backward=False)
+    ctx = engine.RasterContext(case.P, 16, case.width, case.height, dev, 3)
+    ctx.forward(sc, cam)
+    assert ctx.num_rendered == raw["num_rendered"] and ctx._capacity > ctx.num_rendered
+    ctx._capacity = raw["num_rendered"] // 2  # pretend the arena was sized for a much emptier view
+    color, _, acc = ctx.forward(sc, cam)
+    g = ctx.backward(case.dL_dcolor.to(dev), case.dL_dacc.to(dev))
+    assert not ctx.check()
+    assert float(acc.abs().max()) == 0.0 and all(float(v.abs().max()) == 0.0 for v in g.values())
+    color, depth, acc = ctx.forward(sc, cam, redo=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(helpers.bits(color.cpu().numpy()), helpers.bits(raw["out_color"]))
+    color, depth, acc = ctx.forward(sc, cam)  # and the arena has been re-learned
+    assert ctx.check()
+    np.testing.assert_array_equal(helpers.bits(color.cpu().numpy()), helpers.bits(raw["out_color"]))
 
 
 @pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/gsr_dropin_ext.so not built (make -C oracle dropin)")

@@ -45,7 +45,9 @@ def _worker(rank, world, port, n_views, q):
     step = window.WindowStep(n_views, g0.numel(), "cpu", render_view)
     stats = step.run()
     window.sgd_update_(params, step.flat, lr=0.1)
-    q.put((rank, step.views, step.flat.clone(), [p.clone() for p in params], stats))
+    # numpy copies travel by value; torch tensors would be handed over as shared-memory descriptors that the
+    # parent can only open while this process is still alive
+    q.put((rank, step.views, step.flat.numpy().copy(), [p.numpy().copy() for p in params], stats))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,6 +66,8 @@ def test_two_ranks_shard_views_and_stay_identical():
         p.join(60)
         assert p.exitcode == 0
     (r0, v0, f0, p0, s0), (r1, v1, f1, p1, s1) = res
+    f0, f1 = torch.from_numpy(f0), torch.from_numpy(f1)
+    p0, p1 = [torch.from_numpy(a) for a in p0], [torch.from_numpy(a) for a in p1]
     assert v0 == [0, 2] and v1 == [1, 3]
     assert torch.equal(f0, f1), "all-reduced gradient must be bit-identical on every rank"
     for a, b in zip(p0, p1):
