@@ -78,15 +78,68 @@ class _ScratchAllocator:
         return self._cell[0]
 
 
+class RenderArena:
+    """Persistent scratch for a training loop: grow-only geometry / image / binning buffers
+    that successive renders reuse, and — once a first render has told how many (Gaussian, tile) instances the
+    scene produces — the sync-free forward (gsr_forward_presized): the binning buffer is kept 30 % larger than
+    the largest instance count seen and the host never waits for the GPU inside a render.
+
+    Pass it as `GaussianRasterizer(settings, arena=...)`. One arena serves ONE render at a time: the buffers of
+    a render are reused by the next one, so a render's backward must run before the arena renders again (use one
+    arena per view when several views are rendered before a joint backward). `check()` — after any
+    synchronisation the loop does anyway, e.g. reading the loss — tells whether every render since the last call
+    fitted; a render that did not produced an empty image and has to be repeated."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._bufs = {k: torch.empty(0, dtype=torch.uint8, device=self.device) for k in ("geom", "binning", "image")}
+        self._fns = {k: _lib.ALLOC_FN(lambda _ctx, n, _k=k: self._grow(_k, n)) for k in self._bufs}
+        self.capacity = 0
+        self._status = torch.zeros((16, 4), dtype=torch.int32).pin_memory()
+        self._head = 0
+        self._unchecked = []
+
+    def _grow(self, kind: str, nbytes: int) -> int:
+        if self._bufs[kind].numel() < nbytes:
+            self._bufs[kind] = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return self._bufs[kind].data_ptr()
+
+    def buffer(self, kind: str) -> torch.Tensor:
+        return self._bufs[kind]
+
+    def learn(self, num_rendered: int) -> None:
+        self.capacity = max(self.capacity, int(num_rendered * 1.3) + 65536)
+
+    def next_status(self) -> int:
+        if len(self._unchecked) >= self._status.shape[0] - 1:
+            self.check()
+        slot = self._head % self._status.shape[0]
+        self._head += 1
+        self._unchecked.append(slot)
+        return self._status[slot].data_ptr()
+
+    def check(self) -> bool:
+        if not self._unchecked:
+            return True
+        torch.cuda.current_stream(self.device).synchronize()
+        st = self._status[self._unchecked]
+        self._unchecked = []
+        ok = bool((st[:, 3] == 0).all())
+        if not ok:
+            self.capacity = 0 if bool((st[:, 3] == 2).any()) else int(st[:, 0].max().item() * 1.3) + 65536
+        return ok
+
+
 def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
 def rasterize_gaussians_cuda(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                              viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree,
-                             campos, prefiltered, debug):
+                             campos, prefiltered, debug, arena: Optional[RenderArena] = None):
     """-> (num_rendered, out_color[3,H,W], out_depth[1,H,W], out_acc[1,H,W], radii[P], geomBuffer,
-    binningBuffer, imgBuffer), exactly the reference's tuple."""
+    binningBuffer, imgBuffer), exactly the reference's tuple. With an `arena` the three buffers are the arena's
+    and, on the sync-free path, num_rendered is the arena's capacity (what the backward must be given)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -95,11 +148,15 @@ def rasterize_gaussians_cuda(background, means3D, colors, opacity, scales, rotat
     dev = means3D.device
     P, H, W = means3D.size(0), int(image_height), int(image_width)
 
-    out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
-    out_depth = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
-    out_acc = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
-    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = _ScratchAllocator(dev), _ScratchAllocator(dev), _ScratchAllocator(dev)
+    # the reference fills these with zeros (rasterize_points.cu:78-81); our kernels write every pixel of every
+    # tile and every Gaussian's radius, so only the P == 0 case (no kernel runs) needs the fill
+    fresh = torch.empty if P != 0 else torch.zeros
+    out_color = fresh((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+    out_depth = fresh((1, H, W), dtype=torch.float32, device=dev)
+    out_acc = fresh((1, H, W), dtype=torch.float32, device=dev)
+    radii = fresh((P,), dtype=torch.int32, device=dev)
+    if arena is None:
+        geom, binning, img = _ScratchAllocator(dev), _ScratchAllocator(dev), _ScratchAllocator(dev)
 
     rendered = 0
     if P != 0:
@@ -118,10 +175,29 @@ def rasterize_gaussians_cuda(background, means3D, colors, opacity, scales, rotat
         a.radii, a.debug = radii.data_ptr(), int(bool(debug))
         n = C.c_int(0)
         with torch.cuda.device(dev):
-            st = lib.gsr_forward(C.byref(a), geom.fn, None, binning.fn, None, img.fn, None, _stream_ptr(dev),
-                                 C.byref(n))
-        _lib.check(st, "gsr_forward")
-        rendered = n.value
+            if arena is None:
+                st = lib.gsr_forward(C.byref(a), geom.fn, None, binning.fn, None, img.fn, None, _stream_ptr(dev),
+                                     C.byref(n))
+                _lib.check(st, "gsr_forward")
+                rendered = n.value
+            elif arena.capacity > 0:
+                arena._grow("geom", lib.gsr_required_geom(P))
+                arena._grow("image", lib.gsr_required_image(W, H))
+                arena._grow("binning", lib.gsr_required_binning(arena.capacity))
+                st = lib.gsr_forward_presized(C.byref(a), arena.buffer("geom").data_ptr(),
+                                              arena.buffer("binning").data_ptr(), arena.capacity,
+                                              arena.buffer("image").data_ptr(), _stream_ptr(dev), arena.next_status())
+                _lib.check(st, "gsr_forward_presized")
+                rendered = arena.capacity
+            else:
+                st = lib.gsr_forward(C.byref(a), arena._fns["geom"], None, arena._fns["binning"], None,
+                                     arena._fns["image"], None, _stream_ptr(dev), C.byref(n))
+                _lib.check(st, "gsr_forward")
+                rendered = n.value
+                arena.learn(rendered)
+    if arena is not None:
+        return (rendered, out_color, out_depth, out_acc, radii, arena.buffer("geom"), arena.buffer("binning"),
+                arena.buffer("image"))
     return rendered, out_color, out_depth, out_acc, radii, geom.tensor, binning.tensor, img.tensor
 
 
@@ -139,16 +215,19 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
     # outputs are uninitialised instead (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element of what it
     # computes; only what it does not touch on this argument combination is zeroed here.
     have_cov = cov3D_precomp is not None and cov3D_precomp.numel() != 0
-    fresh = torch.empty if P != 0 else torch.zeros
-    dL_dmeans3D = fresh((P, 3), **opts)
-    dL_dmeans2D = fresh((P, 3), **opts)
-    dL_dcolors = fresh((P, NUM_CHANNELS), **opts)
-    dL_dconic = fresh((P, 2, 2), **opts)
-    dL_dopacity = fresh((P, 1), **opts)
-    dL_dcov3D = fresh((P, 6), **opts)
-    dL_dsh = fresh((P, M, 3), **opts)
-    dL_dscales = (torch.zeros if have_cov else fresh)((P, 3), **opts)
-    dL_drotations = (torch.zeros if have_cov else fresh)((P, 4), **opts)
+    widths = (3, 3, NUM_CHANNELS, 4, 1, 6, M * 3, 3, 4)  # one allocation, nine 256-byte aligned views
+    starts, off = [], 0
+    for w in widths:
+        starts.append(off)
+        off += (P * w + 63) // 64 * 64
+    flat = (torch.empty if P != 0 else torch.zeros)((off,), **opts)
+    views = [flat[st:st + P * w] for st, w in zip(starts, widths)]
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors = views[0].view(P, 3), views[1].view(P, 3), views[2].view(P, NUM_CHANNELS)
+    dL_dconic, dL_dopacity, dL_dcov3D = views[3].view(P, 2, 2), views[4].view(P, 1), views[5].view(P, 6)
+    dL_dsh, dL_dscales, dL_drotations = views[6].view(P, M, 3), views[7].view(P, 3), views[8].view(P, 4)
+    if have_cov and P != 0:
+        dL_dscales.zero_()
+        dL_drotations.zero_()
 
     if P != 0:
         keep = [_f32c(t) for t in (background, means3D, sh, colors, scales, rotations, cov3D_precomp, viewmatrix,
@@ -194,13 +273,13 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings: GaussianRasterizationSettings):
+                raster_settings: GaussianRasterizationSettings, arena: Optional[RenderArena] = None):
         rs = raster_settings
         (num_rendered, color, out_depth, out_acc, radii, geomBuffer, binningBuffer, imgBuffer) = \
             rasterize_gaussians_cuda(rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
                                      cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
                                      rs.image_height, rs.image_width, sh, rs.sh_degree, rs.camera_center,
-                                     rs.prefiltered, False)
+                                     rs.prefiltered, False, arena)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
@@ -224,15 +303,17 @@ class _RasterizeGaussians(torch.autograd.Function):
             rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_acc, sh, rs.sh_degree,
             rs.camera_center, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, False)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
-                grad_cov3Ds_precomp, None)
+                grad_cov3Ds_precomp, None, None)
 
 
 class GaussianRasterizer(torch.nn.Module):
     """Reference: GaussianRasterizer (include/gs/gs/rasterizer.cuh:52-80, src/gs/rasterizer.cu:152-288)."""
 
-    def __init__(self, raster_settings: GaussianRasterizationSettings):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, arena: Optional[RenderArena] = None):
+        """arena (ours, optional): persistent scratch + sync-free forward for training loops, see RenderArena."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.arena = arena
 
     def mark_visible(self, positions: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
@@ -256,4 +337,4 @@ class GaussianRasterizer(torch.nn.Module):
         rs = rs._replace(bg=rs.bg.to(dev), viewmatrix=rs.viewmatrix.to(dev), projmatrix=rs.projmatrix.to(dev),
                          camera_center=rs.camera_center.to(dev))
         return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                         cov3D_precomp, rs)
+                                         cov3D_precomp, rs, self.arena)

@@ -47,6 +47,35 @@ def test_autograd_through_gaussian_rasterizer(built_library, cuda_device):
     assert_grad("dL_dmean2D", means2D.grad.cpu().numpy(), raw["dL_dmean2D"])
 
 
+def test_render_arena_gives_the_same_gradients_without_waiting(built_library, cuda_device):
+    """GaussianRasterizer(settings, arena=RenderArena): first render synchronous (learns the instance count), the
+    following ones through gsr_forward_presized; images bit-identical, gradients as without an arena."""
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import rasterizer, scene
+    case = helpers.scene_case(6000, 502, 3, intr=SMALL, heavy=True)
+    dev = cuda_device
+    cam = scene.Camera(case.width, case.height, case.tanfovx, case.tanfovy, case.viewmatrix, case.projmatrix,
+                       case.camera_center)
+    rs = scene.settings_for(cam, case.background, case.sh_degree)
+    raw = helpers.run_ours(case, dev)
+    arena = rasterizer.RenderArena(dev)
+    wC, wS = case.dL_dcolor.to(dev), case.dL_dacc.to(dev)
+    for it in range(3):
+        leaves = {k: _leaf(getattr(case, k), dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        color, radii, depth, acc = rasterizer.GaussianRasterizer(rs, arena=arena)(
+            leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+            rotations=leaves["rotations"])
+        ((color * wC).sum() + (acc * wS).sum()).backward()
+        torch.cuda.synchronize()
+        assert arena.check() and (it == 0 or arena.capacity > raw["num_rendered"])
+        np.testing.assert_array_equal(helpers.bits(color.detach().cpu().numpy()), helpers.bits(raw["out_color"]))
+        np.testing.assert_array_equal(radii.cpu().numpy(), raw["radii"])
+        for leaf, name in (("means3D", "dL_dmean3D"), ("shs", "dL_dsh"), ("opacities", "dL_dopacity"),
+                           ("scales", "dL_dscale"), ("rotations", "dL_drot")):
+            assert_grad(name, leaves[leaf].grad.cpu().numpy().reshape(raw[name].shape), raw[name])
+
+
 def test_mark_visible_matches_oracle(built_library, cuda_device):
     import gs_livm_b200  # noqa: F401
     from gs_livm_b200 import rasterizer
