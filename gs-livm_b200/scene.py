@@ -220,3 +220,47 @@ def settings_for(cam: Camera, background: torch.Tensor, sh_degree: int, scale_mo
     from .rasterizer import GaussianRasterizationSettings
     return GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, background, scale_modifier,
                                          cam.viewmatrix, cam.projmatrix, sh_degree, cam.camera_center, False)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs[0] of BASELINE.json: one NTU-VIRAL-shaped frame as the producer side sees it — a LiDAR sweep of the
+# street canyon plus the colour image of the keyframe camera. The VGPR / Gaussian-initialisation restatement that
+# turns it into Gaussians is test infrastructure (oracle/vgpr.py); this only makes the synthetic sensor data.
+def lidar_frame(n_points: int, seed: int, length: float = 30.0, width: float = 11.0, height: float = 6.0,
+                noise: float = 0.005) -> np.ndarray:
+    """n_points returns on the canyon's surfaces, area-uniform, `noise` m of range noise along the normal."""
+    rng = np.random.default_rng(seed)
+    planes = _planes(length, width, height)
+    area = np.array([ue * ve for (_, _, _, _, ue, ve) in planes])
+    counts = rng.multinomial(n_points, area / area.sum())
+    out = []
+    for (org, ua, va, na, ue, ve), c in zip(planes, counts):
+        p = np.zeros((c, 3))
+        p[:, ua] = rng.random(c) * ue
+        p[:, va] = rng.random(c) * ve
+        p += org
+        p[:, na] += rng.normal(0.0, noise, size=c)
+        out.append(p)
+    pts = np.concatenate(out)
+    return pts[rng.permutation(pts.shape[0])]
+
+
+def frame_colour(cam: Camera, intr: Dict = NTU):
+    """Colour look-up the way gpProcess::getColors does it (src/gp3d/gpprocess.cu:917-969, without lens
+    distortion): project into the keyframe image, drop what falls outside. The image is procedural."""
+    view = cam.viewmatrix.cpu().numpy().astype(np.float64)  # stored transposed: row-vector convention
+
+    def colour_of(xyz: np.ndarray):
+        pc = np.concatenate([xyz.astype(np.float64), np.ones((xyz.shape[0], 1))], axis=1) @ view
+        z = pc[:, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = (intr["fx"] * pc[:, 0] / z + 0.5 * intr["width"]).astype(np.int64)
+            v = (intr["fy"] * pc[:, 1] / z + 0.5 * intr["height"]).astype(np.int64)
+        valid = (z > 0.2) & (u >= 0) & (u < intr["width"]) & (v >= 0) & (v < intr["height"])
+        r = 127.5 + 100.0 * np.sin(0.045 * u) * np.cos(0.03 * v)
+        g = 127.5 + 100.0 * np.sin(0.02 * u + 0.05 * v)
+        b = 127.5 + 100.0 * np.cos(0.06 * v)
+        rgb = np.clip(np.stack([r, g, b], axis=1), 0, 255).astype(np.uint8)
+        return rgb, valid
+
+    return colour_of
