@@ -337,11 +337,28 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   const float focal_x = a.width / (2.0f * a.tan_fovx);
 
   if (a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) {  // the four accumulated outputs start from zero
-    const size_t n = (size_t)a.P * sizeof(float);
-    GSR_CUDA(cudaMemsetAsync(a.dL_dmean2D, 0, 3 * n, stream), "zero dL_dmean2D");
-    GSR_CUDA(cudaMemsetAsync(a.dL_dconic, 0, 4 * n, stream), "zero dL_dconic");
-    GSR_CUDA(cudaMemsetAsync(a.dL_dopacity, 0, n, stream), "zero dL_dopacity");
-    GSR_CUDA(cudaMemsetAsync(a.dL_dcolor, 0, 3 * n, stream), "zero dL_dcolor");
+    // adjacent arrays (one flat gradient buffer, as gs_livm_b200.engine lays them out) are cleared by one memset
+    struct Span {
+      char* p;
+      size_t n;
+    } spans[4] = {{reinterpret_cast<char*>(a.dL_dmean2D), 3 * (size_t)a.P * sizeof(float)},
+                  {reinterpret_cast<char*>(a.dL_dconic), 4 * (size_t)a.P * sizeof(float)},
+                  {reinterpret_cast<char*>(a.dL_dopacity), (size_t)a.P * sizeof(float)},
+                  {reinterpret_cast<char*>(a.dL_dcolor), 3 * (size_t)a.P * sizeof(float)}};
+    for (int i = 0; i < 4; ++i)
+      for (int j = i + 1; j < 4; ++j)
+        if (spans[j].p < spans[i].p) {
+          Span t = spans[i];
+          spans[i] = spans[j], spans[j] = t;
+        }
+    for (int i = 0; i < 4;) {
+      char* p = spans[i].p;
+      size_t n = spans[i].n;
+      int j = i + 1;
+      while (j < 4 && spans[j].p == p + n) n += spans[j++].n;
+      GSR_CUDA(cudaMemsetAsync(p, 0, n, stream), "zero accumulated gradients");
+      i = j;
+    }
   }
   if (a.R > 0) {
     const char* impl = getenv("GSR_BWD_IMPL");
