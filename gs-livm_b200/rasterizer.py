@@ -107,6 +107,14 @@ class RenderArena:
     def buffer(self, kind: str) -> torch.Tensor:
         return self._bufs[kind]
 
+    def reserve(self, lib, P: int, W: int, H: int) -> None:
+        key = (P, W, H, self.capacity)
+        if key != getattr(self, "_reserved", None):
+            self._grow("geom", lib.gsr_required_geom(P))
+            self._grow("image", lib.gsr_required_image(W, H))
+            self._grow("binning", lib.gsr_required_binning(self.capacity))
+            self._reserved = key
+
     def learn(self, num_rendered: int) -> None:
         self.capacity = max(self.capacity, int(num_rendered * 1.3) + 65536)
 
@@ -151,9 +159,8 @@ def rasterize_gaussians_cuda(background, means3D, colors, opacity, scales, rotat
     # the reference fills these with zeros (rasterize_points.cu:78-81); our kernels write every pixel of every
     # tile and every Gaussian's radius, so only the P == 0 case (no kernel runs) needs the fill
     fresh = torch.empty if P != 0 else torch.zeros
-    out_color = fresh((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
-    out_depth = fresh((1, H, W), dtype=torch.float32, device=dev)
-    out_acc = fresh((1, H, W), dtype=torch.float32, device=dev)
+    planes = fresh((NUM_CHANNELS + 2, H, W), dtype=torch.float32, device=dev)  # one allocation, three views
+    out_color, out_depth, out_acc = planes[:NUM_CHANNELS], planes[NUM_CHANNELS:NUM_CHANNELS + 1], planes[NUM_CHANNELS + 1:]
     radii = fresh((P,), dtype=torch.int32, device=dev)
     if arena is None:
         geom, binning, img = _ScratchAllocator(dev), _ScratchAllocator(dev), _ScratchAllocator(dev)
@@ -181,9 +188,7 @@ def rasterize_gaussians_cuda(background, means3D, colors, opacity, scales, rotat
                 _lib.check(st, "gsr_forward")
                 rendered = n.value
             elif arena.capacity > 0:
-                arena._grow("geom", lib.gsr_required_geom(P))
-                arena._grow("image", lib.gsr_required_image(W, H))
-                arena._grow("binning", lib.gsr_required_binning(arena.capacity))
+                arena.reserve(lib, P, W, H)
                 st = lib.gsr_forward_presized(C.byref(a), arena.buffer("geom").data_ptr(),
                                               arena.buffer("binning").data_ptr(), arena.capacity,
                                               arena.buffer("image").data_ptr(), _stream_ptr(dev), arena.next_status())
@@ -334,7 +339,9 @@ class GaussianRasterizer(torch.nn.Module):
         rotations = empty if rotations is None else rotations
         cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
         rs = self.raster_settings
-        rs = rs._replace(bg=rs.bg.to(dev), viewmatrix=rs.viewmatrix.to(dev), projmatrix=rs.projmatrix.to(dev),
-                         camera_center=rs.camera_center.to(dev))
+        if not (rs.bg.device == dev and rs.viewmatrix.device == dev and rs.projmatrix.device == dev
+                and rs.camera_center.device == dev):  # reference: .to(torch::kCUDA) on every call (rasterizer.cu:219-241)
+            rs = rs._replace(bg=rs.bg.to(dev), viewmatrix=rs.viewmatrix.to(dev), projmatrix=rs.projmatrix.to(dev),
+                             camera_center=rs.camera_center.to(dev))
         return _RasterizeGaussians.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
                                          cov3D_precomp, rs, self.arena)

@@ -18,12 +18,14 @@ class Case:
     """Inputs of one render in the reference's layout (CPU torch tensors)."""
 
     def __init__(self, means3D, scales, rotations, opacities, shs, background, viewmatrix, projmatrix, camera_center,
-                 tanfovx, tanfovy, width, height, sh_degree, colors_precomp=None, dL_dcolor=None, dL_dacc=None):
+                 tanfovx, tanfovy, width, height, sh_degree, colors_precomp=None, dL_dcolor=None, dL_dacc=None,
+                 cov3D_precomp=None):
         t = lambda a: None if a is None else torch.as_tensor(np.asarray(a)).contiguous()  # noqa: E731
         self.means3D, self.scales, self.rotations, self.opacities = t(means3D), t(scales), t(rotations), t(opacities)
         self.shs, self.background = t(shs), t(background)
         self.viewmatrix, self.projmatrix, self.camera_center = t(viewmatrix), t(projmatrix), t(camera_center)
         self.colors_precomp, self.dL_dcolor, self.dL_dacc = t(colors_precomp), t(dL_dcolor), t(dL_dacc)
+        self.cov3D_precomp = t(cov3D_precomp)  # given -> scales / rotations must be None (reference rasterizer.cu:165-169)
         self.tanfovx, self.tanfovy = float(tanfovx), float(tanfovy)
         self.width, self.height, self.sh_degree = int(width), int(height), int(sh_degree)
         self.P = int(self.means3D.shape[0])
@@ -70,7 +72,8 @@ def run_oracle_cpu(case: Case, backward: bool = True, nthreads: int = 4) -> Dict
     sc = cpu.OracleScene(case.means3D, case.opacities, case.background, case.viewmatrix, case.projmatrix,
                          case.camera_center, case.tanfovx, case.tanfovy, case.width, case.height,
                          shs=None if case.use_colors else case.shs, sh_degree=case.sh_degree,
-                         colors_precomp=case.colors_precomp, scales=case.scales, rotations=case.rotations)
+                         colors_precomp=case.colors_precomp, scales=case.scales, rotations=case.rotations,
+                         cov3D_precomp=case.cov3D_precomp)
     out = cpu.forward(sc, nthreads=nthreads)
     if backward and case.dL_dcolor is not None:
         out.update(cpu.backward(sc, out, case.dL_dcolor, case.dL_dacc, nthreads=nthreads))
@@ -97,8 +100,9 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile") ->
     shs = None if case.use_colors else case.shs
     bg, m3, sc, rot, op = d(case.background), d(case.means3D), d(case.scales), d(case.rotations), d(case.opacities)
     sh, col, view, proj, cam = d(shs), d(case.colors_precomp), d(case.viewmatrix), d(case.projmatrix), d(case.camera_center)
+    cov = d(case.cov3D_precomp)
     R, color, depth, acc, radii, gb, bb, ib = rasterizer.rasterize_gaussians_cuda(
-        bg, m3, col, op, sc, rot, 1.0, torch.empty(0, device=dev), view, proj, case.tanfovx, case.tanfovy,
+        bg, m3, col, op, sc, rot, 1.0, cov, view, proj, case.tanfovx, case.tanfovy,
         case.height, case.width, sh, case.sh_degree, cam, False, False)
     g, b, im = debug.geom_state(gb, case.P), debug.binning_state(bb, R), debug.image_state(ib, case.width, case.height)
     os.environ.pop("GSR_SORT", None)
@@ -110,7 +114,7 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile") ->
                ranges=im["ranges"], accum_alpha=im["accum_alpha"], n_contrib=im["n_contrib"], tile_last=im["tile_last"])
     if backward and case.dL_dcolor is not None:
         grads = rasterizer.rasterize_gaussians_backward_cuda(
-            bg, m3, radii, col, sc, rot, 1.0, torch.empty(0, device=dev), view, proj, case.tanfovx, case.tanfovy,
+            bg, m3, radii, col, sc, rot, 1.0, cov, view, proj, case.tanfovx, case.tanfovy,
             d(case.dL_dcolor), d(case.dL_dacc), sh, case.sh_degree, cam, gb, R, bb, ib, False)
         out.update(dict(zip(GRAD_NAMES, grads)))
     torch.cuda.synchronize()

@@ -108,6 +108,30 @@ def test_colors_precomp_and_sh_paths_agree_on_geometry(built_library, cuda_devic
         check_backward(b, ref, case)
 
 
+def test_precomputed_covariance_path(built_library, cuda_device):
+    """cov3D_precomp instead of scales + rotations (reference rasterizer.cu:165-169, forward.cu:239-247): with the
+    covariances the scale/rotation path computes, the render is bit-identical to it; the gradients stop at
+    dL_dcov3D (dL_dscale / dL_drot stay zero) and match the oracle."""
+    case = helpers.scene_case(5000, 151, 2, intr=SMALL, heavy=True)
+    ref_sr = helpers.run_oracle_cpu(case)
+    ours_sr = helpers.run_ours(case, cuda_device)
+    c = helpers.Case(case.means3D, None, None, case.opacities, case.shs, case.background, case.viewmatrix,
+                     case.projmatrix, case.camera_center, case.tanfovx, case.tanfovy, case.width, case.height,
+                     case.sh_degree, dL_dcolor=case.dL_dcolor, dL_dacc=case.dL_dacc,
+                     cov3D_precomp=np.asarray(ref_sr["cov3D"], np.float32))
+    ref = helpers.run_oracle_cpu(c)
+    ours = helpers.run_ours(c, cuda_device)
+    check_forward_exact(ours, ref, c, vs_cuda_reference=False)
+    vis = np.asarray(ref["radii"]) > 0
+    # (Gaussians culled only by the 0.3 m scale test of the scale/rotation path are not culled here)
+    both = vis & (np.asarray(ref_sr["radii"]) > 0)
+    np.testing.assert_array_equal(np.asarray(ours["radii"])[both], np.asarray(ours_sr["radii"])[both])
+    if not (ref["fragile"] != 0).any():
+        for name in ("dL_dmean2D", "dL_dcolor", "dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dsh"):
+            assert_grad(name, np.asarray(ours[name]).reshape(np.asarray(ref[name]).shape), ref[name])
+    assert float(np.abs(ours["dL_dscale"]).max()) == 0.0 and float(np.abs(ours["dL_drot"]).max()) == 0.0
+
+
 def _replicated(case, copies):
     """Every Gaussian `copies` times: exact depth ties everywhere, so the order of equal keys (ascending Gaussian
     id, what the reference's stable sort produces) is exercised."""

@@ -43,7 +43,8 @@ def main():
                 for n, v in ctx.stage_times().items():
                     acc[n] += max(v, 0.0)  # -1: the stage did not run on this path
                 tot += e0.elapsed_time(e1)
-        print(f"ours P={P} {W}x{H} R={ctx.num_rendered} visible={int((ctx.radii > 0).sum())}")
+        ctx.check()
+        print(f"ours P={P} {W}x{H} R={getattr(ctx, 'last_rendered', ctx.num_rendered)} visible={int((ctx.radii > 0).sum())}")
         for n in _lib.STAGES:
             print(f"  {n:12s} {acc[n] / iters * 1000:9.1f} us")
         print(f"  sum stages   {sum(acc.values()) / iters * 1000:9.1f} us ; fwd+bwd wall (events) {tot / iters * 1000:9.1f} us")
