@@ -222,15 +222,19 @@ def run_ours(args, rank, world, dev):
 
     sc_cpu, sc, cams_cpu, cams, dC, dS = build_workload(dev)
     H, W = cams[0].height, cams[0].width
-    ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE)
-    flat = ctx.param_grads()
+    from gs_livm_b200 import window
+    grad_floats = (3 + 16 * 3 + 3 + 4 + 1 + 3 + 4 + 3 + 6) * P_GAUSS  # RasterContext.GRAD_LAYOUT
+    param_floats = (3 + 16 * 3 + 3 + 4 + 1) * P_GAUSS                 # what the window all-reduces: 236 B/Gaussian
+    exchange = window.GradExchange(grad_floats, param_floats, dev) if world > 1 else None
+    ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE, grad_flat=exchange.flat if exchange else None)
+    assert ctx.param_grads().numel() == param_floats
 
     def step_resident(i):
         cam = cams[(rank + i) % WINDOW]
         ctx.forward(sc, cam)
         ctx.backward(dC, dS)
-        if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if exchange is not None:
+            exchange.allreduce_()  # libgsr_b200's own exchange over peer memory where available, else NCCL
 
     # ---- device-resident timing: W warm-up, K timed steps, CUDA events, max over ranks ----
     # RasterContext is sync-free after its first frame (gsr_forward_presized): the warm-up also walks the whole
@@ -379,7 +383,11 @@ def run_ours(args, rank, world, dev):
                                "(BASELINE.json configs[1]); one keyframe view per GPU per step, 8-pose window",
                    "P": P_GAUSS, "P_visible": P_v, "R": R, "sh_degree": SH_DEGREE, "width": W, "height": H,
                    "parallelism": "view-sharded window, replicated Gaussians" + (
-                       ", NCCL all-reduce of 236 B/Gaussian per step" if world > 1 else ""),
+                       ", all-reduce of 236 B/Gaussian per step: %s%s" % (
+                           {"multimem": "own NVSwitch-multicast kernel (multimem.ld_reduce/st)",
+                            "p2p": "own two-shot peer-to-peer kernels", "nccl": "NCCL"}[exchange.mode],
+                           "; calibration ms " + json.dumps(getattr(exchange, "calibration_ms", {}))
+                           if hasattr(exchange, "calibration_ms") else "") if world > 1 else ""),
                    "l2": "inputs (236 MB of Gaussians + 150 MB of per-frame state) exceed the 126 MB L2; no flush needed",
                    "library_kernels": LIB_KERNELS_PER_STEP},
         "clocks": clocks,

@@ -88,6 +88,8 @@ SYMBOLS = {
     "gsr_forward_presized": (C.c_int, [C.POINTER(FwdArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "gsr_backward": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
+    "gsr_window_allreduce_multimem": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+    "gsr_window_allreduce_p2p": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gsr_mark_visible": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_view_geom": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GeomView)]),
     "gsr_view_binning": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BinningView)]),

@@ -40,13 +40,15 @@ class _Arena:
 class RasterContext:
     """One (Gaussian set, image size) rasterization context on one device."""
 
-    def __init__(self, P: int, M: int, width: int, height: int, device, sh_degree: int = 3, sync_free: bool = True):
+    def __init__(self, P: int, M: int, width: int, height: int, device, sh_degree: int = 3, sync_free: bool = True,
+                 grad_flat: Optional[torch.Tensor] = None):
         """sync_free: after a first frame has told how many (Gaussian, tile) instances the scene produces, later
         forwards go through gsr_forward_presized — the binning arena is kept 30 % larger than the largest R seen
         and the host never waits for the GPU inside a forward. `check()` (any time after a synchronisation the
         caller does anyway) tells whether every frame since the last check fitted; a frame that did not is
         redone through the synchronous path by `forward(..., redo=True)`."""
         self.lib = _lib.load()
+        self.grad_numel = (3 + int(M) * 3 + 3 + 4 + 1 + 3 + 4 + 3 + 6) * int(P)
         self.P, self.M, self.W, self.H, self.D = int(P), int(M), int(width), int(height), int(sh_degree)
         self.device = torch.device(device)
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -59,7 +61,10 @@ class RasterContext:
         # multi-GPU window all-reduces (236 B per Gaussian at M = 16)
         sizes = [(n, (self.M * 3 if w is None else w)) for n, w in GRAD_LAYOUT]
         total = sum(w for _, w in sizes) * self.P
-        self.grad_flat = torch.zeros((total,), **f32)
+        # (a multi-GPU window passes its symmetric gradient buffer here: window.GradExchange.flat)
+        self.grad_flat = torch.zeros((total,), **f32) if grad_flat is None else grad_flat
+        if self.grad_flat.numel() < total or self.grad_flat.dtype != torch.float32:
+            raise ValueError("grad_flat must hold %d float32 values" % total)
         self.grads: Dict[str, torch.Tensor] = {}
         off = 0
         for n, w in sizes:

@@ -8,9 +8,12 @@ single-GPU kernels, and the per-Gaussian parameter gradients (59 floats = 236 B 
 3) are summed with ONE all-reduce over a flat buffer (NCCL over NVLink/NVSwitch) before the identical
 update is applied everywhere. There is no other cross-rank traffic on the data path.
 
-The collective is NCCL's (torch.distributed); there is no compute step whose output feeds the collective
-tile by tile — the gradients are only complete when the last tile of the backward has finished — so a
-fused compute+collective kernel has nothing to overlap here ("multi-GPU").
+The exchange is ours where the fabric allows it (GradExchange): the gradient buffer is a symmetric allocation
+(torch's _symmetric_memory: peer-mapped and, on NVSwitch systems, one multicast object) and the sum is taken by
+libgsr_b200's own kernels over peer memory — multimem.ld_reduce / multimem.st through the switch, or a two-shot
+peer-to-peer reduce-scatter + all-gather — bracketed by the symmetric-memory barrier. NCCL's all-reduce remains the
+fallback (no peer access, gloo/CPU tests). The gradients are only complete when the last kernel of the backward has
+finished, so there is no tile-by-tile overlap to be had with the compute ("multi-GPU").
 """
 from __future__ import annotations
 
@@ -32,6 +35,93 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+class GradExchange:
+    """Flat FP32 gradient buffer of one rank + the all-reduce (sum) of its first `numel_reduce` elements.
+
+    mode "multimem": NVSwitch multicast (gsr_window_allreduce_multimem); "p2p": two-shot over peer loads
+    (gsr_window_allreduce_p2p); "nccl": torch.distributed.all_reduce. `prefer` forces one of them ("auto": the
+    best the system offers). Every rank ends up with the same bits in all modes (each slice is summed once, in
+    one place, then distributed)."""
+
+    def __init__(self, numel_total: int, numel_reduce: int, device, group=None, prefer: str = "auto"):
+        self.group = group
+        self.n = int(numel_reduce)
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.mode, self.why, self.hdl, self.flat = "nccl", "", None, None
+        if self.world > 1 and self.device.type == "cuda" and self.n % 4 == 0 and prefer in ("auto", "multimem", "p2p"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                flat = symm_mem.empty(int(numel_total), dtype=torch.float32, device=self.device)
+                hdl = symm_mem.rendezvous(flat, grp)
+                flat.zero_()
+                self.flat, self.hdl = flat, hdl
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                self.mode = "multimem" if (mc != 0 and prefer != "p2p") else "p2p"
+                if prefer == "multimem" and mc == 0:
+                    self.why = "no multicast support: using p2p"
+            except Exception as e:  # no peer access / symmetric memory unavailable
+                self.why = "symmetric memory unavailable (%s)" % (repr(e)[:200],)
+        if self.flat is None:
+            self.flat = torch.zeros(int(numel_total), dtype=torch.float32, device=self.device)
+        if self.mode != "nccl":
+            from . import _lib
+            self._lib = _lib
+            self.lib = _lib.load()
+            import ctypes as C
+            off = int(getattr(self.hdl, "offset", 0) or 0)
+            self._mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) + (off if self.mode == "multimem" else 0)
+            ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
+            self._peers = (C.c_void_p * self.world)(*ptrs)
+            if ptrs[self.rank] != self.flat.data_ptr():
+                raise RuntimeError("symmetric buffer pointer mismatch")
+            if prefer == "auto":
+                self._calibrate()
+
+    def _calibrate(self) -> None:
+        """auto: time what the system offers on the real buffer (contents are zeros at this point) and keep the
+        fastest; the ranks agree on the choice through a MAX all-reduce of the timings."""
+        modes = (["multimem"] if self._mc else []) + ["p2p", "nccl"]
+        times = []
+        for m in modes:
+            self.mode = m
+            for _ in range(2):
+                self.allreduce_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                self.allreduce_()
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            times.append(e0.elapsed_time(e1) / 3)
+        t = torch.tensor(times, dtype=torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.calibration_ms = dict(zip(modes, (float(v) for v in t.tolist())))
+        self.mode = modes[int(torch.argmin(t).item())]
+
+    def allreduce_(self) -> torch.Tensor:
+        if self.world <= 1:
+            return self.flat
+        if self.mode == "nccl":
+            dist.all_reduce(self.flat[:self.n], op=dist.ReduceOp.SUM, group=self.group)
+            return self.flat
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.hdl.barrier(channel=0)  # every rank's gradients are complete
+        if self.mode == "multimem":
+            st = self.lib.gsr_window_allreduce_multimem(self._mc, self.n, self.rank, self.world, stream)
+            self._lib.check(st, "gsr_window_allreduce_multimem")
+        else:
+            st = self.lib.gsr_window_allreduce_p2p(self._peers, self.n, self.rank, self.world, 1, stream)
+            self._lib.check(st, "gsr_window_allreduce_p2p")
+            self.hdl.barrier(channel=1)  # every slice is reduced
+            st = self.lib.gsr_window_allreduce_p2p(self._peers, self.n, self.rank, self.world, 2, stream)
+            self._lib.check(st, "gsr_window_allreduce_p2p")
+        self.hdl.barrier(channel=2)  # every rank holds the sum; buffers may be rewritten
+        return self.flat
 
 
 class WindowStep:

@@ -201,6 +201,19 @@ GSR_API int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, ch
 
 GSR_API int gsr_backward(const gsr_bwd_args* args, void* stream);
 
+/* Gradient exchange of the view-sharded keyframe window (no counterpart in the reference, which is single-GPU;
+ * SURVEY.md 8e): all-reduce (sum, FP32) of the flat per-Gaussian parameter-gradient buffer, written against peer
+ * memory. The buffer is a symmetric allocation (same size on every rank, peer-mapped; e.g. torch's
+ * _symmetric_memory). The caller brackets the calls with a barrier across the ranks on the same stream.
+ *   gsr_window_allreduce_multimem: NVSwitch multicast path (multimem.ld_reduce + multimem.st); `multicast_buffer`
+ *     is the multicast mapping of the buffer.
+ *   gsr_window_allreduce_p2p: phase 1 = reduce-scatter, phase 2 = all-gather over plain peer loads, a barrier in
+ *     between; peer_buffers[r] = rank r's buffer as mapped into this process (host array of `world` pointers).
+ * n_floats must be a multiple of 4, buffers 16-byte aligned, world <= 16. */
+GSR_API int gsr_window_allreduce_multimem(void* multicast_buffer, size_t n_floats, int rank, int world, void* stream);
+GSR_API int gsr_window_allreduce_p2p(void* const* peer_buffers, size_t n_floats, int rank, int world, int phase,
+                                     void* stream);
+
 GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present, void* stream);
 
