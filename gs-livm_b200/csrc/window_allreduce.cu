@@ -16,6 +16,8 @@
 //    with plain peer loads) and all-gather (rank r copies the other reduced slices from their owners).
 // Both need every rank's gradients complete before, and every rank's stores complete after: the caller brackets
 // the kernels with the symmetric-memory barrier (gs_livm_b200/window.py), enqueued on the same stream.
+#include <cstdlib>
+
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -25,17 +27,19 @@ struct PeerPtrs {
   float4* p[16];
 };
 
+// .weak: plain (non-synchronising) accesses — ordering against the other ranks comes from the barriers around the
+// kernel, not from these instructions.
 __device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
   float4 v;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("multimem.ld_reduce.weak.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(mc)
                : "memory");
   return v;
 }
 __device__ __forceinline__ void multimem_st(float4* mc, const float4& v) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y),
-               "f"(v.z), "f"(v.w)
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
 }
 
@@ -46,7 +50,7 @@ __device__ __forceinline__ void slice_of(size_t n4, int rank, int world, size_t&
   hi = min(n4, lo + per);
 }
 
-constexpr int kInFlight = 4;  // independent 16-byte requests per thread
+constexpr int kInFlight = 8;  // independent 16-byte requests per thread
 
 __global__ void __launch_bounds__(512) allreduce_multimem_kernel(float4* mc, size_t n4, int rank, int world) {
   size_t lo, hi;
@@ -115,7 +119,11 @@ int grid_for(int dev) {
   static int sms[64] = {};
   if (dev < 0 || dev >= 64) return 148 * 2;
   if (!sms[dev] && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
-  return sms[dev] * 4;
+  static const int mult = [] {
+    const char* e = getenv("GSR_AR_GRID");  // tuning knob: CTAs per SM of the exchange kernels
+    return e ? atoi(e) : 2;
+  }();
+  return sms[dev] * (mult > 0 ? mult : 2);
 }
 
 }  // namespace
