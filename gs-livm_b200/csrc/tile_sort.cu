@@ -132,21 +132,31 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
     rw = rmaxx - rminx;
     ntiles = (uint32_t)rw * (uint32_t)(rmaxy - rminy);
   }
-  // lanes that append to the same tile share one atomicAdd on its cursor (see preprocess.cu)
+  // lanes that append to the same tile share one atomicAdd on its cursor (see preprocess.cu); two tiles per
+  // iteration so that two cursor round trips are in flight
+  auto tile_of = [&](uint32_t k) -> uint32_t {
+    if (k >= ntiles) return 0xffffffffu;
+    const int ry = (int)k / rw;
+    return (uint32_t)((rminy + ry) * grid_x + rminx + ((int)k - ry * rw));
+  };
   const uint32_t most = __reduce_max_sync(kFull, ntiles);
-  for (uint32_t k = 0; k < most; ++k) {
-    uint32_t t = 0xffffffffu;
-    if (k < ntiles) {
-      const int ry = (int)k / rw;
-      t = (uint32_t)((rminy + ry) * grid_x + rminx + ((int)k - ry * rw));
+  for (uint32_t k = 0; k < most; k += 2) {
+    const uint32_t t0 = tile_of(k), t1 = tile_of(k + 1);
+    const uint32_t p0 = __match_any_sync(kFull, t0), p1 = __match_any_sync(kFull, t1);
+    const int l0 = __ffs(p0) - 1, l1 = __ffs(p1) - 1;
+    uint32_t b0 = 0, b1 = 0;
+    if (t0 != 0xffffffffu && lane == l0) b0 = atomicAdd(&cursor[t0], (uint32_t)__popc(p0));
+    if (t1 != 0xffffffffu && lane == l1) b1 = atomicAdd(&cursor[t1], (uint32_t)__popc(p1));
+    b0 = __shfl_sync(kFull, b0, l0);
+    b1 = __shfl_sync(kFull, b1, l1);
+    const uint32_t below = (1u << lane) - 1u;
+    if (t0 != 0xffffffffu) {
+      const uint32_t pos = b0 + __popc(p0 & below);
+      seg_keys[pos] = depth_bits;
+      seg_vals[pos] = (uint32_t)idx;
     }
-    const uint32_t peers = __match_any_sync(kFull, t);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (t != 0xffffffffu && lane == leader) base = atomicAdd(&cursor[t], (uint32_t)__popc(peers));
-    base = __shfl_sync(kFull, base, leader);
-    if (t != 0xffffffffu) {
-      const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+    if (t1 != 0xffffffffu) {
+      const uint32_t pos = b1 + __popc(p1 & below);
       seg_keys[pos] = depth_bits;
       seg_vals[pos] = (uint32_t)idx;
     }
