@@ -43,7 +43,7 @@ P_GAUSS = 1_000_000
 SH_DEGREE = 3
 SEED = 20241017 + 2
 WINDOW = 8
-MY_KERNELS_PER_STEP = 8  # preprocess, tile_scan, scatter_instances, tile_sort (long + short lists), blend_fwd, blend_bwd, geom_bwd
+MY_KERNELS_PER_STEP = 9  # preprocess, tile_scan, scatter_instances, tile_sort (long + short lists), block_lists, blend_fwd, blend_bwd, geom_bwd
 LIB_KERNELS_PER_STEP = ("none on the per-tile binning path (cub scan + radix sort only when a tile list exceeds 12032 "
                         "instances); cudaMemsetAsync: tile counters + the 4 accumulated gradient arrays (44 B/Gaussian)")
 
@@ -285,20 +285,24 @@ def run_ours(args, rank, world, dev):
     copy_stream = torch.cuda.Stream(device=dev)
     target_dev = [torch.empty((3, H, W), device=dev) for _ in range(2)]
 
-    def step_e2e(i):
-        cpu_cam = cams_cpu[(rank + i) % WINDOW]
-        packed = host_cams[(rank + i) % WINDOW].to(dev, non_blocking=True)
-        # the step's target image goes up on a copy stream while the forward renders; the loss waits for it
+    cam_stage = torch.zeros(35).pin_memory()  # the step's camera, written by the host before the step is launched
+    cam_dev = torch.zeros(35, device=dev)
+
+    def step_body(j):
+        """One step as the operator's user writes it; nothing in here waits for the GPU, so it can be launched
+        eagerly or captured once and replayed (rasterizer.CapturedStep). j: which target staging buffer."""
         main = torch.cuda.current_stream(dev)
+        cam_dev.copy_(cam_stage, non_blocking=True)
+        # the step's target image goes up on a copy stream while the forward renders; the loss waits for it
         copy_stream.wait_stream(main)  # the buffer's previous use (two steps ago) is over
         with torch.cuda.stream(copy_stream):
-            target = target_dev[i % 2]
-            target.copy_(host_targets[i % 2], non_blocking=True)
+            target = target_dev[j]
+            target.copy_(host_targets[j], non_blocking=True)
         uploaded = torch.cuda.Event()
         uploaded.record(copy_stream)
-        rs = rasterizer.GaussianRasterizationSettings(H, W, cpu_cam.tanfovx, cpu_cam.tanfovy, sc["background"], 1.0,
-                                                      packed[:16].view(4, 4), packed[16:32].view(4, 4), SH_DEGREE,
-                                                      packed[32:35], False)
+        rs = rasterizer.GaussianRasterizationSettings(H, W, cams_cpu[0].tanfovx, cams_cpu[0].tanfovy, sc["background"],
+                                                      1.0, cam_dev[:16].view(4, 4), cam_dev[16:32].view(4, 4),
+                                                      SH_DEGREE, cam_dev[32:35], False)
         for t in list(leaves.values()) + [means2D]:
             t.grad = None
         color, radii, depth, acc = rasterizer.GaussianRasterizer(rs, arena=arena)(
@@ -311,6 +315,15 @@ def run_ours(args, rank, world, dev):
             for t in leaves.values():
                 dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    captured = [None, None]
+
+    def step_e2e(i):
+        cam_stage.copy_(host_cams[(rank + i) % WINDOW])  # 140 bytes, host to pinned host
+        if captured[i % 2] is not None:
+            captured[i % 2].replay()  # the whole step, copies included, is one graph launch
+        else:
+            step_body(i % 2)
         torch.cuda.current_stream().synchronize()  # the step's result is on the host
         if not arena.check():
             raise SystemExit("bench: a view did not fit the presized binning buffer; the measurement is void")
@@ -329,6 +342,15 @@ def run_ours(args, rank, world, dev):
                                                             rotations=leaves["rotations"])
             caps.append(arena.capacity)
         arena.capacity = max(caps)
+    e2e_mode = "eager launches"
+    if os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
+        try:
+            for j in range(2):
+                captured[j] = rasterizer.CapturedStep(lambda j=j: step_body(j), arena)
+            e2e_mode = "CUDA-graph replay (rasterizer.CapturedStep), one graph per target staging buffer"
+        except Exception as exc:  # e.g. a collective that cannot be captured on this system
+            captured[0] = captured[1] = None
+            e2e_mode = "eager launches (graph capture failed: %s)" % type(exc).__name__
     for i in range(3):
         step_e2e(i)
     barrier_sync(world)
@@ -395,7 +417,8 @@ def run_ours(args, rank, world, dev):
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                 "path": "GaussianRasterizer(settings, arena=RenderArena) (tensor-level mirror of the reference operator, "
                         "persistent scratch, sync-free forward) + torch autograd + L1 loss; "
-                        "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream"},
+                        "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream; "
+                        "launched as: " + e2e_mode},
         "gpu_launches": MY_KERNELS_PER_STEP * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_base,

@@ -1,0 +1,263 @@
+// Back-to-front backward of the tile blend, pair-sparse formulation: dL/dC, dL/dS -> per-Gaussian
+// dL/d{mean2D, conic, opacity, colour}. sm_100a.
+//
+// Replaces BACKWARD::render / renderCUDA<3> (reference src/cuda_rasterizer/backward.cu:438-603,675-713).
+// Like the reference, NO depth gradient is produced (backward.cu:567-571, rasterizer.cu:77-80).
+//
+// Same work decomposition as blend_fwd_sparse.cu, walked in reverse: a warp owns an 8x4 pixel block and
+// the block's candidate list (block_lists.cu), 32 candidates at a time, starting at the last group the
+// forward found a contributor in (block_used). Per group:
+//  B. lane = PIXEL walks the set bits of its transposed mask from the back: re-evaluates alpha, advances the
+//     reference's reverse recurrence (T, accumulated colour behind the pair) and leaves the only two
+//     numbers of the pair that depend on that recurrence in a shared-memory slot [candidate][pixel]:
+//     u = G * dL/dalpha and w = alpha * T (zeros for a pair the reference skips);
+//  C. lane = CANDIDATE walks the set bits of its own coverage mask, reads the slots and accumulates the 9
+//     sums of its Gaussian in registers; every gradient is linear in u or w:
+//        dL/dcolour_c += w dL/dC_c            dL/dopacity += u
+//        dL/dconic    += -1/2 (op u) {dx^2, dx dy, dy^2}
+//        dL/dmean2D   += -(op u) {cx dx + cy dy, cz dy + cy dx} {W/2, H/2}
+//     and leaves with 9 RED.ADD.F32 per (Gaussian, block) -- no shuffle butterfly per pair, no atomics per
+//     pair (the reference issues 9 same-address atomics per blended pair).
+// The sums are the reference's sums in another order and association (as between two runs of the
+// reference itself): compared at 1e-4 relative, not bitwise.
+#include <cstdlib>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+namespace {
+
+constexpr int kWarps = 8;
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kSlotStride = 33;  // [candidate][pixel] slots, padded against bank conflicts
+
+struct __align__(16) WarpBuf {
+  float4 a[32];  // {mean2D.x, mean2D.y, conic.x, conic.y}
+  float4 b[32];  // {conic.z, opacity, r, g}
+  float4 c[32];  // {b, bits(index in tile list + 1), bits(Gaussian id), -}
+  float4 pix[32];  // per pixel {dL/dC_r, dL/dC_g, dL/dC_b, -}
+  float2 slot[32 * kSlotStride];
+};
+
+struct BwdArgs {
+  const uint2* ranges;
+  const uint32_t* tile_order;
+  const SplatRecord* inst;
+  const uint32_t* point_list;
+  const uint2* blist;
+  const uint32_t* block_count;
+  const uint32_t* block_used;
+  int W, H, grid_x;
+  const float* bg;
+  const float* final_T;
+  const uint32_t* n_contrib;
+  const float *dL_dpix, *dL_dacc;
+  float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor;
+};
+
+template <int ILP>
+__global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpBuf& buf = reinterpret_cast<WarpBuf*>(smem_raw)[warp];
+  const int tile = (int)a.tile_order[blockIdx.x];
+  const uint2 range = a.ranges[tile];
+  const int n = (int)(range.y - range.x);
+  if (n == 0) return;
+  const int used = (int)a.block_used[tile * 8 + warp];
+  if (used == 0) return;  // nothing was blended into this warp's pixels
+  const int cnt = min((int)a.block_count[tile * 8 + warp], used * 32);
+  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)warp * n;
+  const SplatRecord* src = a.inst + range.x;
+  const uint32_t* ids = a.point_list + range.x;
+
+  const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
+  const int wx = tile_x * kTile + (warp & 1) * 8, wy = tile_y * kTile + (warp >> 1) * 4;
+  const int px = wx + (lane & 7), py = wy + (lane >> 3);
+  const bool inside = px < a.W && py < a.H;
+  const float pxf = (float)px, pyf = (float)py;
+  const size_t p = (size_t)a.W * py + px;
+  const size_t plane = (size_t)a.W * a.H;
+  const uint32_t last_contributor = inside ? a.n_contrib[p] : 0u;
+
+  // per-pixel state of the reverse traversal (reference backward.cu:480-501)
+  const float T_final = inside ? a.final_T[p] : 0.f;
+  float T = T_final;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_s = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_s = 0.f, last_alpha = 0.f;
+  float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f, dacc = 0.f;
+  if (inside) {
+    dpx0 = a.dL_dpix[p], dpx1 = a.dL_dpix[plane + p], dpx2 = a.dL_dpix[2 * plane + p];
+    dacc = a.dL_dacc[p];
+  }
+  const float bg_dot = __ldg(a.bg) * dpx0 + __ldg(a.bg + 1) * dpx1 + __ldg(a.bg + 2) * dpx2;
+  buf.pix[lane] = make_float4(dpx0, dpx1, dpx2, 0.f);
+  const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+  const float wxf = (float)wx, wyf = (float)wy;
+
+  // Groups used-1 .. 0. Within a group lane s holds candidate (31 - s) of the group, so that ascending bit order
+  // in the transposed masks is descending list order. Register pipeline as in the forward.
+  const int ngroups = used;
+  auto slot_index = [&](int g, int l) { return g * 32 + 31 - l; };  // list position of lane l's candidate in group g
+  uint2 ent = make_uint2(0u, 0u), ent_next = make_uint2(0u, 0u);
+  float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+  uint32_t gid = 0;
+  {
+    const int i0 = slot_index(ngroups - 1, lane);
+    if (i0 < cnt) ent = list[i0];
+    const int i1 = slot_index(ngroups - 2, lane);
+    if (ngroups >= 2 && i1 < cnt) ent_next = list[i1];
+    if (i0 < cnt) {
+      const float4* q = reinterpret_cast<const float4*>(src + ent.x);
+      r0 = q[0], r1 = q[1], r2 = q[2];
+      gid = ids[ent.x];
+    }
+  }
+
+  for (int g = ngroups - 1; g >= 0; --g) {
+    buf.a[lane] = make_float4(r0.x, r0.y, r1.x, r1.y);
+    buf.b[lane] = make_float4(r1.z, r1.w, r2.x, r2.y);
+    buf.c[lane] = make_float4(r2.z, __uint_as_float(ent.x + 1u), 0.f, 0.f);
+    const uint32_t cov = (slot_index(g, lane) < cnt) ? ent.y : 0u;
+    const uint32_t my_id = gid;
+    // this candidate's own parameters for phase C (before the pipeline registers move on)
+    const float mx = r0.x, my = r0.y, cx = r1.x, cy = r1.y, cz = r1.z, op = r1.w;
+    __syncwarp();
+
+    ent = ent_next;
+    if (g >= 1 && slot_index(g - 1, lane) < cnt) {
+      const float4* q = reinterpret_cast<const float4*>(src + ent.x);
+      r0 = q[0], r1 = q[1], r2 = q[2];
+      gid = ids[ent.x];
+    }
+    ent_next = make_uint2(0u, 0u);
+    if (g >= 2 && slot_index(g - 2, lane) < cnt) ent_next = list[slot_index(g - 2, lane)];
+
+    uint32_t x = cov;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+      const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+      const uint32_t y = __shfl_xor_sync(kFull, x, j);
+      x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    uint32_t cand = x;
+
+    // ---- phase B: lane = pixel ----
+    while (cand) {
+      int e[ILP];
+      float al[ILP], G[ILP];
+#pragma unroll
+      for (int u = 0; u < ILP; ++u) {
+        const bool valid = cand != 0u;
+        e[u] = valid ? __ffs((int)cand) - 1 : -1;
+        cand &= cand - 1u;
+        const int ee = max(e[u], 0);
+        const float4 qa = buf.a[ee];
+        const float4 qb = buf.b[ee];
+        const float4 qc = buf.c[ee];
+        const float dx = qa.x - pxf, dy = qa.y - pyf;
+        const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
+                                      -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
+        const float gg = expf(power);
+        const float v = fminf(0.99f, __fmul_rn(qb.y, gg));
+        const bool on = valid && (__float_as_uint(qc.y) <= last_contributor) && !(power > 0.0f) && !(v < 1.0f / 255.0f);
+        G[u] = gg, al[u] = on ? v : -1.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < ILP; ++u) {
+        if (e[u] < 0) continue;
+        float2 out = make_float2(0.f, 0.f);
+        if (al[u] >= 0.0f) {  // reference backward.cu:546-600
+          const float4 qb = buf.b[e[u]];
+          const float4 qc = buf.c[e[u]];
+          const float alpha = al[u];
+          // one correctly rounded reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581)
+          const float inv = __frcp_rn(1.f - alpha);
+          T = T * inv;
+          const float keep = 1.f - last_alpha;
+          acc0 = last_alpha * lc0 + keep * acc0;
+          acc1 = last_alpha * lc1 + keep * acc1;
+          acc2 = last_alpha * lc2 + keep * acc2;
+          acc_s = last_alpha * last_s + keep * acc_s;
+          lc0 = qb.z, lc1 = qb.w, lc2 = qc.x, last_s = 1.0f;
+          float dL_dalpha = (lc0 - acc0) * dpx0 + (lc1 - acc1) * dpx1 + (lc2 - acc2) * dpx2;
+          dL_dalpha += (1.0f - acc_s) * dacc;
+          dL_dalpha *= T;
+          last_alpha = alpha;
+          dL_dalpha += (-T_final * inv) * bg_dot;
+          out = make_float2(G[u] * dL_dalpha, alpha * T);
+        }
+        buf.slot[e[u] * kSlotStride + lane] = out;
+      }
+    }
+    __syncwarp();
+
+    // ---- phase C: lane = candidate ----
+    {
+      float s_op = 0.f, s_x = 0.f, s_y = 0.f, s_xx = 0.f, s_xy = 0.f, s_yy = 0.f, s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f;
+      bool hit = false;
+      uint32_t todo = cov;
+      const float2* row = buf.slot + lane * kSlotStride;
+      while (todo) {
+        const int k = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const float2 uw = row[k];
+        const float4 dp = buf.pix[k];
+        const float dx = mx - (wxf + (float)(k & 7)), dy = my - (wyf + (float)(k >> 3));
+        hit = hit || (uw.y != 0.0f);
+        const float v = op * uw.x;
+        const float vdx = v * dx, vdy = v * dy;
+        s_op += uw.x;
+        s_x += vdx, s_y += vdy;
+        s_xx = fmaf(vdx, dx, s_xx), s_xy = fmaf(vdx, dy, s_xy), s_yy = fmaf(vdy, dy, s_yy);
+        s_c0 = fmaf(uw.y, dp.x, s_c0), s_c1 = fmaf(uw.y, dp.y, s_c1), s_c2 = fmaf(uw.y, dp.z, s_c2);
+      }
+      if (hit) {
+        const size_t id = my_id;
+        atomicAdd(a.dL_dcolor + 3 * id + 0, s_c0);
+        atomicAdd(a.dL_dcolor + 3 * id + 1, s_c1);
+        atomicAdd(a.dL_dcolor + 3 * id + 2, s_c2);
+        atomicAdd(a.dL_dmean2D + 3 * id + 0, -(cx * s_x + cy * s_y) * ddelx_dx);
+        atomicAdd(a.dL_dmean2D + 3 * id + 1, -(cz * s_y + cy * s_x) * ddely_dy);
+        atomicAdd(a.dL_dconic + 4 * id + 0, -0.5f * s_xx);
+        atomicAdd(a.dL_dconic + 4 * id + 1, -0.5f * s_xy);
+        atomicAdd(a.dL_dconic + 4 * id + 3, -0.5f * s_yy);
+        atomicAdd(a.dL_dopacity + id, s_op);
+      }
+    }
+    __syncwarp();  // slots and records are rewritten by the next group
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
+                                    const float* background, const float* dL_dpix, const float* dL_dacc,
+                                    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                                    cudaStream_t s) {
+  const int grid_x = (width + kTile - 1) / kTile, grid_y = (height + kTile - 1) / kTile;
+  constexpr int kSmem = (int)sizeof(WarpBuf) * kWarps;
+  static const int ilp = [] {
+    const char* e = getenv("GSR_BWD_ILP");  // tuning knob: alphas evaluated per lane per step (1 or 2)
+    return e ? atoi(e) : 2;
+  }();
+  auto kernel = ilp == 1 ? blend_bwd_sparse_kernel<1> : blend_bwd_sparse_kernel<2>;
+  static bool configured[64][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev][ilp == 1]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev][ilp == 1] = true;
+  }
+  BwdArgs a;
+  a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
+  a.blist = b.blist, a.block_count = img.block_count, a.block_used = img.block_used;
+  a.W = width, a.H = height, a.grid_x = grid_x;
+  a.bg = background, a.final_T = img.final_T, a.n_contrib = img.n_contrib;
+  a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;
+  a.dL_dmean2D = dL_dmean2D, a.dL_dconic = dL_dconic, a.dL_dopacity = dL_dopacity, a.dL_dcolor = dL_dcolor;
+  kernel<<<grid_x * grid_y, kWarps * 32, kSmem, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gsr

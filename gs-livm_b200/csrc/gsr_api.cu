@@ -92,6 +92,8 @@ ImageState carve_image(char* chunk, int width, int height) {
   carve(chunk, s.tile_order, tiles);
   carve(chunk, s.tile_count, tiles);
   carve(chunk, s.summary, 4);
+  carve(chunk, s.block_count, tiles * 8);
+  carve(chunk, s.block_used, tiles * 8);
   return s;
 }
 
@@ -104,6 +106,7 @@ BinningState carve_binning(char* chunk, int R) {
   carve(chunk, b.keys, n);
   carve(chunk, b.vals_unsorted, n);
   carve(chunk, b.vals, n + 4);  // +16 B: blend_bwd bulk-copies ids from an aligned-down start
+  carve(chunk, b.blist, 8 * n);
   b.sort_temp_bytes = sort_temp_bytes(R);
   carve(chunk, b.sort_temp, b.sort_temp_bytes);
   return b;
@@ -175,7 +178,8 @@ size_t gsr_required_image(int width, int height) {
   if (width < 0 || height < 0) return 0;
   return required_bytes([&] {
     ImageState s = carve_image(nullptr, width, height);
-    return (size_t)(reinterpret_cast<uintptr_t>(s.summary + 4));
+    const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    return (size_t)(reinterpret_cast<uintptr_t>(s.block_used + tiles * 8));
   });
 }
 
@@ -200,13 +204,31 @@ static int validate_fwd(const gsr_fwd_args& a, const char* who) {
   return GSR_OK;
 }
 
-static int launch_blend_forward(const gsr_fwd_args& a, const ImageState& img, const BinningState& bin, int debug,
-                                cudaStream_t stream) {
-  static const bool fwd_warp = [] { const char* e = getenv("GSR_FWD_IMPL"); return !(e && !strcmp(e, "mask")); }();
+// Blend implementations: "sparse" (default; per-block candidate lists, blend_*_sparse.cu), "warp" (lock-step warps
+// over the whole tile list, blend_fwd.cu / blend_bwd.cu), "mask" (coverage-mask experiment). The sparse backward
+// needs the sparse forward's block_used, so it is only taken when the forward was sparse as well.
+enum BlendImpl { kBlendSparse = 0, kBlendWarp = 1, kBlendMask = 2 };
+static BlendImpl blend_impl(const char* var) {
+  const char* e = getenv(var);
+  if (e && !strcmp(e, "warp")) return kBlendWarp;
+  if (e && !strcmp(e, "mask")) return kBlendMask;
+  return kBlendSparse;
+}
+static BlendImpl fwd_impl() { static const BlendImpl v = blend_impl("GSR_FWD_IMPL"); return v; }
+static BlendImpl bwd_impl() {
+  static const BlendImpl v = blend_impl("GSR_BWD_IMPL");
+  return (v == kBlendSparse && fwd_impl() != kBlendSparse) ? kBlendWarp : v;
+}
+
+static int launch_blend_forward(const gsr_fwd_args& a, const ImageState& img, const BinningState& bin, int tiles,
+                                int grid_x, int debug, cudaStream_t stream) {
+  const BlendImpl impl = fwd_impl();
+  if (impl == kBlendSparse)
+    GSR_STAGE(GSR_STAGE_FINALIZE, launch_block_lists(tiles, img, bin, grid_x, stream), "block_lists", debug, stream);
+  auto fn = impl == kBlendSparse ? launch_blend_fwd_sparse : impl == kBlendWarp ? launch_blend_fwd : launch_blend_fwd_mask;
   GSR_STAGE(GSR_STAGE_BLEND_FWD,
-            (fwd_warp ? launch_blend_fwd : launch_blend_fwd_mask)(a.width, a.height, img, bin, a.background, a.out_color,
-                                                                  a.out_depth, a.out_acc, stream),
-            "blend_fwd", debug, stream);
+            fn(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream), "blend_fwd",
+            debug, stream);
   return GSR_OK;
 }
 
@@ -275,11 +297,12 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
                 "duplicate_with_keys", debug, stream);
       const int bit = (int)higher_msb((uint32_t)tiles);
       GSR_STAGE(GSR_STAGE_SORT, run_sort(bin, R, 32 + bit, stream), "sort", debug, stream);
-      GSR_STAGE(GSR_STAGE_FINALIZE, launch_finalize_binning(R, bin, geom, grid_x, img.ranges, stream), "finalize_binning",
-                debug, stream);
+      // no stage timer here: on this path GSR_STAGE_FINALIZE times block_lists (launch_blend_forward)
+      GSR_CUDA(launch_finalize_binning(R, bin, geom, grid_x, img.ranges, stream), "finalize_binning");
+      if (debug) GSR_CUDA(cudaStreamSynchronize(stream), "finalize_binning");
     }
   }
-  if (int st = launch_blend_forward(a, img, bin, debug, stream)) return st;
+  if (int st = launch_blend_forward(a, img, bin, tiles, grid_x, debug, stream)) return st;
   *num_rendered = R;
   return GSR_OK;
 }
@@ -312,7 +335,7 @@ int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, char* binn
   GSR_STAGE(GSR_STAGE_DUPLICATE, launch_scatter_instances(a.P, geom, radii, img, bin, grid_x, grid_y, stream),
             "scatter_instances", debug, stream);
   GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, -1, img, bin, geom, grid_x, stream), "tile_sort", debug, stream);
-  return launch_blend_forward(a, img, bin, debug, stream);
+  return launch_blend_forward(a, img, bin, tiles, grid_x, debug, stream);
 }
 
 int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
@@ -361,10 +384,11 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
     }
   }
   if (a.R > 0) {
-    const char* impl = getenv("GSR_BWD_IMPL");
-    const bool bwd_mask = impl && !strcmp(impl, "mask");
-    GSR_STAGE(GSR_STAGE_BLEND_BWD, (bwd_mask ? launch_blend_bwd_mask : launch_blend_bwd)(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
-                               a.dL_dconic, a.dL_dopacity, a.dL_dcolor, stream),
+    const BlendImpl impl = bwd_impl();
+    auto fn = impl == kBlendSparse ? launch_blend_bwd_sparse : impl == kBlendWarp ? launch_blend_bwd : launch_blend_bwd_mask;
+    GSR_STAGE(GSR_STAGE_BLEND_BWD,
+              fn(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D, a.dL_dconic,
+                 a.dL_dopacity, a.dL_dcolor, stream),
               "blend_bwd", debug, stream);
   }
   GSR_STAGE(GSR_STAGE_GEOM_BWD, launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);

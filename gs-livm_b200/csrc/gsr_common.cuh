@@ -61,6 +61,8 @@ struct ImageState {
   uint32_t* tile_order; // [tiles] tile ids, longest instance lists first (launch order of the blend CTAs)
   uint32_t* tile_count; // [tiles] instances per tile (preprocess), then the tile's scatter cursor (tile_sort.cu)
   uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, overflow code (sync-free forward)}
+  uint32_t* block_count;  // [tiles*8] candidates per 8x4 pixel block (block_lists.cu)
+  uint32_t* block_used;   // [tiles*8] groups of 32 candidates up to the block's last contributor (blend_fwd_sparse.cu)
 };
 
 // tile_sort.cu: lists up to kSmallMax instances are sorted by a 256-thread CTA (kSmallCap slots of shared
@@ -75,6 +77,8 @@ struct BinningState {
   uint32_t* vals;           // [R] sorted == reference point_list
   SplatRecord* inst;        // [R] records in sorted order
   InstAux* aux;             // [R] clipped boxes / thresholds / ids in sorted order
+  uint2* blist;             // [8R] per-block candidate lists {index in the tile list, coverage mask}: block b of a
+                            //      tile with range [r, r+n) owns entries 8r + b*n .. 8r + (b+1)*n (block_lists.cu)
   char* sort_temp;
   size_t sort_temp_bytes;
 };
@@ -116,6 +120,14 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
                              int grid_x, cudaStream_t s);
 cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, uint32_t* tile_last,
                                cudaStream_t s);
+cudaError_t launch_block_lists(int tiles, const ImageState& img, const BinningState& b, int grid_x, cudaStream_t s);
+cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
+                                    const float* background, float* out_color, float* out_depth, float* out_acc,
+                                    cudaStream_t s);
+cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
+                                    const float* background, const float* dL_dpix, const float* dL_dacc,
+                                    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+                                    cudaStream_t s);
 cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,
                              const float* background, float* out_color, float* out_depth, float* out_acc,
                              cudaStream_t s);

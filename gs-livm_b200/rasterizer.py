@@ -138,6 +138,50 @@ class RenderArena:
         return ok
 
 
+class CapturedStep:
+    """CUDA-graph replay of one optimisation step built on `GaussianRasterizer(settings, arena=RenderArena)`
+    (ours; the reference's mapping loop launches every kernel of every iteration from the host,
+    src/liw/lioOptimization.cpp:1693-1760).
+
+    `step_fn()` is the step as the caller would write it eagerly — host-to-device copies from PINNED staging
+    tensors, the render, the loss, `loss.backward()`, the device-to-host copy of the loss — with three rules:
+    no host synchronisation inside, every tensor it reads from the outside keeps its address (write new camera /
+    image data INTO the staging tensors before `replay()`), and the arena already knows its capacity (one eager
+    render did `arena.learn`). It runs `warmup` times eagerly on a side stream, is captured once, and
+    `replay()` then launches the whole step — ~20 kernels and copies — with one host call. Tensors created
+    inside `step_fn` (outputs, `.grad`s, the loss) live in the graph's memory pool and are overwritten by every
+    replay; `result` is whatever `step_fn` returned at capture time.
+
+    After `replay()` and whatever synchronisation the loop does anyway, `arena.check()` tells whether the frame
+    fitted the presized binning buffer, exactly as on the eager path."""
+
+    def __init__(self, step_fn, arena: RenderArena, warmup: int = 3):
+        if arena.capacity <= 0:
+            raise ValueError("CapturedStep: the arena has no capacity yet; render once eagerly first")
+        self.arena = arena
+        dev = arena.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                step_fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if not arena.check():
+            raise RuntimeError("CapturedStep: a warm-up render did not fit the arena")
+        before = len(arena._unchecked)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = step_fn()
+        self._slots = arena._unchecked[before:]  # status words the captured renders report into
+        del arena._unchecked[before:]
+
+    def replay(self):
+        self.graph.replay()
+        self.arena._unchecked.extend(self._slots)
+        return self.result
+
+
 def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
