@@ -28,13 +28,15 @@ namespace gsr {
 namespace {
 
 constexpr int kWarps = 8;
+constexpr int kHeavy = 2048;   // tiles with at least this many instances use the FINE shape
+constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kSlotStride = 33;  // [candidate][pixel] slots, padded against bank conflicts
+constexpr int kSlotStride = 33;  // [candidate][pixel] slots, padded against bank conflicts (FINE uses 9 of them)
 
 struct __align__(16) WarpBuf {
   float4 a[32];  // {mean2D.x, mean2D.y, conic.x, conic.y}
   float4 b[32];  // {conic.z, opacity, r, g}
-  float4 c[32];  // {b, bits(index in tile list + 1), bits(Gaussian id), -}
+  float4 c[32];  // {b, bits(index in tile list + 1), -, -}
   float4 pix[32];  // per pixel {dL/dC_r, dL/dC_g, dL/dC_b, -}
   float2 slot[32 * kSlotStride];
 };
@@ -47,7 +49,7 @@ struct BwdArgs {
   const uint2* blist;
   const uint32_t* block_count;
   const uint32_t* block_used;
-  int W, H, grid_x;
+  int W, H, grid_x, heavy, fine_tiles;
   const float* bg;
   const float* final_T;
   const uint32_t* n_contrib;
@@ -55,56 +57,99 @@ struct BwdArgs {
   float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor;
 };
 
-template <int ILP>
-__global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const BwdArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpBuf& buf = reinterpret_cast<WarpBuf*>(smem_raw)[warp];
-  const int tile = (int)a.tile_order[blockIdx.x];
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(kFull, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+  }
+  return x;
+}
+
+// Per-pixel state of the reverse traversal (reference backward.cu:480-501).
+struct PixelState {
+  float T, T_final, acc0, acc1, acc2, acc_s, lc0, lc1, lc2, last_s, last_alpha;
+  float dpx0, dpx1, dpx2, dacc, bg_dot;
+};
+
+// Advance the recurrence over one blended pair (reference backward.cu:546-585) and return dL/dalpha of the pair.
+// rgb = the candidate's colour.
+__device__ __forceinline__ float pair_recurrence(PixelState& s, float alpha, float r, float g, float b) {
+  // one correctly rounded reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581)
+  const float inv = __frcp_rn(1.f - alpha);
+  s.T = s.T * inv;
+  const float keep = 1.f - s.last_alpha;
+  s.acc0 = s.last_alpha * s.lc0 + keep * s.acc0;
+  s.acc1 = s.last_alpha * s.lc1 + keep * s.acc1;
+  s.acc2 = s.last_alpha * s.lc2 + keep * s.acc2;
+  s.acc_s = s.last_alpha * s.last_s + keep * s.acc_s;
+  s.lc0 = r, s.lc1 = g, s.lc2 = b, s.last_s = 1.0f;
+  float dL_dalpha = (r - s.acc0) * s.dpx0 + (g - s.acc1) * s.dpx1 + (b - s.acc2) * s.dpx2;
+  dL_dalpha += (1.0f - s.acc_s) * s.dacc;
+  dL_dalpha *= s.T;
+  s.last_alpha = alpha;
+  dL_dalpha += (-s.T_final * inv) * s.bg_dot;
+  return dL_dalpha;
+}
+
+// One warp, one 8x4 pixel block of a tile (COARSE, SLOTS = 1) or one 4x2 quarter `sub` of it with four lanes per
+// pixel (FINE, SLOTS = 4; see blend_fwd_sparse.cu): the four lanes evaluate exp/alpha of four consecutive
+// candidates of their pixel at once, all replay the ordered recurrence, and the lane that evaluated a pair leaves
+// its (u, w) in the pair's slot.
+template <int SLOTS, int ILP>
+__device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, int tile, int block, int sub, int lane) {
+  constexpr int NPIX = 32 / SLOTS;                        // pixels of this warp
+  constexpr int STRIDE = SLOTS == 1 ? kSlotStride : 9;    // slot row stride
   const uint2 range = a.ranges[tile];
   const int n = (int)(range.y - range.x);
   if (n == 0) return;
-  const int used = (int)a.block_used[tile * 8 + warp];
-  if (used == 0) return;  // nothing was blended into this warp's pixels
-  const int cnt = min((int)a.block_count[tile * 8 + warp], used * 32);
-  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)warp * n;
+  const int used = (int)a.block_used[tile * 8 + block];
+  if (used == 0) return;  // nothing was blended into this block's pixels
+  const int cnt = min((int)a.block_count[tile * 8 + block], used * 32);
+  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)block * n;
   const SplatRecord* src = a.inst + range.x;
   const uint32_t* ids = a.point_list + range.x;
 
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-  const int wx = tile_x * kTile + (warp & 1) * 8, wy = tile_y * kTile + (warp >> 1) * 4;
-  const int px = wx + (lane & 7), py = wy + (lane >> 3);
+  const int pix = SLOTS == 1 ? lane : (lane & 7), slot = SLOTS == 1 ? 0 : (lane >> 3);
+  // origin of this warp's pixels, the pixel of this lane, and its shift inside the block's 32-bit coverage masks
+  const int wx = tile_x * kTile + (block & 1) * 8 + (SLOTS == 1 ? 0 : 4 * (sub & 1));
+  const int wy = tile_y * kTile + (block >> 1) * 4 + (SLOTS == 1 ? 0 : 2 * (sub >> 1));
+  const int px = wx + (SLOTS == 1 ? (pix & 7) : (pix & 3)), py = wy + (SLOTS == 1 ? (pix >> 3) : (pix >> 2));
+  const int sh = 16 * (sub >> 1) + 4 * (sub & 1);
   const bool inside = px < a.W && py < a.H;
   const float pxf = (float)px, pyf = (float)py;
   const size_t p = (size_t)a.W * py + px;
   const size_t plane = (size_t)a.W * a.H;
   const uint32_t last_contributor = inside ? a.n_contrib[p] : 0u;
+  if (SLOTS == 4 && __all_sync(kFull, last_contributor == 0u)) return;
 
-  // per-pixel state of the reverse traversal (reference backward.cu:480-501)
-  const float T_final = inside ? a.final_T[p] : 0.f;
-  float T = T_final;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc_s = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_s = 0.f, last_alpha = 0.f;
-  float dpx0 = 0.f, dpx1 = 0.f, dpx2 = 0.f, dacc = 0.f;
+  PixelState st;
+  st.T_final = inside ? a.final_T[p] : 0.f;
+  st.T = st.T_final;
+  st.acc0 = st.acc1 = st.acc2 = st.acc_s = st.lc0 = st.lc1 = st.lc2 = st.last_s = st.last_alpha = 0.f;
+  st.dpx0 = st.dpx1 = st.dpx2 = st.dacc = 0.f;
   if (inside) {
-    dpx0 = a.dL_dpix[p], dpx1 = a.dL_dpix[plane + p], dpx2 = a.dL_dpix[2 * plane + p];
-    dacc = a.dL_dacc[p];
+    st.dpx0 = a.dL_dpix[p], st.dpx1 = a.dL_dpix[plane + p], st.dpx2 = a.dL_dpix[2 * plane + p];
+    st.dacc = a.dL_dacc[p];
   }
-  const float bg_dot = __ldg(a.bg) * dpx0 + __ldg(a.bg + 1) * dpx1 + __ldg(a.bg + 2) * dpx2;
-  buf.pix[lane] = make_float4(dpx0, dpx1, dpx2, 0.f);
+  st.bg_dot = __ldg(a.bg) * st.dpx0 + __ldg(a.bg + 1) * st.dpx1 + __ldg(a.bg + 2) * st.dpx2;
+  if (slot == 0) buf.pix[pix] = make_float4(st.dpx0, st.dpx1, st.dpx2, 0.f);
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
   const float wxf = (float)wx, wyf = (float)wy;
 
-  // Groups used-1 .. 0. Within a group lane s holds candidate (31 - s) of the group, so that ascending bit order
+  // Groups used-1 .. 0. Within a group lane l holds candidate (31 - l) of the group, so that ascending bit order
   // in the transposed masks is descending list order. Register pipeline as in the forward.
   const int ngroups = used;
-  auto slot_index = [&](int g, int l) { return g * 32 + 31 - l; };  // list position of lane l's candidate in group g
+  auto list_index = [&](int g, int l) { return g * 32 + 31 - l; };
   uint2 ent = make_uint2(0u, 0u), ent_next = make_uint2(0u, 0u);
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
   uint32_t gid = 0;
   {
-    const int i0 = slot_index(ngroups - 1, lane);
+    const int i0 = list_index(ngroups - 1, lane);
     if (i0 < cnt) ent = list[i0];
-    const int i1 = slot_index(ngroups - 2, lane);
+    const int i1 = list_index(ngroups - 2, lane);
     if (ngroups >= 2 && i1 < cnt) ent_next = list[i1];
     if (i0 < cnt) {
       const float4* q = reinterpret_cast<const float4*>(src + ent.x);
@@ -117,76 +162,96 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
     buf.a[lane] = make_float4(r0.x, r0.y, r1.x, r1.y);
     buf.b[lane] = make_float4(r1.z, r1.w, r2.x, r2.y);
     buf.c[lane] = make_float4(r2.z, __uint_as_float(ent.x + 1u), 0.f, 0.f);
-    const uint32_t cov = (slot_index(g, lane) < cnt) ? ent.y : 0u;
+    uint32_t cov = (list_index(g, lane) < cnt) ? ent.y : 0u;
+    if (SLOTS == 4) cov = ((cov >> sh) & 0xfu) | (((cov >> (sh + 8)) & 0xfu) << 4);  // this quarter's 4x2 bits
     const uint32_t my_id = gid;
     // this candidate's own parameters for phase C (before the pipeline registers move on)
     const float mx = r0.x, my = r0.y, cx = r1.x, cy = r1.y, cz = r1.z, op = r1.w;
     __syncwarp();
 
     ent = ent_next;
-    if (g >= 1 && slot_index(g - 1, lane) < cnt) {
+    if (g >= 1 && list_index(g - 1, lane) < cnt) {
       const float4* q = reinterpret_cast<const float4*>(src + ent.x);
       r0 = q[0], r1 = q[1], r2 = q[2];
       gid = ids[ent.x];
     }
     ent_next = make_uint2(0u, 0u);
-    if (g >= 2 && slot_index(g - 2, lane) < cnt) ent_next = list[slot_index(g - 2, lane)];
+    if (g >= 2 && list_index(g - 2, lane) < cnt) ent_next = list[list_index(g - 2, lane)];
 
-    uint32_t x = cov;
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-      const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-      const uint32_t y = __shfl_xor_sync(kFull, x, j);
-      x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
-    }
-    uint32_t cand = x;
+    uint32_t cand = transpose32(SLOTS == 1 ? cov : cov * 0x01010101u, lane);
 
     // ---- phase B: lane = pixel ----
-    while (cand) {
-      int e[ILP];
-      float al[ILP], G[ILP];
+    if (SLOTS == 1) {
+      while (cand) {
+        int e[ILP];
+        float al[ILP], G[ILP];
 #pragma unroll
-      for (int u = 0; u < ILP; ++u) {
-        const bool valid = cand != 0u;
-        e[u] = valid ? __ffs((int)cand) - 1 : -1;
-        cand &= cand - 1u;
-        const int ee = max(e[u], 0);
-        const float4 qa = buf.a[ee];
-        const float4 qb = buf.b[ee];
-        const float4 qc = buf.c[ee];
-        const float dx = qa.x - pxf, dy = qa.y - pyf;
-        const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
-                                      -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
-        const float gg = expf(power);
-        const float v = fminf(0.99f, __fmul_rn(qb.y, gg));
-        const bool on = valid && (__float_as_uint(qc.y) <= last_contributor) && !(power > 0.0f) && !(v < 1.0f / 255.0f);
-        G[u] = gg, al[u] = on ? v : -1.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < ILP; ++u) {
-        if (e[u] < 0) continue;
-        float2 out = make_float2(0.f, 0.f);
-        if (al[u] >= 0.0f) {  // reference backward.cu:546-600
-          const float4 qb = buf.b[e[u]];
-          const float4 qc = buf.c[e[u]];
-          const float alpha = al[u];
-          // one correctly rounded reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581)
-          const float inv = __frcp_rn(1.f - alpha);
-          T = T * inv;
-          const float keep = 1.f - last_alpha;
-          acc0 = last_alpha * lc0 + keep * acc0;
-          acc1 = last_alpha * lc1 + keep * acc1;
-          acc2 = last_alpha * lc2 + keep * acc2;
-          acc_s = last_alpha * last_s + keep * acc_s;
-          lc0 = qb.z, lc1 = qb.w, lc2 = qc.x, last_s = 1.0f;
-          float dL_dalpha = (lc0 - acc0) * dpx0 + (lc1 - acc1) * dpx1 + (lc2 - acc2) * dpx2;
-          dL_dalpha += (1.0f - acc_s) * dacc;
-          dL_dalpha *= T;
-          last_alpha = alpha;
-          dL_dalpha += (-T_final * inv) * bg_dot;
-          out = make_float2(G[u] * dL_dalpha, alpha * T);
+        for (int u = 0; u < ILP; ++u) {
+          const bool valid = cand != 0u;
+          e[u] = valid ? __ffs((int)cand) - 1 : -1;
+          cand &= cand - 1u;
+          const int ee = max(e[u], 0);
+          const float4 qa = buf.a[ee];
+          const float4 qb = buf.b[ee];
+          const float4 qc = buf.c[ee];
+          const float dx = qa.x - pxf, dy = qa.y - pyf;
+          const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
+                                        -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
+          const float gg = expf(power);
+          const float v = fminf(0.99f, __fmul_rn(qb.y, gg));
+          const bool on = valid && (__float_as_uint(qc.y) <= last_contributor) && !(power > 0.0f) && !(v < 1.0f / 255.0f);
+          G[u] = gg, al[u] = on ? v : -1.0f;
         }
-        buf.slot[e[u] * kSlotStride + lane] = out;
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+          if (e[u] < 0) continue;
+          float2 out = make_float2(0.f, 0.f);
+          if (al[u] >= 0.0f) {  // reference backward.cu:546-600
+            const float4 qb = buf.b[e[u]];
+            const float4 qc = buf.c[e[u]];
+            const float dL_dalpha = pair_recurrence(st, al[u], qb.z, qb.w, qc.x);
+            out = make_float2(G[u] * dL_dalpha, al[u] * st.T);
+          }
+          buf.slot[e[u] * STRIDE + pix] = out;
+        }
+      }
+    } else {
+      while (__any_sync(kFull, cand != 0u)) {  // the four lanes of a pixel hold the same mask
+        int e[4];
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          valid[j] = cand != 0u;
+          e[j] = valid[j] ? __ffs((int)cand) - 1 : 0;
+          cand &= cand - 1u;
+        }
+        const int mine = slot == 0 ? e[0] : slot == 1 ? e[1] : slot == 2 ? e[2] : e[3];
+        const bool vmine = slot == 0 ? valid[0] : slot == 1 ? valid[1] : slot == 2 ? valid[2] : valid[3];
+        float al, G;
+        {
+          const float4 qa = buf.a[mine];
+          const float4 qb = buf.b[mine];
+          const float4 qc = buf.c[mine];
+          const float dx = qa.x - pxf, dy = qa.y - pyf;
+          const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
+                                        -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
+          G = expf(power);
+          const float v = fminf(0.99f, __fmul_rn(qb.y, G));
+          const bool on = vmine && (__float_as_uint(qc.y) <= last_contributor) && !(power > 0.0f) && !(v < 1.0f / 255.0f);
+          al = on ? v : -1.0f;
+        }
+        float2 out = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float alj = __shfl_sync(kFull, al, j * 8 + pix);
+          if (alj >= 0.0f) {
+            const float4 qb = buf.b[e[j]];
+            const float4 qc = buf.c[e[j]];
+            const float dL_dalpha = pair_recurrence(st, alj, qb.z, qb.w, qc.x);
+            if (slot == j) out = make_float2(G * dL_dalpha, alj * st.T);
+          }
+        }
+        if (vmine) buf.slot[mine * STRIDE + pix] = out;
       }
     }
     __syncwarp();
@@ -196,13 +261,14 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
       float s_op = 0.f, s_x = 0.f, s_y = 0.f, s_xx = 0.f, s_xy = 0.f, s_yy = 0.f, s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f;
       bool hit = false;
       uint32_t todo = cov;
-      const float2* row = buf.slot + lane * kSlotStride;
+      const float2* row = buf.slot + lane * STRIDE;
       while (todo) {
         const int k = __ffs((int)todo) - 1;
         todo &= todo - 1u;
         const float2 uw = row[k];
         const float4 dp = buf.pix[k];
-        const float dx = mx - (wxf + (float)(k & 7)), dy = my - (wyf + (float)(k >> 3));
+        const float kx = (float)(SLOTS == 1 ? (k & 7) : (k & 3)), ky = (float)(SLOTS == 1 ? (k >> 3) : (k >> 2));
+        const float dx = mx - (wxf + kx), dy = my - (wyf + ky);
         hit = hit || (uw.y != 0.0f);
         const float v = op * uw.x;
         const float vdx = v * dx, vdy = v * dy;
@@ -228,6 +294,26 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
   }
 }
 
+// grid = 4*fine_tiles FINE candidates (tile_order[b/4], two blocks b%4 per CTA) followed by `tiles` COARSE candidates.
+template <int ILP>
+__global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpBuf& buf = reinterpret_cast<WarpBuf*>(smem_raw)[warp];
+  const int b = (int)blockIdx.x;
+  if (b < 4 * a.fine_tiles) {
+    const int tile = (int)a.tile_order[b >> 2];
+    const uint2 r = a.ranges[tile];
+    if ((int)(r.y - r.x) < a.heavy) return;
+    blend_bwd_block<4, 1>(a, buf, tile, 2 * (b & 3) + (warp >> 2), warp & 3, lane);
+  } else {
+    const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
+    const uint2 r = a.ranges[tile];
+    if ((int)(r.y - r.x) >= a.heavy) return;
+    blend_bwd_block<1, ILP>(a, buf, tile, warp, 0, lane);
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
@@ -235,9 +321,10 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
                                     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                                     cudaStream_t s) {
   const int grid_x = (width + kTile - 1) / kTile, grid_y = (height + kTile - 1) / kTile;
+  const int tiles = grid_x * grid_y;
   constexpr int kSmem = (int)sizeof(WarpBuf) * kWarps;
   static const int ilp = [] {
-    const char* e = getenv("GSR_BWD_ILP");  // tuning knob: alphas evaluated per lane per step (1 or 2)
+    const char* e = getenv("GSR_BWD_ILP");  // tuning knob: alphas evaluated per lane per step, COARSE shape (1 or 2)
     return e ? atoi(e) : 2;
   }();
   auto kernel = ilp == 1 ? blend_bwd_sparse_kernel<1> : blend_bwd_sparse_kernel<2>;
@@ -253,10 +340,16 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
   a.blist = b.blist, a.block_count = img.block_count, a.block_used = img.block_used;
   a.W = width, a.H = height, a.grid_x = grid_x;
+  static const int heavy = [] {
+    const char* e = getenv("GSR_BWD_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
+    return e ? atoi(e) : kHeavy;
+  }();
+  a.heavy = heavy;
+  a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;
   a.bg = background, a.final_T = img.final_T, a.n_contrib = img.n_contrib;
   a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;
   a.dL_dmean2D = dL_dmean2D, a.dL_dconic = dL_dconic, a.dL_dopacity = dL_dopacity, a.dL_dcolor = dL_dcolor;
-  kernel<<<grid_x * grid_y, kWarps * 32, kSmem, s>>>(a);
+  kernel<<<4 * a.fine_tiles + tiles, kWarps * 32, kSmem, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -26,15 +26,14 @@ namespace gsr {
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kWindow = 4;  // groups of 32 candidates resident per warp (power of two)
+constexpr int kHeavy = 2048;   // tiles with at least this many instances use the FINE shape
+constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kNever = 0x7fffffff;
 
 struct __align__(16) WarpBuf {
-  float4 a[kWindow * 32];  // {mean2D.x, mean2D.y, conic.x, conic.y}
-  float4 b[kWindow * 32];  // {conic.z, opacity, r, g}
-  float4 c[kWindow * 32];  // {b, depth, bits(index in tile list + 1), -}
-  uint32_t mask[kWindow * 32];  // [segment][pixel] candidates of the segment's group that cover the pixel
+  float4 a[32];  // {mean2D.x, mean2D.y, conic.x, conic.y}
+  float4 b[32];  // {conic.z, opacity, r, g}
+  float4 c[32];  // {b, depth, bits(index in tile list + 1), -}
 };
 
 struct FwdArgs {
@@ -44,7 +43,7 @@ struct FwdArgs {
   const uint2* blist;
   const uint32_t* block_count;
   uint32_t* block_used;
-  int W, H, grid_x;
+  int W, H, grid_x, heavy, fine_tiles;
   const float* bg;
   float *out_color, *out_depth, *out_acc, *final_T;
   uint32_t *n_contrib, *tile_last;
@@ -61,31 +60,51 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
   return x;
 }
 
-template <int ILP>
-__global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const FwdArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpBuf& buf = reinterpret_cast<WarpBuf*>(smem_raw)[warp];
-  const int tile = (int)a.tile_order[blockIdx.x];
+// alpha of one (pixel, candidate) pair, in the reference's operation order (forward.cu:358-375); -1 = skipped
+__device__ __forceinline__ float pair_alpha(const float4 qa, const float4 qb, float pxf, float pyf, bool valid) {
+  const float dx = __fadd_rn(qa.x, -pxf);
+  const float dy = __fadd_rn(qa.y, -pyf);
+  const float quad = __fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x)));
+  const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
+  const float v = fminf(0.99f, __fmul_rn(qb.y, expf(power)));
+  // reference: `if (power > 0) continue; ... if (alpha < 1/255) continue;`
+  return (valid && !(power > 0.0f) && !(v < 1.0f / 255.0f)) ? v : -1.0f;
+}
+
+// One warp, one 8x4 pixel block of a tile (COARSE, SLOTS = 1: lane = pixel, ILP pairs per step) or one 4x2 quarter
+// `sub` of it (FINE, SLOTS = 4: four lanes per pixel). FINE is for the tiles with the longest lists, whose
+// per-pixel chains of ~1 000 dependent pairs would otherwise outlast the rest of the frame: the four lanes of a
+// pixel evaluate the alphas of four consecutive candidates of the pixel at once, exchange them with shuffles,
+// and all replay the ordered transmittance recurrence; each lane accumulates one output channel (slot 0: S and
+// D, slots 1-3: R, G, B) so every channel still sees the reference's exact sequence of operations.
+template <int SLOTS, int ILP>
+__device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int tile, int block, int sub, int lane) {
   const uint2 range = a.ranges[tile];
   const int n = (int)(range.y - range.x);
-  const int cnt = n ? (int)a.block_count[tile * 8 + warp] : 0;
-  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)warp * n;
+  const int cnt = n ? (int)a.block_count[tile * 8 + block] : 0;
+  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)block * n;
   const SplatRecord* src = a.inst + range.x;
 
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-  const int px = tile_x * kTile + (warp & 1) * 8 + (lane & 7);
-  const int py = tile_y * kTile + (warp >> 1) * 4 + (lane >> 3);
+  const int pix = SLOTS == 1 ? lane : (lane & 7), slot = SLOTS == 1 ? 0 : (lane >> 3);
+  // pixel inside the 8x4 block, and the bit that stands for it in the coverage masks
+  const int bx = SLOTS == 1 ? (pix & 7) : 4 * (sub & 1) + (pix & 3);
+  const int by = SLOTS == 1 ? (pix >> 3) : 2 * (sub >> 1) + (pix >> 2);
+  const int px = tile_x * kTile + (block & 1) * 8 + bx;
+  const int py = tile_y * kTile + (block >> 1) * 4 + by;
   const bool inside = px < a.W && py < a.H;
   const float pxf = (float)px, pyf = (float)py;
 
-  float T = 1.0f, A = 0.f, D = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  float T = 1.0f, A = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // COARSE: D, R, G, B; FINE: acc0 = own channel
   uint32_t last_contributor = 0;
   bool done = !inside;
-  int last_group = -1;  // group of this pixel's last contributor
+  int used = 0;
+  // FINE: which word of a parked record this lane's channel is (slot 0: depth, 1-3: r, g, b)
+  const float* chan = SLOTS == 1 ? nullptr
+                                 : (slot == 0 ? &buf.c[0].y : slot == 1 ? &buf.b[0].z : slot == 2 ? &buf.b[0].w : &buf.c[0].x);
 
   const int ngroups = (cnt + 31) >> 5;
-  // register pipeline: list entry two groups ahead of the staging point, record one group ahead
+  // register pipeline: list entry two groups ahead, record one group ahead
   uint2 ent = make_uint2(0u, 0u), ent_next = make_uint2(0u, 0u);
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
   if (lane < cnt) ent = list[lane];
@@ -95,107 +114,143 @@ __global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const Fwd
     r0 = q[0], r1 = q[1], r2 = q[2];
   }
 
-  // Lanes walk the list at their own pace inside a window of kWindow groups: `staged` groups have been parked in
-  // shared memory (group g in segment g % kWindow, records and per-pixel masks). A lane holds the bits it still
-  // owes of group `base` in `lo` and, once that group is staged, of group base + 1 in `hi`.
-  uint32_t lo = 0u, hi = 0u;
-  bool hi_loaded = false;
-  int base = -1, staged = 0;
-
-  while (true) {
-    const int low = done ? kNever : (lo ? base : base + 1);  // oldest group this lane may still read
-    const int min_low = __reduce_min_sync(kFull, low);       // also orders the window's reads before its re-use
-    if (min_low >= ngroups) break;                           // every lane is saturated or has consumed its list
-    while (staged < ngroups && staged - min_low < kWindow) {
-      const int seg = (staged % kWindow) * 32 + lane;
-      buf.a[seg] = make_float4(r0.x, r0.y, r1.x, r1.y);
-      buf.b[seg] = make_float4(r1.z, r1.w, r2.x, r2.y);
-      buf.c[seg] = make_float4(r2.z, r2.w, __uint_as_float(ent.x + 1u), 0.f);
-      buf.mask[seg] = transpose32((staged * 32 + lane < cnt) ? ent.y : 0u, lane);
-      ++staged;
-      // prefetch: records of the next group to stage, list entries of the one after
-      ent = ent_next;
-      if (staged * 32 + lane < cnt) {
-        const float4* q = reinterpret_cast<const float4*>(src + ent.x);
-        r0 = q[0], r1 = q[1], r2 = q[2];
-      }
-      ent_next = ((staged + 1) * 32 + lane < cnt) ? list[(staged + 1) * 32 + lane] : make_uint2(0u, 0u);
-      __syncwarp();
+  for (int g = 0; g < ngroups; ++g) {
+    // park this group's records; the vote at the end of the previous iteration ordered its reads
+    buf.a[lane] = make_float4(r0.x, r0.y, r1.x, r1.y);
+    buf.b[lane] = make_float4(r1.z, r1.w, r2.x, r2.y);
+    buf.c[lane] = make_float4(r2.z, r2.w, __uint_as_float(ent.x + 1u), 0.f);
+    uint32_t x = (g * 32 + lane < cnt) ? ent.y : 0u;
+    if (SLOTS == 4) {  // this quarter's 4x2 bits, replicated so that all four lanes of a pixel receive its mask
+      const int sh = 16 * (sub >> 1) + 4 * (sub & 1);
+      x = (((x >> sh) & 0xfu) | (((x >> (sh + 8)) & 0xfu) << 4)) * 0x01010101u;
     }
+    __syncwarp();
 
-    if (!done) {
-      // advance by at most one group per step, branch-free
-      if (!hi_loaded && base + 1 < staged) hi = buf.mask[((base + 1) % kWindow) * 32 + lane], hi_loaded = true;
-      if (lo == 0u && hi_loaded) {
-        lo = hi, hi = 0u, ++base;
-        hi_loaded = base + 1 < staged;
-        if (hi_loaded) hi = buf.mask[((base + 1) % kWindow) * 32 + lane];
-      }
-      unsigned long long c = ((unsigned long long)hi << 32) | lo;
-      const int seg0 = (base & (kWindow - 1)) * 32;  // base >= 0 whenever c != 0
-      int e[ILP], grp[ILP];
-      bool valid[ILP];
+    // prefetch: records of group g+1, list entries of group g+2
+    ent = ent_next;
+    if ((g + 1) * 32 + lane < cnt) {
+      const float4* q = reinterpret_cast<const float4*>(src + ent.x);
+      r0 = q[0], r1 = q[1], r2 = q[2];
+    }
+    ent_next = ((g + 2) * 32 + lane < cnt) ? list[(g + 2) * 32 + lane] : make_uint2(0u, 0u);
+
+    x = transpose32(x, lane);  // every lane takes part, saturated or not
+    uint32_t cand = done ? 0u : x;
+    const uint32_t before = last_contributor;
+
+    if (SLOTS == 1) {
+      while (cand) {  // lanes leave as their own pixel runs out of pairs
+        int e[ILP];
+        float al[ILP];
 #pragma unroll
-      for (int u = 0; u < ILP; ++u) {
-        valid[u] = c != 0ull;
-        const int bit = valid[u] ? __ffsll((long long)c) - 1 : 0;
-        c &= c - 1ull;
-        e[u] = (seg0 + bit) & (kWindow * 32 - 1);
-        grp[u] = base + (bit >> 5);
-      }
-      lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
-      float al[ILP];
+        for (int u = 0; u < ILP; ++u) {
+          const bool valid = cand != 0u;
+          e[u] = valid ? __ffs((int)cand) - 1 : 0;
+          cand &= cand - 1u;
+          al[u] = pair_alpha(buf.a[e[u]], buf.b[e[u]], pxf, pyf, valid);
+        }
 #pragma unroll
-      for (int u = 0; u < ILP; ++u) {
-        const float4 qa = buf.a[e[u]];
-        const float4 qb = buf.b[e[u]];
-        const float dx = __fadd_rn(qa.x, -pxf);
-        const float dy = __fadd_rn(qa.y, -pyf);
-        const float quad = __fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x)));
-        const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
-        const float v = fminf(0.99f, __fmul_rn(qb.y, expf(power)));
-        // reference: `if (power > 0) continue; ... if (alpha < 1/255) continue;`
-        al[u] = (valid[u] && !(power > 0.0f) && !(v < 1.0f / 255.0f)) ? v : -1.0f;
+        for (int u = 0; u < ILP; ++u) {
+          if (al[u] >= 0.0f && !done) {
+            const float4 qb = buf.b[e[u]];
+            const float4 qc = buf.c[e[u]];
+            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -al[u]));
+            if (test_T < 0.0001f) {  // reference: done = true; continue
+              done = true;
+              cand = 0u;
+            } else {
+              A = __fmaf_rn(T, al[u], A);
+              acc0 = __fmaf_rn(T, __fmul_rn(al[u], qc.y), acc0);
+              acc1 = __fmaf_rn(T, __fmul_rn(al[u], qb.z), acc1);
+              acc2 = __fmaf_rn(T, __fmul_rn(al[u], qb.w), acc2);
+              acc3 = __fmaf_rn(T, __fmul_rn(al[u], qc.x), acc3);
+              T = test_T;
+              last_contributor = __float_as_uint(qc.z);
+            }
+          }
+        }
       }
+    } else {
+      while (__any_sync(kFull, cand != 0u)) {  // the four lanes of a pixel hold the same mask
+        int e[4];
+        bool valid[4];
 #pragma unroll
-      for (int u = 0; u < ILP; ++u) {
-        if (al[u] >= 0.0f && !done) {
-          const float4 qb = buf.b[e[u]];
-          const float4 qc = buf.c[e[u]];
-          const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -al[u]));
-          if (test_T < 0.0001f) {  // reference: done = true; continue
-            done = true;
-          } else {
-            A = __fmaf_rn(T, al[u], A);
-            D = __fmaf_rn(T, __fmul_rn(al[u], qc.y), D);
-            C0 = __fmaf_rn(T, __fmul_rn(al[u], qb.z), C0);
-            C1 = __fmaf_rn(T, __fmul_rn(al[u], qb.w), C1);
-            C2 = __fmaf_rn(T, __fmul_rn(al[u], qc.x), C2);
-            T = test_T;
-            last_contributor = __float_as_uint(qc.z);
-            last_group = grp[u];
+        for (int j = 0; j < 4; ++j) {
+          valid[j] = cand != 0u;
+          e[j] = valid[j] ? __ffs((int)cand) - 1 : 0;
+          cand &= cand - 1u;
+        }
+        const int mine = slot == 0 ? e[0] : slot == 1 ? e[1] : slot == 2 ? e[2] : e[3];
+        const bool vmine = slot == 0 ? valid[0] : slot == 1 ? valid[1] : slot == 2 ? valid[2] : valid[3];
+        const float al = pair_alpha(buf.a[mine], buf.b[mine], pxf, pyf, vmine);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float alj = __shfl_sync(kFull, al, j * 8 + pix);
+          if (alj >= 0.0f && !done) {
+            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alj));
+            if (test_T < 0.0001f) {
+              done = true;
+              cand = 0u;
+            } else {
+              A = __fmaf_rn(T, alj, A);
+              acc0 = __fmaf_rn(T, __fmul_rn(alj, chan[4 * e[j]]), acc0);
+              T = test_T;
+              last_contributor = __float_as_uint(buf.c[e[j]].z);
+            }
           }
         }
       }
     }
+    if (__any_sync(kFull, last_contributor != before)) used = g + 1;
+    if (__all_sync(kFull, done)) break;  // also orders this group's shared-memory reads before the next stores
   }
 
   if (inside) {
     const size_t p = (size_t)a.W * py + px;
     const size_t plane = (size_t)a.W * a.H;
-    a.final_T[p] = T;
-    a.n_contrib[p] = last_contributor;
-    a.out_color[p] = __fmaf_rn(__ldg(a.bg + 0), T, C0);
-    a.out_color[plane + p] = __fmaf_rn(__ldg(a.bg + 1), T, C1);
-    a.out_color[2 * plane + p] = __fmaf_rn(__ldg(a.bg + 2), T, C2);
-    a.out_depth[p] = D;
-    a.out_acc[p] = A;
+    if (SLOTS == 1) {
+      a.final_T[p] = T;
+      a.n_contrib[p] = last_contributor;
+      a.out_color[p] = __fmaf_rn(__ldg(a.bg + 0), T, acc1);
+      a.out_color[plane + p] = __fmaf_rn(__ldg(a.bg + 1), T, acc2);
+      a.out_color[2 * plane + p] = __fmaf_rn(__ldg(a.bg + 2), T, acc3);
+      a.out_depth[p] = acc0;
+      a.out_acc[p] = A;
+    } else if (slot == 0) {
+      a.final_T[p] = T;
+      a.n_contrib[p] = last_contributor;
+      a.out_depth[p] = acc0;
+      a.out_acc[p] = A;
+    } else {
+      a.out_color[(size_t)(slot - 1) * plane + p] = __fmaf_rn(__ldg(a.bg + (slot - 1)), T, acc0);
+    }
   }
   const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
-  const int used = __reduce_max_sync(kFull, last_group + 1);
   if (lane == 0) {
-    a.block_used[tile * 8 + warp] = (uint32_t)used;  // groups of this block's list the backward has to walk
-    if (wmax) atomicMax(&a.tile_last[tile], wmax);   // tile_last is zeroed by order_tiles
+    // groups of this block's list the backward has to walk (block_lists zeroes block_used)
+    if (SLOTS == 1) a.block_used[tile * 8 + block] = (uint32_t)used;
+    else if (used) atomicMax(&a.block_used[tile * 8 + block], (uint32_t)used);
+    if (wmax) atomicMax(&a.tile_last[tile], wmax);  // tile_last is zeroed by order_tiles
+  }
+}
+
+// grid = 4*fine_tiles FINE candidates (tile_order[b/4], two blocks b%4 per CTA) followed by `tiles` COARSE candidates;
+// a CTA whose tile belongs to the other shape exits at once. The longest lists therefore start first.
+template <int ILP>
+__global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const FwdArgs a) {
+  __shared__ WarpBuf bufs[kWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = (int)blockIdx.x;
+  if (b < 4 * a.fine_tiles) {
+    const int tile = (int)a.tile_order[b >> 2];
+    const uint2 r = a.ranges[tile];
+    if ((int)(r.y - r.x) < a.heavy) return;
+    blend_block<4, 1>(a, bufs[warp], tile, 2 * (b & 3) + (warp >> 2), warp & 3, lane);
+  } else {
+    const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
+    const uint2 r = a.ranges[tile];
+    if ((int)(r.y - r.x) >= a.heavy) return;
+    blend_block<1, ILP>(a, bufs[warp], tile, warp, 0, lane);
   }
 }
 
@@ -205,28 +260,27 @@ cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img
                                     const float* background, float* out_color, float* out_depth, float* out_acc,
                                     cudaStream_t s) {
   const int grid_x = (width + kTile - 1) / kTile, grid_y = (height + kTile - 1) / kTile;
+  const int tiles = grid_x * grid_y;
   FwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.blist = b.blist;
   a.block_count = img.block_count, a.block_used = img.block_used;
   a.W = width, a.H = height, a.grid_x = grid_x;
+  static const int heavy = [] {
+    const char* e = getenv("GSR_FWD_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
+    return e ? atoi(e) : kHeavy;
+  }();
+  a.heavy = heavy;
+  a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;  // only the longest kFineCap lists can be FINE
   a.bg = background, a.out_color = out_color, a.out_depth = out_depth, a.out_acc = out_acc;
   a.final_T = img.final_T, a.n_contrib = img.n_contrib, a.tile_last = img.tile_last;
   static const int ilp = [] {
-    const char* e = getenv("GSR_FWD_ILP");  // tuning knob: alphas evaluated per lane per step (1, 2 or 4)
+    const char* e = getenv("GSR_FWD_ILP");  // tuning knob: alphas evaluated per lane per step, COARSE shape (1, 2 or 4)
     return e ? atoi(e) : 4;
   }();
-  const int tiles = grid_x * grid_y;
-  constexpr int kSmem = (int)sizeof(WarpBuf) * kWarps;
-  auto kernel = ilp == 1 ? blend_fwd_sparse_kernel<1> : ilp == 2 ? blend_fwd_sparse_kernel<2> : blend_fwd_sparse_kernel<4>;
-  static bool configured[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
-  kernel<<<tiles, kWarps * 32, kSmem, s>>>(a);
+  const int grid = 4 * a.fine_tiles + tiles;
+  if (ilp == 1) blend_fwd_sparse_kernel<1><<<grid, kWarps * 32, 0, s>>>(a);
+  else if (ilp == 2) blend_fwd_sparse_kernel<2><<<grid, kWarps * 32, 0, s>>>(a);
+  else blend_fwd_sparse_kernel<4><<<grid, kWarps * 32, 0, s>>>(a);
   return cudaGetLastError();
 }
 
