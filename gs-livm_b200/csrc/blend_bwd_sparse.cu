@@ -4,20 +4,22 @@
 // Replaces BACKWARD::render / renderCUDA<3> (reference src/cuda_rasterizer/backward.cu:438-603,675-713).
 // Like the reference, NO depth gradient is produced (backward.cu:567-571, rasterizer.cu:77-80).
 //
-// Same work decomposition as blend_fwd_sparse.cu, walked in reverse: a warp owns an 8x4 pixel block and
-// the block's candidate list (block_lists.cu), 32 candidates at a time, starting at the last group the
-// forward found a contributor in (block_used). Per group:
-//  B. lane = PIXEL walks the set bits of its transposed mask from the back: re-evaluates alpha, advances the
+// The forward (blend_fwd_sparse.cu) leaves, per 8x4 pixel block and per group of 32 candidates of the block's
+// list (block_lists.cu), one word per pixel: which candidates of the group it blended into that pixel. Those
+// are exactly the pairs the reference's backward does not `continue` on (backward.cu:528-544), so this kernel
+// walks them and nothing else, groups in reverse from each pixel's last one (last_group):
+//  B. lane = PIXEL walks the set bits of its hit word from the top: re-evaluates alpha, advances the
 //     reference's reverse recurrence (T, accumulated colour behind the pair) and leaves the only two
 //     numbers of the pair that depend on that recurrence in a shared-memory slot [candidate][pixel]:
-//     u = G * dL/dalpha and w = alpha * T (zeros for a pair the reference skips);
-//  C. lane = CANDIDATE walks the set bits of its own coverage mask, reads the slots and accumulates the 9
-//     sums of its Gaussian in registers; every gradient is linear in u or w:
+//     u = G * dL/dalpha and w = alpha * T;
+//  C. lane = CANDIDATE walks the set bits of the transposed hit words (its pixels), reads the slots and
+//     accumulates the 9 sums of its Gaussian in registers; every gradient is linear in u or w:
 //        dL/dcolour_c += w dL/dC_c            dL/dopacity += u
 //        dL/dconic    += -1/2 (op u) {dx^2, dx dy, dy^2}
 //        dL/dmean2D   += -(op u) {cx dx + cy dy, cz dy + cy dx} {W/2, H/2}
 //     and leaves with 9 RED.ADD.F32 per (Gaussian, block) -- no shuffle butterfly per pair, no atomics per
-//     pair (the reference issues 9 same-address atomics per blended pair).
+//     pair (the reference issues 9 same-address atomics per blended pair). Records of candidates that were
+//     blended nowhere in the block are never fetched.
 // The sums are the reference's sums in another order and association (as between two runs of the
 // reference itself): compared at 1e-4 relative, not bitwise.
 #include <cstdlib>
@@ -28,7 +30,6 @@ namespace gsr {
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kHeavy = 2048;   // tiles with at least this many instances use the FINE shape
 constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kSlotStride = 33;  // [candidate][pixel] slots, padded against bank conflicts (FINE uses 9 of them)
@@ -36,7 +37,7 @@ constexpr int kSlotStride = 33;  // [candidate][pixel] slots, padded against ban
 struct __align__(16) WarpBuf {
   float4 a[32];  // {mean2D.x, mean2D.y, conic.x, conic.y}
   float4 b[32];  // {conic.z, opacity, r, g}
-  float4 c[32];  // {b, bits(index in tile list + 1), -, -}
+  float cb[32];  // b
   float4 pix[32];  // per pixel {dL/dC_r, dL/dC_g, dL/dC_b, -}
   float2 slot[32 * kSlotStride];
 };
@@ -48,11 +49,12 @@ struct BwdArgs {
   const uint32_t* point_list;
   const uint2* blist;
   const uint32_t* block_count;
-  const uint32_t* block_used;
+  const uint32_t* bhits;
+  const uint32_t* tail_hits;
+  const uint32_t* last_group;
   int W, H, grid_x, heavy, fine_tiles;
   const float* bg;
   const float* final_T;
-  const uint32_t* n_contrib;
   const float *dL_dpix, *dL_dacc;
   float *dL_dmean2D, *dL_dconic, *dL_dopacity, *dL_dcolor;
 };
@@ -93,37 +95,48 @@ __device__ __forceinline__ float pair_recurrence(PixelState& s, float alpha, flo
   return dL_dalpha;
 }
 
+// exp / alpha of a blended pair, same operation order as the forward (the pair is known to pass its tests)
+__device__ __forceinline__ void pair_alpha(const float4 qa, const float4 qb, float pxf, float pyf, float& alpha, float& G) {
+  const float dx = __fadd_rn(qa.x, -pxf), dy = __fadd_rn(qa.y, -pyf);
+  const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
+                                -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
+  G = expf(power);
+  alpha = fminf(0.99f, __fmul_rn(qb.y, G));
+}
+
 // One warp, one 8x4 pixel block of a tile (COARSE, SLOTS = 1) or one 4x2 quarter `sub` of it with four lanes per
 // pixel (FINE, SLOTS = 4; see blend_fwd_sparse.cu): the four lanes evaluate exp/alpha of four consecutive
-// candidates of their pixel at once, all replay the ordered recurrence, and the lane that evaluated a pair leaves
+// pairs of their pixel at once, all replay the ordered recurrence, and the lane that evaluated a pair leaves
 // its (u, w) in the pair's slot.
 template <int SLOTS, int ILP>
 __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, int tile, int block, int sub, int lane) {
-  constexpr int NPIX = 32 / SLOTS;                        // pixels of this warp
-  constexpr int STRIDE = SLOTS == 1 ? kSlotStride : 9;    // slot row stride
+  constexpr int STRIDE = SLOTS == 1 ? kSlotStride : 9;  // slot row stride
   const uint2 range = a.ranges[tile];
   const int n = (int)(range.y - range.x);
   if (n == 0) return;
-  const int used = (int)a.block_used[tile * 8 + block];
-  if (used == 0) return;  // nothing was blended into this block's pixels
-  const int cnt = min((int)a.block_count[tile * 8 + block], used * 32);
+  const int cnt = (int)a.block_count[tile * 8 + block];
   const uint2* list = a.blist + (size_t)8 * range.x + (size_t)block * n;
+  const uint32_t* hits = a.bhits + (size_t)8 * range.x + (size_t)block * n;
+  const uint32_t* tail = a.tail_hits + (size_t)(tile * 8 + block) * 32;
   const SplatRecord* src = a.inst + range.x;
   const uint32_t* ids = a.point_list + range.x;
 
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
   const int pix = SLOTS == 1 ? lane : (lane & 7), slot = SLOTS == 1 ? 0 : (lane >> 3);
-  // origin of this warp's pixels, the pixel of this lane, and its shift inside the block's 32-bit coverage masks
+  // pixel inside the 8x4 block (= its bit in the coverage / its word in the hit masks), origin of this warp's pixels
+  const int bx = SLOTS == 1 ? (pix & 7) : 4 * (sub & 1) + (pix & 3);
+  const int by = SLOTS == 1 ? (pix >> 3) : 2 * (sub >> 1) + (pix >> 2);
   const int wx = tile_x * kTile + (block & 1) * 8 + (SLOTS == 1 ? 0 : 4 * (sub & 1));
   const int wy = tile_y * kTile + (block >> 1) * 4 + (SLOTS == 1 ? 0 : 2 * (sub >> 1));
-  const int px = wx + (SLOTS == 1 ? (pix & 7) : (pix & 3)), py = wy + (SLOTS == 1 ? (pix >> 3) : (pix >> 2));
-  const int sh = 16 * (sub >> 1) + 4 * (sub & 1);
+  const int px = tile_x * kTile + (block & 1) * 8 + bx, py = tile_y * kTile + (block >> 1) * 4 + by;
+  const int word = 8 * by + bx;
   const bool inside = px < a.W && py < a.H;
   const float pxf = (float)px, pyf = (float)py;
   const size_t p = (size_t)a.W * py + px;
   const size_t plane = (size_t)a.W * a.H;
-  const uint32_t last_contributor = inside ? a.n_contrib[p] : 0u;
-  if (SLOTS == 4 && __all_sync(kFull, last_contributor == 0u)) return;
+  const int lg = inside ? (int)a.last_group[p] : 0;  // groups [0, lg) hold this pixel's pairs
+  const int used = __reduce_max_sync(kFull, lg);
+  if (used == 0) return;  // nothing was blended into this warp's pixels
 
   PixelState st;
   st.T_final = inside ? a.final_T[p] : 0.f;
@@ -139,115 +152,93 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
   const float wxf = (float)wx, wyf = (float)wy;
 
-  // Groups used-1 .. 0. Within a group lane l holds candidate (31 - l) of the group, so that ascending bit order
-  // in the transposed masks is descending list order. Register pipeline as in the forward.
-  const int ngroups = used;
-  auto list_index = [&](int g, int l) { return g * 32 + 31 - l; };
-  uint2 ent = make_uint2(0u, 0u), ent_next = make_uint2(0u, 0u);
+  // hit word of this lane's pixel for group g (zero beyond the pixel's own last group)
+  auto hit_word = [&](int g) -> uint32_t {
+    if (g < 0 || g >= lg) return 0u;
+    return ((g + 1) * 32 <= cnt) ? hits[g * 32 + word] : tail[word];
+  };
+  // candidate-major view of a group's hit words: lane = candidate, bit = pixel of this warp
+  auto by_candidate = [&](uint32_t h) -> uint32_t {
+    const uint32_t t = transpose32(h, lane);
+    return SLOTS == 1 ? t : (t & 0xffu);
+  };
+
+  // Register pipeline, groups used-1 .. 0: hit words two groups ahead; one group ahead their candidate-major view
+  // and, for the candidates that were blended somewhere in this warp's pixels, the list entry -> record and id.
+  uint32_t h_cur = hit_word(used - 1), h_next = hit_word(used - 2);
+  uint32_t cm_next = by_candidate(h_cur);
   float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
   uint32_t gid = 0;
-  {
-    const int i0 = list_index(ngroups - 1, lane);
-    if (i0 < cnt) ent = list[i0];
-    const int i1 = list_index(ngroups - 2, lane);
-    if (ngroups >= 2 && i1 < cnt) ent_next = list[i1];
-    if (i0 < cnt) {
-      const float4* q = reinterpret_cast<const float4*>(src + ent.x);
-      r0 = q[0], r1 = q[1], r2 = q[2];
-      gid = ids[ent.x];
-    }
+  if (cm_next) {
+    const uint32_t at = list[(used - 1) * 32 + lane].x;
+    const float4* q = reinterpret_cast<const float4*>(src + at);
+    r0 = q[0], r1 = q[1], r2 = q[2];
+    gid = ids[at];
   }
 
-  for (int g = ngroups - 1; g >= 0; --g) {
+  for (int g = used - 1; g >= 0; --g) {
     buf.a[lane] = make_float4(r0.x, r0.y, r1.x, r1.y);
     buf.b[lane] = make_float4(r1.z, r1.w, r2.x, r2.y);
-    buf.c[lane] = make_float4(r2.z, __uint_as_float(ent.x + 1u), 0.f, 0.f);
-    uint32_t cov = (list_index(g, lane) < cnt) ? ent.y : 0u;
-    if (SLOTS == 4) cov = ((cov >> sh) & 0xfu) | (((cov >> (sh + 8)) & 0xfu) << 4);  // this quarter's 4x2 bits
-    const uint32_t my_id = gid;
+    buf.cb[lane] = r2.z;
+    const uint32_t cm = cm_next, my_id = gid;
+    uint32_t hh = h_cur;
     // this candidate's own parameters for phase C (before the pipeline registers move on)
     const float mx = r0.x, my = r0.y, cx = r1.x, cy = r1.y, cz = r1.z, op = r1.w;
     __syncwarp();
 
-    ent = ent_next;
-    if (g >= 1 && list_index(g - 1, lane) < cnt) {
-      const float4* q = reinterpret_cast<const float4*>(src + ent.x);
+    h_cur = h_next;
+    h_next = hit_word(g - 2);
+    cm_next = by_candidate(h_cur);
+    if (cm_next) {  // g >= 1 here: h_cur is zero below group 0
+      const uint32_t at = list[(g - 1) * 32 + lane].x;
+      const float4* q = reinterpret_cast<const float4*>(src + at);
       r0 = q[0], r1 = q[1], r2 = q[2];
-      gid = ids[ent.x];
+      gid = ids[at];
     }
-    ent_next = make_uint2(0u, 0u);
-    if (g >= 2 && list_index(g - 2, lane) < cnt) ent_next = list[list_index(g - 2, lane)];
 
-    uint32_t cand = transpose32(SLOTS == 1 ? cov : cov * 0x01010101u, lane);
-
-    // ---- phase B: lane = pixel ----
+    // ---- phase B: lane = pixel, pairs from the back ----
     if (SLOTS == 1) {
-      while (cand) {
+      while (hh) {
         int e[ILP];
+        bool valid[ILP];
         float al[ILP], G[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
-          const bool valid = cand != 0u;
-          e[u] = valid ? __ffs((int)cand) - 1 : -1;
-          cand &= cand - 1u;
-          const int ee = max(e[u], 0);
-          const float4 qa = buf.a[ee];
-          const float4 qb = buf.b[ee];
-          const float4 qc = buf.c[ee];
-          const float dx = qa.x - pxf, dy = qa.y - pyf;
-          const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
-                                        -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
-          const float gg = expf(power);
-          const float v = fminf(0.99f, __fmul_rn(qb.y, gg));
-          const bool on = valid && (__float_as_uint(qc.y) <= last_contributor) && !(power > 0.0f) && !(v < 1.0f / 255.0f);
-          G[u] = gg, al[u] = on ? v : -1.0f;
+          valid[u] = hh != 0u;
+          e[u] = valid[u] ? 31 - __clz((int)hh) : 0;
+          hh &= ~(1u << e[u]);
+          pair_alpha(buf.a[e[u]], buf.b[e[u]], pxf, pyf, al[u], G[u]);
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
-          if (e[u] < 0) continue;
-          float2 out = make_float2(0.f, 0.f);
-          if (al[u] >= 0.0f) {  // reference backward.cu:546-600
+          if (valid[u]) {  // reference backward.cu:546-600
             const float4 qb = buf.b[e[u]];
-            const float4 qc = buf.c[e[u]];
-            const float dL_dalpha = pair_recurrence(st, al[u], qb.z, qb.w, qc.x);
-            out = make_float2(G[u] * dL_dalpha, al[u] * st.T);
+            const float dL_dalpha = pair_recurrence(st, al[u], qb.z, qb.w, buf.cb[e[u]]);
+            buf.slot[e[u] * STRIDE + pix] = make_float2(G[u] * dL_dalpha, al[u] * st.T);
           }
-          buf.slot[e[u] * STRIDE + pix] = out;
         }
       }
     } else {
-      while (__any_sync(kFull, cand != 0u)) {  // the four lanes of a pixel hold the same mask
+      while (__any_sync(kFull, hh != 0u)) {  // the four lanes of a pixel hold the same word
         int e[4];
         bool valid[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          valid[j] = cand != 0u;
-          e[j] = valid[j] ? __ffs((int)cand) - 1 : 0;
-          cand &= cand - 1u;
+          valid[j] = hh != 0u;
+          e[j] = valid[j] ? 31 - __clz((int)hh) : 0;
+          hh &= ~(1u << e[j]);
         }
         const int mine = slot == 0 ? e[0] : slot == 1 ? e[1] : slot == 2 ? e[2] : e[3];
         const bool vmine = slot == 0 ? valid[0] : slot == 1 ? valid[1] : slot == 2 ? valid[2] : valid[3];
         float al, G;
-        {
-          const float4 qa = buf.a[mine];
-          const float4 qb = buf.b[mine];
-          const float4 qc = buf.c[mine];
-          const float dx = qa.x - pxf, dy = qa.y - pyf;
-          const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
-                                        -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
-          G = expf(power);
-          const float v = fminf(0.99f, __fmul_rn(qb.y, G));
-          const bool on = vmine && (__float_as_uint(qc.y) <= last_contributor) && !(power > 0.0f) && !(v < 1.0f / 255.0f);
-          al = on ? v : -1.0f;
-        }
+        pair_alpha(buf.a[mine], buf.b[mine], pxf, pyf, al, G);
         float2 out = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float alj = __shfl_sync(kFull, al, j * 8 + pix);
-          if (alj >= 0.0f) {
+          if (valid[j]) {
             const float4 qb = buf.b[e[j]];
-            const float4 qc = buf.c[e[j]];
-            const float dL_dalpha = pair_recurrence(st, alj, qb.z, qb.w, qc.x);
+            const float dL_dalpha = pair_recurrence(st, alj, qb.z, qb.w, buf.cb[e[j]]);
             if (slot == j) out = make_float2(G * dL_dalpha, alj * st.T);
           }
         }
@@ -257,10 +248,9 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
     __syncwarp();
 
     // ---- phase C: lane = candidate ----
-    {
+    if (cm) {
       float s_op = 0.f, s_x = 0.f, s_y = 0.f, s_xx = 0.f, s_xy = 0.f, s_yy = 0.f, s_c0 = 0.f, s_c1 = 0.f, s_c2 = 0.f;
-      bool hit = false;
-      uint32_t todo = cov;
+      uint32_t todo = cm;
       const float2* row = buf.slot + lane * STRIDE;
       while (todo) {
         const int k = __ffs((int)todo) - 1;
@@ -269,7 +259,6 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
         const float4 dp = buf.pix[k];
         const float kx = (float)(SLOTS == 1 ? (k & 7) : (k & 3)), ky = (float)(SLOTS == 1 ? (k >> 3) : (k >> 2));
         const float dx = mx - (wxf + kx), dy = my - (wyf + ky);
-        hit = hit || (uw.y != 0.0f);
         const float v = op * uw.x;
         const float vdx = v * dx, vdy = v * dy;
         s_op += uw.x;
@@ -277,18 +266,16 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
         s_xx = fmaf(vdx, dx, s_xx), s_xy = fmaf(vdx, dy, s_xy), s_yy = fmaf(vdy, dy, s_yy);
         s_c0 = fmaf(uw.y, dp.x, s_c0), s_c1 = fmaf(uw.y, dp.y, s_c1), s_c2 = fmaf(uw.y, dp.z, s_c2);
       }
-      if (hit) {
-        const size_t id = my_id;
-        atomicAdd(a.dL_dcolor + 3 * id + 0, s_c0);
-        atomicAdd(a.dL_dcolor + 3 * id + 1, s_c1);
-        atomicAdd(a.dL_dcolor + 3 * id + 2, s_c2);
-        atomicAdd(a.dL_dmean2D + 3 * id + 0, -(cx * s_x + cy * s_y) * ddelx_dx);
-        atomicAdd(a.dL_dmean2D + 3 * id + 1, -(cz * s_y + cy * s_x) * ddely_dy);
-        atomicAdd(a.dL_dconic + 4 * id + 0, -0.5f * s_xx);
-        atomicAdd(a.dL_dconic + 4 * id + 1, -0.5f * s_xy);
-        atomicAdd(a.dL_dconic + 4 * id + 3, -0.5f * s_yy);
-        atomicAdd(a.dL_dopacity + id, s_op);
-      }
+      const size_t id = my_id;
+      atomicAdd(a.dL_dcolor + 3 * id + 0, s_c0);
+      atomicAdd(a.dL_dcolor + 3 * id + 1, s_c1);
+      atomicAdd(a.dL_dcolor + 3 * id + 2, s_c2);
+      atomicAdd(a.dL_dmean2D + 3 * id + 0, -(cx * s_x + cy * s_y) * ddelx_dx);
+      atomicAdd(a.dL_dmean2D + 3 * id + 1, -(cz * s_y + cy * s_x) * ddely_dy);
+      atomicAdd(a.dL_dconic + 4 * id + 0, -0.5f * s_xx);
+      atomicAdd(a.dL_dconic + 4 * id + 1, -0.5f * s_xy);
+      atomicAdd(a.dL_dconic + 4 * id + 3, -0.5f * s_yy);
+      atomicAdd(a.dL_dopacity + id, s_op);
     }
     __syncwarp();  // slots and records are rewritten by the next group
   }
@@ -316,6 +303,8 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
 
 }  // namespace
 
+int blend_heavy_threshold();  // blend_fwd_sparse.cu: one threshold, the two kernels must agree on the shape of a tile
+
 cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
                                     const float* background, const float* dL_dpix, const float* dL_dacc,
                                     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
@@ -324,7 +313,7 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   const int tiles = grid_x * grid_y;
   constexpr int kSmem = (int)sizeof(WarpBuf) * kWarps;
   static const int ilp = [] {
-    const char* e = getenv("GSR_BWD_ILP");  // tuning knob: alphas evaluated per lane per step, COARSE shape (1 or 2)
+    const char* e = getenv("GSR_BWD_ILP");  // tuning knob: pairs evaluated per lane per step, COARSE shape (1 or 2)
     return e ? atoi(e) : 2;
   }();
   auto kernel = ilp == 1 ? blend_bwd_sparse_kernel<1> : blend_bwd_sparse_kernel<2>;
@@ -338,15 +327,12 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   }
   BwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
-  a.blist = b.blist, a.block_count = img.block_count, a.block_used = img.block_used;
+  a.blist = b.blist, a.block_count = img.block_count;
+  a.bhits = b.bhits, a.tail_hits = img.tail_hits, a.last_group = img.last_group;
   a.W = width, a.H = height, a.grid_x = grid_x;
-  static const int heavy = [] {
-    const char* e = getenv("GSR_BWD_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
-    return e ? atoi(e) : kHeavy;
-  }();
-  a.heavy = heavy;
+  a.heavy = blend_heavy_threshold();
   a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;
-  a.bg = background, a.final_T = img.final_T, a.n_contrib = img.n_contrib;
+  a.bg = background, a.final_T = img.final_T;
   a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;
   a.dL_dmean2D = dL_dmean2D, a.dL_dconic = dL_dconic, a.dL_dopacity = dL_dopacity, a.dL_dcolor = dL_dcolor;
   kernel<<<4 * a.fine_tiles + tiles, kWarps * 32, kSmem, s>>>(a);

@@ -26,7 +26,7 @@ namespace gsr {
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kHeavy = 2048;   // tiles with at least this many instances use the FINE shape
+constexpr int kHeavy = 4096;   // tiles with at least this many instances use the FINE shape
 constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -42,7 +42,9 @@ struct FwdArgs {
   const SplatRecord* inst;
   const uint2* blist;
   const uint32_t* block_count;
-  uint32_t* block_used;
+  uint32_t* last_group;
+  uint32_t* bhits;
+  uint32_t* tail_hits;
   int W, H, grid_x, heavy, fine_tiles;
   const float* bg;
   float *out_color, *out_depth, *out_acc, *final_T;
@@ -84,6 +86,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
   const int cnt = n ? (int)a.block_count[tile * 8 + block] : 0;
   const uint2* list = a.blist + (size_t)8 * range.x + (size_t)block * n;
   const SplatRecord* src = a.inst + range.x;
+  uint32_t* hits = a.bhits + (size_t)8 * range.x + (size_t)block * n;  // full groups; the partial last one: tail_hits
 
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
   const int pix = SLOTS == 1 ? lane : (lane & 7), slot = SLOTS == 1 ? 0 : (lane >> 3);
@@ -98,7 +101,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
   float T = 1.0f, A = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // COARSE: D, R, G, B; FINE: acc0 = own channel
   uint32_t last_contributor = 0;
   bool done = !inside;
-  int used = 0;
+  int last_group = 0;  // 1 + group of this pixel's last contributor
   // FINE: which word of a parked record this lane's channel is (slot 0: depth, 1-3: r, g, b)
   const float* chan = SLOTS == 1 ? nullptr
                                  : (slot == 0 ? &buf.c[0].y : slot == 1 ? &buf.b[0].z : slot == 2 ? &buf.b[0].w : &buf.c[0].x);
@@ -137,6 +140,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
     x = transpose32(x, lane);  // every lane takes part, saturated or not
     uint32_t cand = done ? 0u : x;
     const uint32_t before = last_contributor;
+    uint32_t hm = 0u;  // candidates of this group blended into this pixel
 
     if (SLOTS == 1) {
       while (cand) {  // lanes leave as their own pixel runs out of pairs
@@ -166,6 +170,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
               acc3 = __fmaf_rn(T, __fmul_rn(al[u], qc.x), acc3);
               T = test_T;
               last_contributor = __float_as_uint(qc.z);
+              hm |= 1u << e[u];
             }
           }
         }
@@ -196,12 +201,17 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
               acc0 = __fmaf_rn(T, __fmul_rn(alj, chan[4 * e[j]]), acc0);
               T = test_T;
               last_contributor = __float_as_uint(buf.c[e[j]].z);
+              hm |= 1u << e[j];
             }
           }
         }
       }
     }
-    if (__any_sync(kFull, last_contributor != before)) used = g + 1;
+    if (slot == 0) {  // the backward walks exactly the blended pairs: word = pixel (bit order of the coverage masks)
+      uint32_t* dst = ((g + 1) * 32 <= cnt) ? hits + g * 32 : a.tail_hits + (size_t)(tile * 8 + block) * 32;
+      dst[8 * by + bx] = hm;
+    }
+    if (last_contributor != before) last_group = g + 1;
     if (__all_sync(kFull, done)) break;  // also orders this group's shared-memory reads before the next stores
   }
 
@@ -211,6 +221,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
     if (SLOTS == 1) {
       a.final_T[p] = T;
       a.n_contrib[p] = last_contributor;
+      a.last_group[p] = (uint32_t)last_group;
       a.out_color[p] = __fmaf_rn(__ldg(a.bg + 0), T, acc1);
       a.out_color[plane + p] = __fmaf_rn(__ldg(a.bg + 1), T, acc2);
       a.out_color[2 * plane + p] = __fmaf_rn(__ldg(a.bg + 2), T, acc3);
@@ -219,6 +230,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
     } else if (slot == 0) {
       a.final_T[p] = T;
       a.n_contrib[p] = last_contributor;
+      a.last_group[p] = (uint32_t)last_group;
       a.out_depth[p] = acc0;
       a.out_acc[p] = A;
     } else {
@@ -226,12 +238,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
     }
   }
   const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
-  if (lane == 0) {
-    // groups of this block's list the backward has to walk (block_lists zeroes block_used)
-    if (SLOTS == 1) a.block_used[tile * 8 + block] = (uint32_t)used;
-    else if (used) atomicMax(&a.block_used[tile * 8 + block], (uint32_t)used);
-    if (wmax) atomicMax(&a.tile_last[tile], wmax);  // tile_last is zeroed by order_tiles
-  }
+  if (lane == 0 && wmax) atomicMax(&a.tile_last[tile], wmax);  // tile_last is zeroed by order_tiles
 }
 
 // grid = 4*fine_tiles FINE candidates (tile_order[b/4], two blocks b%4 per CTA) followed by `tiles` COARSE candidates;
@@ -256,6 +263,16 @@ __global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const Fwd
 
 }  // namespace
 
+// One threshold for the forward and the backward: both must give a tile the same warp shape (the hit masks the
+// forward leaves are per warp shape only in who writes them, but a tile's pixels must all have been written).
+int blend_heavy_threshold() {
+  static const int heavy = [] {
+    const char* e = getenv("GSR_BLEND_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
+    return e ? atoi(e) : kHeavy;
+  }();
+  return heavy;
+}
+
 cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
                                     const float* background, float* out_color, float* out_depth, float* out_acc,
                                     cudaStream_t s) {
@@ -263,13 +280,10 @@ cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img
   const int tiles = grid_x * grid_y;
   FwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.blist = b.blist;
-  a.block_count = img.block_count, a.block_used = img.block_used;
+  a.block_count = img.block_count, a.last_group = img.last_group;
+  a.bhits = b.bhits, a.tail_hits = img.tail_hits;
   a.W = width, a.H = height, a.grid_x = grid_x;
-  static const int heavy = [] {
-    const char* e = getenv("GSR_FWD_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
-    return e ? atoi(e) : kHeavy;
-  }();
-  a.heavy = heavy;
+  a.heavy = blend_heavy_threshold();
   a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;  // only the longest kFineCap lists can be FINE
   a.bg = background, a.out_color = out_color, a.out_depth = out_depth, a.out_acc = out_acc;
   a.final_T = img.final_T, a.n_contrib = img.n_contrib, a.tile_last = img.tile_last;

@@ -28,7 +28,6 @@ struct BlockListArgs {
   const SplatRecord* inst;
   uint2* blist;
   uint32_t* block_count;
-  uint32_t* block_used;
   int grid_x;
 };
 
@@ -61,7 +60,7 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
   const uint2 range = a.ranges[tile];
   const int n = (int)(range.y - range.x);
   if (n == 0) {
-    if (threadIdx.x < 8) a.block_count[tile * 8 + threadIdx.x] = 0, a.block_used[tile * 8 + threadIdx.x] = 0;
+    if (threadIdx.x < 8) a.block_count[tile * 8 + threadIdx.x] = 0;
     return;
   }
   const float tx0 = (float)((tile % a.grid_x) * kTile), ty0 = (float)((tile / a.grid_x) * kTile);
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
     run += total;
     // counts[it & 1] is rewritten two iterations from now, behind the next iteration's barrier
   }
-  if (warp == 0 && lane < 8) a.block_count[tile * 8 + lane] = run, a.block_used[tile * 8 + lane] = 0;  // see blend_fwd_sparse
+  if (warp == 0 && lane < 8) a.block_count[tile * 8 + lane] = run;
 }
 
 }  // namespace
@@ -115,7 +114,7 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
 cudaError_t launch_block_lists(int tiles, const ImageState& img, const BinningState& b, int grid_x, cudaStream_t s) {
   BlockListArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.blist = b.blist;
-  a.block_count = img.block_count, a.block_used = img.block_used, a.grid_x = grid_x;
+  a.block_count = img.block_count, a.grid_x = grid_x;
   block_lists_kernel<<<tiles, kWarps * 32, 0, s>>>(a);
   return cudaGetLastError();
 }

@@ -93,7 +93,8 @@ ImageState carve_image(char* chunk, int width, int height) {
   carve(chunk, s.tile_count, tiles);
   carve(chunk, s.summary, 4);
   carve(chunk, s.block_count, tiles * 8);
-  carve(chunk, s.block_used, tiles * 8);
+  carve(chunk, s.last_group, N);
+  carve(chunk, s.tail_hits, tiles * 8 * 32);
   return s;
 }
 
@@ -107,6 +108,7 @@ BinningState carve_binning(char* chunk, int R) {
   carve(chunk, b.vals_unsorted, n);
   carve(chunk, b.vals, n + 4);  // +16 B: blend_bwd bulk-copies ids from an aligned-down start
   carve(chunk, b.blist, 8 * n);
+  carve(chunk, b.bhits, 8 * n);
   b.sort_temp_bytes = sort_temp_bytes(R);
   carve(chunk, b.sort_temp, b.sort_temp_bytes);
   return b;
@@ -179,7 +181,7 @@ size_t gsr_required_image(int width, int height) {
   return required_bytes([&] {
     ImageState s = carve_image(nullptr, width, height);
     const size_t tiles = (size_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    return (size_t)(reinterpret_cast<uintptr_t>(s.block_used + tiles * 8));
+    return (size_t)(reinterpret_cast<uintptr_t>(s.tail_hits + tiles * 8 * 32));
   });
 }
 
@@ -206,7 +208,7 @@ static int validate_fwd(const gsr_fwd_args& a, const char* who) {
 
 // Blend implementations: "sparse" (default; per-block candidate lists, blend_*_sparse.cu), "warp" (lock-step warps
 // over the whole tile list, blend_fwd.cu / blend_bwd.cu), "mask" (coverage-mask experiment). The sparse backward
-// needs the sparse forward's block_used, so it is only taken when the forward was sparse as well.
+// needs the sparse forward's hit masks, so it is only taken when the forward was sparse as well.
 enum BlendImpl { kBlendSparse = 0, kBlendWarp = 1, kBlendMask = 2 };
 static BlendImpl blend_impl(const char* var) {
   const char* e = getenv(var);

@@ -62,7 +62,8 @@ struct ImageState {
   uint32_t* tile_count; // [tiles] instances per tile (preprocess), then the tile's scatter cursor (tile_sort.cu)
   uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, overflow code (sync-free forward)}
   uint32_t* block_count;  // [tiles*8] candidates per 8x4 pixel block (block_lists.cu)
-  uint32_t* block_used;   // [tiles*8] groups of 32 candidates up to the block's last contributor (blend_fwd_sparse.cu)
+  uint32_t* last_group;   // [W*H] 1 + the group (of 32 candidates of its block's list) of the pixel's last contributor
+  uint32_t* tail_hits;    // [tiles*8][32] hit masks of each block's last, partial group (see BinningState::bhits)
 };
 
 // tile_sort.cu: lists up to kSmallMax instances are sorted by a 256-thread CTA (kSmallCap slots of shared
@@ -79,6 +80,9 @@ struct BinningState {
   InstAux* aux;             // [R] clipped boxes / thresholds / ids in sorted order
   uint2* blist;             // [8R] per-block candidate lists {index in the tile list, coverage mask}: block b of a
                             //      tile with range [r, r+n) owns entries 8r + b*n .. 8r + (b+1)*n (block_lists.cu)
+  uint32_t* bhits;          // [8R] same indexing: word 32g + p of a block = which candidates of the block's group g
+                            //      were blended into pixel p (bit 8*row + col order) by the forward; the backward walks
+                            //      exactly those pairs. A last group of fewer than 32 candidates lives in tail_hits.
   char* sort_temp;
   size_t sort_temp_bytes;
 };
