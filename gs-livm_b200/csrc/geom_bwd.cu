@@ -132,12 +132,22 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   float A0 = 0, A1 = 0, A2 = 0, B0 = 0, B1 = 0, B2 = 0, C0 = 0, C1 = 0, C2 = 0;  // rows of M = S*R
   float R00 = 0, R01 = 0, R02 = 0, R10 = 0, R11 = 0, R12 = 0, R20 = 0, R21 = 0, R22 = 0;
   float mx = 0.f, my = 0.f, mz = 0.f;
+  uint32_t cl_early = 0;
+  float dRGB_early[3] = {0.f, 0.f, 0.f};
   if (active) {
 
   const float* V = s_view;
   const float* PM = s_proj;
   mx = __ldg(a.means3D + 3 * (size_t)idx), my = __ldg(a.means3D + 3 * (size_t)idx + 1),
   mz = __ldg(a.means3D + 3 * (size_t)idx + 2);
+  // every other per-Gaussian input is requested here as well, so that one memory latency is exposed, not five
+  const float4 dcon = __ldg(reinterpret_cast<const float4*>(a.dL_dconic) + idx);  // x, y, (unused), w
+  const float d2x = __ldg(a.dL_dmean2D + 3 * (size_t)idx), d2y = __ldg(a.dL_dmean2D + 3 * (size_t)idx + 1);
+  if (a.shs) {
+    cl_early = a.clamped[idx];
+    dRGB_early[0] = __ldg(a.dL_dcolor + 3 * (size_t)idx), dRGB_early[1] = __ldg(a.dL_dcolor + 3 * (size_t)idx + 1);
+    dRGB_early[2] = __ldg(a.dL_dcolor + 3 * (size_t)idx + 2);
+  }
 
   // ---- forward recomputation: 3D covariance (same DAG as preprocess.cu) --------------------------
   float c0, c1, c2, c3, c4, c5;
@@ -194,7 +204,6 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   const float cb = dot3_ref(T00, v0, T01, v1, T02, v2);
   const float cc = __fadd_rn(dot3_ref(T10, v0, T11, v1, T12, v2), 0.3f);
 
-  const float4 dcon = __ldg(reinterpret_cast<const float4*>(a.dL_dconic) + idx);  // x, y, (unused), w
   const float denom = ca * cc - cb * cb;
   const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
   float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
@@ -238,7 +247,6 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
     const float m_w = 1.0f / hw;
     const float mul1 = (PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12]) * m_w * m_w;
     const float mul2 = (PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13]) * m_w * m_w;
-    const float d2x = __ldg(a.dL_dmean2D + 3 * (size_t)idx), d2y = __ldg(a.dL_dmean2D + 3 * (size_t)idx + 1);
     gmx += (PM[0] * m_w - PM[3] * mul1) * d2x + (PM[1] * m_w - PM[3] * mul2) * d2y;
     gmy += (PM[4] * m_w - PM[7] * mul1) * d2x + (PM[5] * m_w - PM[7] * mul2) * d2y;
     gmz += (PM[8] * m_w - PM[11] * mul1) * d2x + (PM[9] * m_w - PM[11] * mul2) * d2y;
@@ -255,10 +263,10 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
     const float ox = mx - s_cam[0], oy = my - s_cam[1], oz = mz - s_cam[2];
     const float len = sqrtf(ox * ox + oy * oy + oz * oz);
     const float x = ox / len, y = oy / len, z = oz / len;
-    const uint32_t cl = a.clamped[idx];
+    const uint32_t cl = cl_early;
     float dRGB[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) dRGB[c] = ((cl >> c) & 1u) ? 0.f : __ldg(a.dL_dcolor + 3 * (size_t)idx + c);
+    for (int c = 0; c < 3; ++c) dRGB[c] = ((cl >> c) & 1u) ? 0.f : dRGB_early[c];
     float b[16], bx[16], by[16], bz[16];
     sh_basis(a.D, x, y, z, b, bx, by, bz);
     const int ncoef = (a.D + 1) * (a.D + 1);

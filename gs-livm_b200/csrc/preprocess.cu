@@ -123,8 +123,16 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
   }
   stage_floats(s_means, a.means3D + (size_t)base * 3, n * 3, a.vec_ok);
   if (a.scales) stage_floats(s_scales, a.scales + (size_t)base * 3, n * 3, a.vec_ok);
-  __syncthreads();
   const int idx = base + tid;
+  // the two per-Gaussian inputs that are not staged are requested before the barrier as well, so their latency
+  // overlaps the staging instead of being exposed in the middle of the covariance math
+  float4 rot_in = make_float4(0.f, 0.f, 0.f, 0.f);
+  float op_in = 0.f;
+  if (tid < n) {
+    if (!a.cov3D_precomp) rot_in = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+    op_in = __ldg(a.opacities + idx);
+  }
+  __syncthreads();
 
   int out_radius = 0;
   int rect_x0 = 0, rect_y0 = 0, rect_w = 1;
@@ -134,6 +142,42 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
   float rdepth = 0.f;
   const float px = tid < n ? s_means[3 * tid] : 0.f, py = tid < n ? s_means[3 * tid + 1] : 0.f,
               pz = tid < n ? s_means[3 * tid + 2] : 0.f;
+
+  // SH rows of the Gaussians that will most likely survive are requested NOW (coalesced cp.async), so the 192-byte
+  // rows arrive while the covariance math runs: in front of the near plane, not oversized, and projected within a
+  // generous bound of the image. The test is only a prefetch heuristic: a survivor it missed is fetched after the
+  // exact tests (second pass below), a culled Gaussian it let through costs one wasted row.
+  bool prefetched = false;
+  if (kVec16) {
+    if (tid < n) {
+      const float zc = xform_row(s_view, 2, px, py, pz);
+      bool likely = zc > 0.2f;
+      float smax = 0.3f;
+      if (a.scales) {
+        smax = fmaxf(fmaxf(s_scales[3 * tid], s_scales[3 * tid + 1]), s_scales[3 * tid + 2]) * a.scale_modifier;
+        likely = likely && !(smax > 0.3f);
+      }
+      if (likely) {
+        const float w = xform_row(s_proj, 3, px, py, pz) + 0.0000001f;
+        const float cxp = 0.5f * ((xform_row(s_proj, 0, px, py, pz) / w + 1.0f) * (float)a.W - 1.0f);
+        const float cyp = 0.5f * ((xform_row(s_proj, 1, px, py, pz) / w + 1.0f) * (float)a.H - 1.0f);
+        const float rb = 3.0f * sqrtf(2.25f * smax * smax * fmaxf(a.focal_x, a.focal_y) * fmaxf(a.focal_x, a.focal_y) / (zc * zc) + 0.3f) + 17.0f;
+        likely = (cxp + rb > 0.f) && (cxp - rb < (float)a.W) && (cyp + rb > 0.f) && (cyp - rb < (float)a.H);
+      }
+      prefetched = likely;
+    }
+    s_survive[tid] = prefetched;
+    __syncthreads();
+    const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
+    for (int q = tid; q < n * 12; q += 256) {
+      const int row = q / 12;
+      if (s_survive[row]) {
+        const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 
   if (tid < n) do {  // single-pass block; `break` == the reference's early `return` with radius/tiles left at 0
     const float* V = s_view;
@@ -166,7 +210,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
       const float* cp = a.cov3D_precomp + (size_t)idx * 6;
       c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2), c3 = __ldg(cp + 3), c4 = __ldg(cp + 4), c5 = __ldg(cp + 5);
     } else {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      const float4 q = rot_in;
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
       const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
@@ -260,7 +304,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
 
     // Conservative extent of {pixels where the reference can reach alpha >= 1/255} (ours).
     // power = -q(d), q = 1/2 d^T Q d, Q = conic, Q^-1 = cov2D  =>  |dx| <= sqrt(2 tau cov_x).
-    const float op = __ldg(a.opacities + idx);
+    const float op = op_in;
     float ex = INFINITY, ey = INFINITY;
     if (op < 1.0f / 255.0f) {
       ex = ey = -INFINITY;  // alpha = op*exp(power<=0) <= op < 1/255 for every pixel
@@ -300,18 +344,22 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
     }
   }
 
-  if (kVec16) {  // cooperative, coalesced staging of the survivors' SH rows (uniform control flow)
-    s_survive[tid] = survive;
-    __syncthreads();
-    const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += 256) {
-      const int row = q / 12;
-      if (s_survive[row]) {
-        const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
+  if (kVec16) {  // second pass: survivors the prefetch heuristic missed (uniform control flow)
+    const bool late = survive && !prefetched;
+    if (__syncthreads_or(late)) {  // also: everybody is done reading s_survive in the first pass
+      s_survive[tid] = late;
+      __syncthreads();
+      const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
+      for (int q = tid; q < n * 12; q += 256) {
+        const int row = q / 12;
+        if (s_survive[row]) {
+          const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
 
