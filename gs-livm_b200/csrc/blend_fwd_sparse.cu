@@ -154,26 +154,24 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
           al[u] = pair_alpha(buf.a[e[u]], buf.b[e[u]], pxf, pyf, valid);
         }
 #pragma unroll
-        for (int u = 0; u < ILP; ++u) {
-          if (al[u] >= 0.0f && !done) {
-            const float4 qb = buf.b[e[u]];
-            const float4 qc = buf.c[e[u]];
-            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -al[u]));
-            if (test_T < 0.0001f) {  // reference: done = true; continue
-              done = true;
-              cand = 0u;
-            } else {
-              A = __fmaf_rn(T, al[u], A);
-              acc0 = __fmaf_rn(T, __fmul_rn(al[u], qc.y), acc0);
-              acc1 = __fmaf_rn(T, __fmul_rn(al[u], qb.z), acc1);
-              acc2 = __fmaf_rn(T, __fmul_rn(al[u], qb.w), acc2);
-              acc3 = __fmaf_rn(T, __fmul_rn(al[u], qc.x), acc3);
-              T = test_T;
-              last_contributor = __float_as_uint(qc.z);
-              hm |= 1u << e[u];
-            }
-          }
+        for (int u = 0; u < ILP; ++u) {  // ordered recurrence, branch-free: only T * (1 - alpha) is on the chain
+          const float4 qb = buf.b[e[u]];
+          const float4 qc = buf.c[e[u]];
+          const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -al[u]));
+          const bool on = al[u] >= 0.0f && !done;
+          const bool kill = on && test_T < 0.0001f;  // reference: done = true; continue
+          const bool ok = on && !kill;
+          A = ok ? __fmaf_rn(T, al[u], A) : A;
+          acc0 = ok ? __fmaf_rn(T, __fmul_rn(al[u], qc.y), acc0) : acc0;
+          acc1 = ok ? __fmaf_rn(T, __fmul_rn(al[u], qb.z), acc1) : acc1;
+          acc2 = ok ? __fmaf_rn(T, __fmul_rn(al[u], qb.w), acc2) : acc2;
+          acc3 = ok ? __fmaf_rn(T, __fmul_rn(al[u], qc.x), acc3) : acc3;
+          T = ok ? test_T : T;
+          last_contributor = ok ? __float_as_uint(qc.z) : last_contributor;
+          hm |= ok ? (1u << e[u]) : 0u;
+          done = done || kill;
         }
+        if (done) cand = 0u;
       }
     } else {
       while (__any_sync(kFull, cand != 0u)) {  // the four lanes of a pixel hold the same mask
@@ -188,23 +186,28 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int 
         const int mine = slot == 0 ? e[0] : slot == 1 ? e[1] : slot == 2 ? e[2] : e[3];
         const bool vmine = slot == 0 ? valid[0] : slot == 1 ? valid[1] : slot == 2 ? valid[2] : valid[3];
         const float al = pair_alpha(buf.a[mine], buf.b[mine], pxf, pyf, vmine);
+        float alj[4], val[4];
+        uint32_t idx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float alj = __shfl_sync(kFull, al, j * 8 + pix);
-          if (alj >= 0.0f && !done) {
-            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alj));
-            if (test_T < 0.0001f) {
-              done = true;
-              cand = 0u;
-            } else {
-              A = __fmaf_rn(T, alj, A);
-              acc0 = __fmaf_rn(T, __fmul_rn(alj, chan[4 * e[j]]), acc0);
-              T = test_T;
-              last_contributor = __float_as_uint(buf.c[e[j]].z);
-              hm |= 1u << e[j];
-            }
-          }
+          alj[j] = __shfl_sync(kFull, al, j * 8 + pix);
+          val[j] = chan[4 * e[j]];
+          idx[j] = __float_as_uint(buf.c[e[j]].z);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // ordered recurrence, branch-free: only T * (1 - alpha) is on the chain
+          const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alj[j]));
+          const bool on = alj[j] >= 0.0f && !done;
+          const bool kill = on && test_T < 0.0001f;
+          const bool ok = on && !kill;
+          A = ok ? __fmaf_rn(T, alj[j], A) : A;
+          acc0 = ok ? __fmaf_rn(T, __fmul_rn(alj[j], val[j]), acc0) : acc0;
+          T = ok ? test_T : T;
+          last_contributor = ok ? idx[j] : last_contributor;
+          hm |= ok ? (1u << e[j]) : 0u;
+          done = done || kill;
+        }
+        if (done) cand = 0u;
       }
     }
     if (slot == 0) {  // the backward walks exactly the blended pairs: word = pixel (bit order of the coverage masks)
