@@ -63,7 +63,7 @@ class GeomView(C.Structure):
 class BinningView(C.Structure):
     _fields_ = [(n, ArrayView) for n in (
         "point_list_keys_unsorted", "point_list_unsorted", "point_list_keys", "point_list", "instance_records",
-        "instance_aux")]
+        "block_candidates")]
 
 
 class ImageView(C.Structure):

@@ -82,28 +82,12 @@ __global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const S
   }
 }
 
-// Conservative box of {pixels where the instance can reach alpha >= 1/255}, clipped to the 16x16 tile at
-// (tx0, ty0), inclusive tile-local coordinates. extent = +inf -> whole tile, -inf -> empty; NaNs make every
-// comparison false -> whole tile (such pairs are then evaluated exactly like the reference evaluates them).
-__device__ __forceinline__ uint32_t clipped_box(float x, float y, float ex, float ey, float tx0, float ty0) {
-  const float lx = x - ex - tx0, hx = x + ex - tx0;
-  const float ly = y - ey - ty0, hy = y + ey - ty0;
-  const int x0 = (lx > 0.0f) ? (int)ceilf(fminf(lx, 16.0f)) : 0;
-  const int x1 = (hx < 15.0f) ? (int)floorf(fmaxf(hx, -1.0f)) : 15;
-  const int y0 = (ly > 0.0f) ? (int)ceilf(fminf(ly, 16.0f)) : 0;
-  const int y1 = (hy < 15.0f) ? (int)floorf(fmaxf(hy, -1.0f)) : 15;
-  if (x1 < x0 || y1 < y0) return 0u;
-  return kBoxValid | (uint32_t)x0 | ((uint32_t)x1 << 4) | ((uint32_t)y0 << 8) | ((uint32_t)y1 << 12);
-}
-
 // One thread per sorted instance: tile range boundaries (identifyTileRanges) fused with the gather of
-// the Gaussian's 48-byte record into sorted order (so the blend kernels read contiguous batches) and with
-// the instance's 16-byte aux record (clipped box, power floor, Gaussian id).
+// the Gaussian's 48-byte record into sorted order (so the blend kernels read contiguous batches).
 __global__ void __launch_bounds__(256) finalize_binning_kernel(int R, const uint64_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ vals,
                                                               const SplatRecord* __restrict__ rec,
                                                               SplatRecord* __restrict__ inst,
-                                                              InstAux* __restrict__ aux, int grid_x,
                                                               uint2* __restrict__ ranges) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
@@ -124,16 +108,6 @@ __global__ void __launch_bounds__(256) finalize_binning_kernel(int R, const uint
   float4* dst = reinterpret_cast<float4*>(inst + i);
   const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
   dst[0] = a, dst[1] = b, dst[2] = c;
-
-  InstAux x;
-  x.box = clipped_box(a.x, a.y, a.z, a.w, (float)((tile % (uint32_t)grid_x) * kTile),
-                      (float)((tile / (uint32_t)grid_x) * kTile));
-  // alpha = min(0.99, o * expf(power)) >= 1/255 needs power >= -ln(255 o) up to a few ulp of expf and of the
-  // product; the margin is 1e-4 absolute in the exponent. A NaN threshold keeps every pair.
-  x.pmin = -(logf(255.0f * b.w) + 1.0e-4f);
-  x.id = id;
-  x.pad = 0;
-  aux[i] = x;
 }
 
 // Launch order of the blend CTAs: tiles bucketed by floor(log2(list length)) and emitted longest
@@ -182,7 +156,7 @@ cudaError_t launch_duplicate_with_keys(int P, const GeomState& g, const int* rad
 cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomState& g, int grid_x, uint2* ranges,
                                     cudaStream_t s) {
   if (R <= 0) return cudaSuccess;
-  finalize_binning_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, b.keys, b.vals, g.rec, b.inst, b.aux, grid_x, ranges);
+  finalize_binning_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, b.keys, b.vals, g.rec, b.inst, ranges);
   return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@
 namespace gsr {
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;  // 10.5 KB of shared memory per warp: 4-warp CTAs pack an SM more tightly than 8-warp ones
 constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kSlotStride = 33;  // [candidate][pixel] slots, padded against bank conflicts (FINE uses 9 of them)
@@ -281,23 +281,25 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
   }
 }
 
-// grid = 4*fine_tiles FINE candidates (tile_order[b/4], two blocks b%4 per CTA) followed by `tiles` COARSE candidates.
+// grid = 8*fine_tiles FINE candidates (tile_order[b/8], block b%8, one 4x2 quarter per warp) followed by 2*tiles
+// COARSE candidates (tile_order[b/2], four blocks per CTA); a CTA whose tile belongs to the other shape exits.
 template <int ILP>
 __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpBuf& buf = reinterpret_cast<WarpBuf*>(smem_raw)[warp];
   const int b = (int)blockIdx.x;
-  if (b < 4 * a.fine_tiles) {
-    const int tile = (int)a.tile_order[b >> 2];
+  if (b < 8 * a.fine_tiles) {
+    const int tile = (int)a.tile_order[b >> 3];
     const uint2 r = a.ranges[tile];
     if ((int)(r.y - r.x) < a.heavy) return;
-    blend_bwd_block<4, 1>(a, buf, tile, 2 * (b & 3) + (warp >> 2), warp & 3, lane);
+    blend_bwd_block<4, 1>(a, buf, tile, b & 7, warp, lane);
   } else {
-    const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
+    const int c = b - 8 * a.fine_tiles;
+    const int tile = (int)a.tile_order[c >> 1];
     const uint2 r = a.ranges[tile];
     if ((int)(r.y - r.x) >= a.heavy) return;
-    blend_bwd_block<1, ILP>(a, buf, tile, warp, 0, lane);
+    blend_bwd_block<1, ILP>(a, buf, tile, (c & 1) * 4 + warp, 0, lane);
   }
 }
 
@@ -335,7 +337,7 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   a.bg = background, a.final_T = img.final_T;
   a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;
   a.dL_dmean2D = dL_dmean2D, a.dL_dconic = dL_dconic, a.dL_dopacity = dL_dopacity, a.dL_dcolor = dL_dcolor;
-  kernel<<<4 * a.fine_tiles + tiles, kWarps * 32, kSmem, s>>>(a);
+  kernel<<<8 * a.fine_tiles + 2 * tiles, kWarps * 32, kSmem, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -102,7 +102,6 @@ BinningState carve_binning(char* chunk, int R) {
   BinningState b;
   const size_t n = (size_t)R;
   carve(chunk, b.inst, n);
-  carve(chunk, b.aux, n);
   carve(chunk, b.keys_unsorted, n);
   carve(chunk, b.keys, n);
   carve(chunk, b.vals_unsorted, n);
@@ -206,14 +205,13 @@ static int validate_fwd(const gsr_fwd_args& a, const char* who) {
   return GSR_OK;
 }
 
-// Blend implementations: "sparse" (default; per-block candidate lists, blend_*_sparse.cu), "warp" (lock-step warps
-// over the whole tile list, blend_fwd.cu / blend_bwd.cu), "mask" (coverage-mask experiment). The sparse backward
+// Blend implementations: "sparse" (default; per-block candidate lists, blend_*_sparse.cu) and "warp" (lock-step
+// warps over the whole tile list, blend_fwd.cu / blend_bwd.cu; the round-1 kernels, kept for A/B). The sparse backward
 // needs the sparse forward's hit masks, so it is only taken when the forward was sparse as well.
-enum BlendImpl { kBlendSparse = 0, kBlendWarp = 1, kBlendMask = 2 };
+enum BlendImpl { kBlendSparse = 0, kBlendWarp = 1 };
 static BlendImpl blend_impl(const char* var) {
   const char* e = getenv(var);
   if (e && !strcmp(e, "warp")) return kBlendWarp;
-  if (e && !strcmp(e, "mask")) return kBlendMask;
   return kBlendSparse;
 }
 static BlendImpl fwd_impl() { static const BlendImpl v = blend_impl("GSR_FWD_IMPL"); return v; }
@@ -227,7 +225,7 @@ static int launch_blend_forward(const gsr_fwd_args& a, const ImageState& img, co
   const BlendImpl impl = fwd_impl();
   if (impl == kBlendSparse)
     GSR_STAGE(GSR_STAGE_FINALIZE, launch_block_lists(tiles, img, bin, grid_x, stream), "block_lists", debug, stream);
-  auto fn = impl == kBlendSparse ? launch_blend_fwd_sparse : impl == kBlendWarp ? launch_blend_fwd : launch_blend_fwd_mask;
+  auto fn = impl == kBlendSparse ? launch_blend_fwd_sparse : launch_blend_fwd;
   GSR_STAGE(GSR_STAGE_BLEND_FWD,
             fn(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream), "blend_fwd",
             debug, stream);
@@ -387,7 +385,7 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   }
   if (a.R > 0) {
     const BlendImpl impl = bwd_impl();
-    auto fn = impl == kBlendSparse ? launch_blend_bwd_sparse : impl == kBlendWarp ? launch_blend_bwd : launch_blend_bwd_mask;
+    auto fn = impl == kBlendSparse ? launch_blend_bwd_sparse : launch_blend_bwd;
     GSR_STAGE(GSR_STAGE_BLEND_BWD,
               fn(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D, a.dL_dconic,
                  a.dL_dopacity, a.dL_dcolor, stream),
@@ -437,7 +435,7 @@ int gsr_view_binning(char* binning_buffer, int R, gsr_binning_view* out) {
   out->point_list_keys = view_of(b.keys, 8, n);
   out->point_list = view_of(b.vals, 4, n);
   out->instance_records = view_of(b.inst, sizeof(SplatRecord), n);
-  out->instance_aux = view_of(b.aux, sizeof(InstAux), n);
+  out->block_candidates = view_of(b.blist, sizeof(uint2), 8 * n);
   return GSR_OK;
 }
 

@@ -29,20 +29,6 @@ struct alignas(16) SplatRecord {
 };
 static_assert(sizeof(SplatRecord) == 48, "record must be 3 x 16 B for bulk copies");
 
-// Per sorted instance, what the coverage-mask blend kernels need before touching the record (16 B):
-//   box   bits 0-3 x0, 4-7 x1, 8-11 y0, 12-15 y1 (inclusive, tile-local pixels), bit 16 = box not empty:
-//         the instance's conservative box of {alpha >= 1/255} clipped to ITS tile;
-//   pmin  pairs with power < pmin cannot reach alpha >= 1/255 (-(ln(255 opacity) + margin));
-//   id    Gaussian index (== point_list), where the backward scatters gradients.
-struct alignas(16) InstAux {
-  uint32_t box;
-  float pmin;
-  uint32_t id;
-  uint32_t pad;
-};
-static_assert(sizeof(InstAux) == 16, "aux records are bulk-copied as 16-byte units");
-constexpr uint32_t kBoxValid = 1u << 16;
-
 struct GeomState {
   SplatRecord* rec;         // [P]
   uint32_t* tiles_touched;  // [P]
@@ -77,7 +63,6 @@ struct BinningState {
   uint64_t* keys;           // [R] sorted
   uint32_t* vals;           // [R] sorted == reference point_list
   SplatRecord* inst;        // [R] records in sorted order
-  InstAux* aux;             // [R] clipped boxes / thresholds / ids in sorted order
   uint2* blist;             // [8R] per-block candidate lists {index in the tile list, coverage mask}: block b of a
                             //      tile with range [r, r+n) owns entries 8r + b*n .. 8r + (b+1)*n (block_lists.cu)
   uint32_t* bhits;          // [8R] same indexing: word 32g + p of a block = which candidates of the block's group g
@@ -135,16 +120,9 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
 cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,
                              const float* background, float* out_color, float* out_depth, float* out_acc,
                              cudaStream_t s);
-cudaError_t launch_blend_fwd_mask(int width, int height, const ImageState& img, const BinningState& b,
-                                  const float* background, float* out_color, float* out_depth, float* out_acc,
-                                  cudaStream_t s);
 cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const BinningState& b,
                              const float* background, const float* dL_dpix, const float* dL_dacc, float* dL_dmean2D,
                              float* dL_dconic, float* dL_dopacity, float* dL_dcolor, cudaStream_t s);
-cudaError_t launch_blend_bwd_mask(int width, int height, const ImageState& img, const BinningState& b,
-                                  const float* background, const float* dL_dpix, const float* dL_dacc,
-                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
-                                  cudaStream_t s);
 cudaError_t launch_geom_bwd(const gsr_bwd_args& a, const GeomState& g, const int* radii, float focal_x, float focal_y,
                             cudaStream_t s);
 

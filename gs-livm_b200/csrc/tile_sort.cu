@@ -12,7 +12,7 @@
 //   tile_sort_kernel        one CTA per tile: LSD radix sort of the segment by depth bits in shared memory
 //                           (only over the bits that differ inside the segment), ties put in ascending-id
 //                           order, then the outputs in final order: point_list_keys (tile << 32 | depth),
-//                           point_list, the gathered 48-byte records and the 16-byte aux records.
+//                           point_list and the gathered 48-byte records.
 //
 // Why this is bit-exact. The reference sorts instances by (tile, depth bits) with a STABLE radix sort of a
 // list written in Gaussian-id order (rows of a Gaussian's rectangle are different tiles), so its result is
@@ -163,19 +163,6 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Same box as finalize_binning_kernel (binning.cu).
-__device__ __forceinline__ uint32_t clipped_box(float x, float y, float ex, float ey, float tx0, float ty0) {
-  const float lx = x - ex - tx0, hx = x + ex - tx0;
-  const float ly = y - ey - ty0, hy = y + ey - ty0;
-  const int x0 = (lx > 0.0f) ? (int)ceilf(fminf(lx, 16.0f)) : 0;
-  const int x1 = (hx < 15.0f) ? (int)floorf(fmaxf(hx, -1.0f)) : 15;
-  const int y0 = (ly > 0.0f) ? (int)ceilf(fminf(ly, 16.0f)) : 0;
-  const int y1 = (hy < 15.0f) ? (int)floorf(fmaxf(hy, -1.0f)) : 15;
-  if (x1 < x0 || y1 < y0) return 0u;
-  return kBoxValid | (uint32_t)x0 | ((uint32_t)x1 << 4) | ((uint32_t)y0 << 8) | ((uint32_t)y1 << 12);
-}
-
 struct TileSortArgs {
   const uint2* ranges;
   const uint32_t* order;
@@ -186,7 +173,6 @@ struct TileSortArgs {
   uint64_t* keys_out;
   uint32_t* vals_out;
   SplatRecord* inst;
-  InstAux* aux;
   int grid_x;
   uint32_t min_len, max_len;  // this launch handles lists with min_len < length <= max_len
 };
@@ -382,7 +368,6 @@ __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t ti
   }
 
   // outputs in final order
-  const float tx0 = (float)((tile % (uint32_t)a.grid_x) * kTile), ty0 = (float)((tile / (uint32_t)a.grid_x) * kTile);
   const uint64_t hi_key = (uint64_t)tile << 32;
   for (int i = tid; i < n; i += kThreads) {
     const size_t g = (size_t)range.x + i;
@@ -393,12 +378,6 @@ __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t ti
     const size_t g = (size_t)range.x + i;
     float4* dst = reinterpret_cast<float4*>(a.inst + g);
     dst[0] = q0, dst[1] = q1, dst[2] = q2;
-    InstAux x;
-    x.box = clipped_box(q0.x, q0.y, q0.z, q0.w, tx0, ty0);
-    x.pmin = -(logf(255.0f * q1.w) + 1.0e-4f);
-    x.id = id;
-    x.pad = 0;
-    a.aux[g] = x;
   };
   for (int i = tid; i < n; i += 2 * kThreads) {  // two independent record gathers in flight per thread
     const int i2 = i + kThreads;
@@ -446,7 +425,9 @@ cudaError_t launch_scatter_instances(int P, const GeomState& g, const int* radii
 
 cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, const BinningState& b, const GeomState& g,
                              int grid_x, cudaStream_t s) {
+  constexpr int kMidCap = 4096;  // a power of two: class boundaries coincide with tile_order's buckets
   constexpr size_t kSmemSmall = sort_smem(kSmallCap, kSmallThreads), kSmemLarge = sort_smem(kLargeCap, kLargeThreads);
+  constexpr size_t kSmemMid = sort_smem(kMidCap, kLargeThreads);
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -456,6 +437,9 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tile_sort_kernel<kLargeCap, kLargeThreads, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLarge);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tile_sort_kernel<kMidCap, kLargeThreads, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMid);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
@@ -469,39 +453,47 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
   TileSortArgs a;
   a.ranges = img.ranges, a.order = img.tile_order, a.summary = img.summary;
   a.seg_keys = reinterpret_cast<const uint32_t*>(b.keys_unsorted), a.seg_vals = b.vals_unsorted;
-  a.rec = g.rec, a.keys_out = b.keys, a.vals_out = b.vals, a.inst = b.inst, a.aux = b.aux, a.grid_x = grid_x;
-  // The few long lists (one 1024-thread CTA each, all of an SM's shared memory) and the many short ones are
-  // independent: the short-list kernel runs on a side stream so it fills the SMs the long lists leave free.
+  a.rec = g.rec, a.keys_out = b.keys, a.vals_out = b.vals, a.inst = b.inst, a.grid_x = grid_x;
+  // Three independent classes, three streams: lists of 4096+ instances (one 1024-thread CTA with all of an SM's
+  // shared memory each), lists of 2048..4095 (1024-thread CTAs, two per SM) and the many short ones (256-thread
+  // CTAs). The longest lists come first in tile_order (bucketed by floor(log2(length))): both persistent kernels
+  // walk its first summary[2] entries and skip the lists of the other class.
   struct Side {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
   };
   static thread_local Side side[64];
   Side* sd = nullptr;
   if (n_large != 0 && dev >= 0 && dev < 64) {  // n_large < 0: not known on the host (sync-free forward)
     sd = &side[dev];
-    if (!sd->stream) {
-      if (cudaStreamCreateWithFlags(&sd->stream, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&sd->join, cudaEventDisableTiming) != cudaSuccess) {
-        sd->stream = nullptr;
+    if (!sd->stream[0]) {
+      bool ok = cudaEventCreateWithFlags(&sd->fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&sd->stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sd->join[i], cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) {
+        sd->stream[0] = nullptr;
         sd = nullptr;
         (void)cudaGetLastError();
       }
     }
   }
-  cudaStream_t small_stream = s;
+  cudaStream_t mid_stream = s, small_stream = s;
   if (sd) {
     cudaError_t e = cudaEventRecord(sd->fork, s);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(sd->stream, sd->fork, 0);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(sd->stream[i], sd->fork, 0);
     if (e != cudaSuccess) return e;
-    small_stream = sd->stream;
+    mid_stream = sd->stream[0], small_stream = sd->stream[1];
   }
-  if (n_large != 0) {  // the longest lists come first in tile_order; the kernel reads their number on the device
-    a.min_len = (uint32_t)kSmallMax, a.max_len = (uint32_t)kLargeCap;
-    const int grid = n_large > 0 ? (n_large < sms ? n_large : sms) : (tiles < sms ? tiles : sms);
-    tile_sort_kernel<kLargeCap, kLargeThreads, true><<<grid, kLargeThreads, kSmemLarge, s>>>(a);
+  if (n_large != 0) {
+    const int cap = n_large > 0 ? n_large : tiles;
+    a.min_len = (uint32_t)kMidCap - 1u, a.max_len = (uint32_t)kLargeCap;
+    tile_sort_kernel<kLargeCap, kLargeThreads, true><<<cap < sms ? cap : sms, kLargeThreads, kSmemLarge, s>>>(a);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    a.min_len = (uint32_t)kSmallMax, a.max_len = (uint32_t)kMidCap - 1u;
+    tile_sort_kernel<kMidCap, kLargeThreads, true><<<cap < 2 * sms ? cap : 2 * sms, kLargeThreads, kSmemMid, mid_stream>>>(a);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
   a.min_len = 0, a.max_len = (uint32_t)kSmallMax;
@@ -509,8 +501,10 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (sd) {
-    e = cudaEventRecord(sd->join, sd->stream);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, sd->join, 0);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaEventRecord(sd->join[i], sd->stream[i]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s, sd->join[i], 0);
+    }
   }
   return e;
 }

@@ -51,7 +51,7 @@ def binning_state(binningBuffer: torch.Tensor, R: int) -> Dict[str, torch.Tensor
         point_list_keys=_typed(binningBuffer, v.point_list_keys, i64, 1)[:, 0],
         point_list=_typed(binningBuffer, v.point_list, i32, 1)[:, 0],
         instance_records=_typed(binningBuffer, v.instance_records, torch.float32, 12),
-        instance_aux=_typed(binningBuffer, v.instance_aux, i32, 4),
+        block_candidates=_typed(binningBuffer, v.block_candidates, i32, 2),
     )
 
 

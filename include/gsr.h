@@ -154,7 +154,7 @@ typedef struct gsr_binning_view {
   gsr_array_view point_list_keys;          /* uint64, sorted */
   gsr_array_view point_list;               /* uint32, sorted */
   gsr_array_view instance_records;         /* 48-byte packed per-instance records in sorted order (ours) */
-  gsr_array_view instance_aux;             /* 16 bytes per sorted instance: clipped box, power floor, id (ours) */
+  gsr_array_view block_candidates;         /* 8 x R uint2 {index in tile list, 8x4 coverage mask}: per-block lists (ours) */
 } gsr_binning_view;
 
 typedef struct gsr_image_view {
