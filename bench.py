@@ -43,7 +43,7 @@ P_GAUSS = 1_000_000
 SH_DEGREE = 3
 SEED = 20241017 + 2
 WINDOW = 8
-MY_KERNELS_PER_STEP = 9  # preprocess, tile_scan, scatter_instances, tile_sort (long + short lists), block_lists, blend_fwd, blend_bwd, geom_bwd
+MY_KERNELS_PER_STEP = 10  # preprocess, tile_scan, scatter_instances, tile_sort (4096+, 2048.., short lists), block_lists, blend_fwd, blend_bwd, geom_bwd
 LIB_KERNELS_PER_STEP = ("none on the per-tile binning path (cub scan + radix sort only when a tile list exceeds 12032 "
                         "instances); cudaMemsetAsync: tile counters + the 4 accumulated gradient arrays (44 B/Gaussian)")
 
@@ -141,21 +141,26 @@ def build_workload(dev):
     return sc_cpu, sc, cams_cpu, cams, dC, dS
 
 
-def algorithmic_bytes(P, P_v, R, px, tiles, M=16):
+def algorithmic_bytes(P, P_v, R, px, tiles, S_c, M=16):
     """SURVEY.md section 8d per-unit figures, restated for OUR data layout where it moves fewer bytes
-    (DESIGN.md 'algorithmic bytes'): 48-byte records instead of separate arrays, no cov3D round trip."""
+    (DESIGN.md 'algorithmic bytes'): 48-byte records instead of separate arrays, no cov3D round trip.
+    S_c = entries of the per-block candidate lists (block_lists.cu), the unit of work of the sparse blend."""
     P_c = P - P_v
     return {
         "preprocess": (12 + 12 + 16 + 4 + 12 * M + 48 + 1 + 4 + 4) * P_v + (12 + 12 + 8) * P_c,
         # per-tile binning (tile_sort.cu): tile_scan over the tile counters; scatter = radii + record head per
         # visible Gaussian in, (depth, id) per instance out; tile_sort = (depth, id) in, key + id + gathered
-        # 48-byte record + 16-byte aux out, 48-byte record gather in. finalize is fused into tile_sort.
+        # 48-byte record out, 48-byte record gather in. "finalize" is block_lists: the 16-byte head of every sorted
+        # record in, one 8-byte entry per (instance, 8x4 block) candidate out.
         "scan": (4 + 8 + 4 + 4 + 4) * tiles,
         "duplicate": 4 * P + 20 * P_v + 8 * R,
-        "sort": (8 + 8 + 4 + 48 + 48 + 16) * R,
-        "finalize": 0,
-        "blend_fwd": 48 * R + 28 * px,
-        "blend_bwd": (48 + 4) * R + 24 * px + 36 * R,
+        "sort": (8 + 8 + 4 + 48 + 48) * R,
+        "finalize": 16 * R + 8 * S_c,
+        # sparse blend: per candidate its list entry and its record, one 4-byte hit word per pixel and group of 32
+        # candidates; the backward reads the hit words and, per candidate blended somewhere in its block (bounded by
+        # S_c here), entry + record + id, and commits 9 floats
+        "blend_fwd": (8 + 48 + 4) * S_c + 32 * px,
+        "blend_bwd": 4 * S_c + (8 + 48 + 4 + 36) * S_c + 28 * px,
         "geom_bwd": (12 + 4 + 12 * M + 1 + 12 + 16 + 12 + 16 + 12 + 12 + 24 + 12 * M + 12 + 16) * P_v + 4 * P_c,
     }
 
@@ -271,6 +276,8 @@ def run_ours(args, rank, world, dev):
     stage_ms = {n: stage_acc[n] / n_stage for n in _lib.STAGES}
     R = ctx.num_rendered
     P_v = int((ctx.radii > 0).sum())
+    from gs_livm_b200 import debug
+    S_c = int(debug.image_state(ctx.image.buf, W, H)["block_count"].sum())  # candidate-list entries of the last frame
 
     # ---- end to end through the public operator: H2D camera + target, autograd, D2H loss ----
     leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
@@ -365,7 +372,7 @@ def run_ours(args, rank, world, dev):
     # ---- roofline + CPU baseline (rank 0 only) ----
     hbm_peak, peak_src, sm_max_mhz = measured_peaks()
     px, tiles = H * W, ((W + 15) // 16) * ((H + 15) // 16)
-    alg = algorithmic_bytes(P_GAUSS, P_v, R, px, tiles)
+    alg = algorithmic_bytes(P_GAUSS, P_v, R, px, tiles, S_c)
     cpu_base, c_fwd, c_bwd = None, None, None
     if world == 1 and not args.no_cpu_baseline:
         cpu_base, c_fwd, c_bwd, _ = cpu_baseline(sc_cpu, cams_cpu[0], dC, dS)
@@ -376,7 +383,7 @@ def run_ours(args, rank, world, dev):
         t = stage_ms[n] * 1e-3
         ach = alg[n] / t / 1e9 if t > 0 else 0.0
         if t <= 0:
-            continue  # the stage does not exist on this path (finalize is fused into the per-tile sort)
+            continue  # the stage did not run
         stages[n] = {"us": round(stage_ms[n] * 1e3, 1), "alg_bytes": int(alg[n]), "achieved_gbs": round(ach, 1),
                      "frac_hbm": round(ach / hbm_peak, 4)}
     if c_fwd is not None:
@@ -403,7 +410,7 @@ def run_ours(args, rank, world, dev):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480 forward+backward "
                                "(BASELINE.json configs[1]); one keyframe view per GPU per step, 8-pose window",
-                   "P": P_GAUSS, "P_visible": P_v, "R": R, "sh_degree": SH_DEGREE, "width": W, "height": H,
+                   "P": P_GAUSS, "P_visible": P_v, "R": R, "block_candidates": S_c, "sh_degree": SH_DEGREE, "width": W, "height": H,
                    "parallelism": "view-sharded window, replicated Gaussians" + (
                        ", all-reduce of 236 B/Gaussian per step: %s%s" % (
                            {"multimem": "own NVSwitch-multicast kernel (multimem.ld_reduce/st)",

@@ -67,7 +67,8 @@ class BinningView(C.Structure):
 
 
 class ImageView(C.Structure):
-    _fields_ = [(n, ArrayView) for n in ("accum_alpha", "n_contrib", "ranges", "tile_last", "tile_order")]
+    _fields_ = [(n, ArrayView) for n in ("accum_alpha", "n_contrib", "ranges", "tile_last", "tile_order", "block_count",
+                                         "last_group")]
 
 
 class AsyncStatus(C.Structure):

@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_kernel(const BwdArgs a)
   } else {
     const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) >= a.heavy) return;
+    // FINE CTAs exist for the first fine_tiles entries of the order only: a heavy tile beyond them is done here
+    if ((int)(r.y - r.x) >= a.heavy && b - 4 * a.fine_tiles < a.fine_tiles) return;
     blend_bwd_warp<1>(a, ring, tile, warp, lane);
   }
 }

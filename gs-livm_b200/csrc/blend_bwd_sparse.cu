@@ -298,14 +298,15 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
     const int c = b - 8 * a.fine_tiles;
     const int tile = (int)a.tile_order[c >> 1];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) >= a.heavy) return;
+    // FINE CTAs exist for the first fine_tiles entries of the order only: a heavy tile beyond them is done here
+    if ((int)(r.y - r.x) >= a.heavy && (c >> 1) < a.fine_tiles) return;
     blend_bwd_block<1, ILP>(a, buf, tile, (c & 1) * 4 + warp, 0, lane);
   }
 }
 
 }  // namespace
 
-int blend_heavy_threshold();  // blend_fwd_sparse.cu: one threshold, the two kernels must agree on the shape of a tile
+int blend_heavy_threshold();  // blend_fwd_sparse.cu
 
 cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
                                     const float* background, const float* dL_dpix, const float* dL_dacc,

@@ -259,21 +259,19 @@ __global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const Fwd
   } else {
     const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
     const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) >= a.heavy) return;
+    // FINE CTAs exist for the first fine_tiles entries of the order only: a heavy tile beyond them is done here
+    if ((int)(r.y - r.x) >= a.heavy && b - 4 * a.fine_tiles < a.fine_tiles) return;
     blend_block<1, ILP>(a, bufs[warp], tile, warp, 0, lane);
   }
 }
 
 }  // namespace
 
-// One threshold for the forward and the backward: both must give a tile the same warp shape (the hit masks the
-// forward leaves are per warp shape only in who writes them, but a tile's pixels must all have been written).
+// List length from which a tile's warps take the FINE shape. The hit masks and last_group the forward leaves are
+// laid out per pixel, independent of the shape, so the two kernels need not agree; one knob is simply enough.
 int blend_heavy_threshold() {
-  static const int heavy = [] {
-    const char* e = getenv("GSR_BLEND_HEAVY");  // tuning knob: list length from which a tile uses the FINE warp shape
-    return e ? atoi(e) : kHeavy;
-  }();
-  return heavy;
+  const char* e = getenv("GSR_BLEND_HEAVY");  // tuning / test knob, read per call
+  return e ? atoi(e) : kHeavy;
 }
 
 cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img, const BinningState& b,

@@ -214,9 +214,10 @@ static BlendImpl blend_impl(const char* var) {
   if (e && !strcmp(e, "warp")) return kBlendWarp;
   return kBlendSparse;
 }
-static BlendImpl fwd_impl() { static const BlendImpl v = blend_impl("GSR_FWD_IMPL"); return v; }
+// read per call (a getenv costs ~100 ns), so one process can compare the implementations (tests)
+static BlendImpl fwd_impl() { return blend_impl("GSR_FWD_IMPL"); }
 static BlendImpl bwd_impl() {
-  static const BlendImpl v = blend_impl("GSR_BWD_IMPL");
+  const BlendImpl v = blend_impl("GSR_BWD_IMPL");
   return (v == kBlendSparse && fwd_impl() != kBlendSparse) ? kBlendWarp : v;
 }
 
@@ -449,6 +450,8 @@ int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* ou
   out->ranges = view_of(s.ranges, 8, tiles);
   out->tile_last = view_of(s.tile_last, 4, tiles);
   out->tile_order = view_of(s.tile_order, 4, tiles);
+  out->block_count = view_of(s.block_count, 4, tiles * 8);
+  out->last_group = view_of(s.last_group, 4, N);
   return GSR_OK;
 }
 

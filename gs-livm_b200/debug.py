@@ -64,4 +64,6 @@ def image_state(imgBuffer: torch.Tensor, width: int, height: int) -> Dict[str, t
         ranges=_typed(imgBuffer, v.ranges, torch.int32, 2),
         tile_last=_typed(imgBuffer, v.tile_last, torch.int32, 1)[:, 0],
         tile_order=_typed(imgBuffer, v.tile_order, torch.int32, 1)[:, 0],
+        block_count=_typed(imgBuffer, v.block_count, torch.int32, 1)[:, 0],
+        last_group=_typed(imgBuffer, v.last_group, torch.int32, 1)[:, 0],
     )

@@ -146,8 +146,9 @@ class CapturedStep:
     `step_fn()` is the step as the caller would write it eagerly — host-to-device copies from PINNED staging
     tensors, the render, the loss, `loss.backward()`, the device-to-host copy of the loss — with three rules:
     no host synchronisation inside, every tensor it reads from the outside keeps its address (write new camera /
-    image data INTO the staging tensors before `replay()`), and the arena already knows its capacity (one eager
-    render did `arena.learn`). It runs `warmup` times eagerly on a side stream, is captured once, and
+    image data INTO the staging tensors before `replay()`), the arena already knows its capacity (one eager
+    render did `arena.learn`), and nothing that keeps an autograd graph alive (the loss, an output that
+    requires grad) survives a call -- keep `.detach()`ed views instead. It runs `warmup` times eagerly on a side stream, is captured once, and
     `replay()` then launches the whole step — ~20 kernels and copies — with one host call. Tensors created
     inside `step_fn` (outputs, `.grad`s, the loss) live in the graph's memory pool and are overwritten by every
     replay; `result` is whatever `step_fn` returned at capture time.

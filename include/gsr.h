@@ -44,7 +44,7 @@ extern "C" {
 #define GSR_API
 #endif
 
-#define GSR_ABI_VERSION 2
+#define GSR_ABI_VERSION 3
 #define GSR_NUM_CHANNELS 3 /* NUM_CHANNELS, include/gs/cuda_rasterizer/config.h:15 */
 #define GSR_BLOCK_X 16     /* BLOCK_X, config.h:16 */
 #define GSR_BLOCK_Y 16     /* BLOCK_Y, config.h:17 */
@@ -163,6 +163,8 @@ typedef struct gsr_image_view {
   gsr_array_view ranges;      /* uint2 per tile */
   gsr_array_view tile_last;   /* uint32 per tile: max n_contrib over the tile's pixels (ours) */
   gsr_array_view tile_order;  /* uint32 per tile: launch order, longest lists first (ours) */
+  gsr_array_view block_count; /* uint32 per 8x4 pixel block (8 per tile): candidates in the block's list (ours) */
+  gsr_array_view last_group;  /* uint32 per pixel: 1 + group of 32 candidates of the pixel's last contributor (ours) */
 } gsr_image_view;
 
 GSR_API int gsr_abi_version(void);
@@ -228,7 +230,7 @@ enum gsr_stage {
   GSR_STAGE_SCAN = 1,       /* prefix sum                <- cub InclusiveSum          (rasterizer_impl.cu:270) */
   GSR_STAGE_DUPLICATE = 2,  /* duplicate_with_keys       <- duplicateWithKeys         (rasterizer_impl.cu:64)  */
   GSR_STAGE_SORT = 3,       /* (tile|depth) radix sort   <- cub SortPairs             (rasterizer_impl.cu:298) */
-  GSR_STAGE_FINALIZE = 4,   /* tile ranges + record gather <- identifyTileRanges      (rasterizer_impl.cu:106) */
+  GSR_STAGE_FINALIZE = 4,   /* per-block candidate lists (block_lists.cu); device-wide path: + identifyTileRanges */
   GSR_STAGE_BLEND_FWD = 5,  /* blend_fwd                 <- renderCUDA fwd            (forward.cu:291-407)   */
   GSR_STAGE_BLEND_BWD = 6,  /* blend_bwd                 <- renderCUDA bwd            (backward.cu:438-603)  */
   GSR_STAGE_GEOM_BWD = 7,   /* fused per-Gaussian bwd    <- computeCov2DCUDA + preprocessCUDA bwd (backward.cu:140-435) */

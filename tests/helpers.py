@@ -82,9 +82,14 @@ def run_oracle_cpu(case: Case, backward: bool = True, nthreads: int = 4) -> Dict
 
 # ------------------------------------------------------------------------------------------------ ours
 SORT_PATHS = ("tile", "device")
+# blend implementations of the library: the pair-sparse kernels with their default warp shapes, the same with the
+# FINE shape (four lanes per pixel) forced on every tile, and the round-1 lock-step kernels
+BLENDS = ("sparse", "sparse-fine", "warp")
+_BLEND_ENV = {"sparse": {}, "sparse-fine": {"GSR_BLEND_HEAVY": "1"},
+              "warp": {"GSR_FWD_IMPL": "warp", "GSR_BWD_IMPL": "warp"}}
 
 
-def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile") -> Dict[str, np.ndarray]:
+def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile", blend: str = "sparse") -> Dict[str, np.ndarray]:
     """Through the tensor-level mirror of the reference operator -> C ABI -> CUDA kernels.
 
     sort_path "tile": per-tile binning (tile_sort.cu, the default; falls back by itself for very long lists);
@@ -96,6 +101,9 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile") ->
         os.environ["GSR_SORT"] = "device"
     else:
         os.environ.pop("GSR_SORT", None)
+    for k in ("GSR_BLEND_HEAVY", "GSR_FWD_IMPL", "GSR_BWD_IMPL"):
+        os.environ.pop(k, None)
+    os.environ.update(_BLEND_ENV[blend])
     d = lambda t: torch.empty(0, device=dev) if t is None else t.to(dev)  # noqa: E731
     shs = None if case.use_colors else case.shs
     bg, m3, sc, rot, op = d(case.background), d(case.means3D), d(case.scales), d(case.rotations), d(case.opacities)
@@ -118,6 +126,8 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile") ->
             d(case.dL_dcolor), d(case.dL_dacc), sh, case.sh_degree, cam, gb, R, bb, ib, False)
         out.update(dict(zip(GRAD_NAMES, grads)))
     torch.cuda.synchronize()
+    for k in _BLEND_ENV[blend]:
+        os.environ.pop(k, None)
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 

@@ -76,6 +76,81 @@ def test_render_arena_gives_the_same_gradients_without_waiting(built_library, cu
             assert_grad(name, leaves[leaf].grad.cpu().numpy().reshape(raw[name].shape), raw[name])
 
 
+def test_captured_step_replays_the_operator_step(built_library, cuda_device):
+    """rasterizer.CapturedStep: the step (camera H2D from a pinned staging tensor, render through the arena, loss,
+    backward, loss D2H) captured as one CUDA graph; replays with a NEW camera written into the staging tensor give
+    the images and gradients of eager renders with that camera."""
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import rasterizer, scene
+    case = helpers.scene_case(6000, 503, 3, intr=SMALL, heavy=True)
+    dev = cuda_device
+    leaves = {k: _leaf(getattr(case, k), dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    wC, wS = case.dL_dcolor.to(dev), case.dL_dacc.to(dev)
+    bg = case.background.to(dev)
+    cams = [torch.cat([case.viewmatrix.reshape(-1), case.projmatrix.reshape(-1), case.camera_center.reshape(-1)])]
+    shifted = case.viewmatrix.clone()
+    shifted[3, 0] += 0.05  # the reference's matrices are stored transposed: row 3 is the translation
+    cams.append(torch.cat([shifted.reshape(-1), (shifted @ (torch.linalg.inv(case.viewmatrix) @ case.projmatrix)).reshape(-1),
+                           case.camera_center.reshape(-1)]))
+    stage = torch.zeros(35).pin_memory()
+    cam_dev = torch.zeros(35, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+    arena = rasterizer.RenderArena(dev)
+    out = {}
+
+    def settings():
+        return rasterizer.GaussianRasterizationSettings(case.height, case.width, case.tanfovx, case.tanfovy, bg, 1.0,
+                                                        cam_dev[:16].view(4, 4), cam_dev[16:32].view(4, 4),
+                                                        case.sh_degree, cam_dev[32:35], False)
+
+    def step():
+        cam_dev.copy_(stage, non_blocking=True)
+        for t in list(leaves.values()) + [means2D]:
+            t.grad = None
+        color, radii, depth, acc = rasterizer.GaussianRasterizer(settings(), arena=arena)(
+            leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+            rotations=leaves["rotations"])
+        loss = (color * wC).sum() + (acc * wS).sum()
+        loss.backward()
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        out["color"] = color.detach()  # (nothing that keeps the autograd graph alive may outlive the step)
+
+    stage.copy_(cams[0])
+    with torch.no_grad():  # eager: the arena learns its capacity
+        cam_dev.copy_(stage)
+        rasterizer.GaussianRasterizer(settings(), arena=arena)(
+            leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+            rotations=leaves["rotations"])
+    torch.cuda.synchronize()
+    assert arena.check()
+    captured = rasterizer.CapturedStep(step, arena)
+    for which in (1, 0, 1):
+        stage.copy_(cams[which])
+        captured.replay()
+        torch.cuda.synchronize()
+        assert arena.check()
+        got_color = out["color"].detach().cpu().numpy().copy()
+        got_loss = float(loss_host[0])
+        got = {k: v.grad.detach().cpu().numpy().copy() for k, v in leaves.items()}
+        # the same step, eagerly, without an arena
+        cam_dev.copy_(stage)
+        fresh = {k: v.detach().clone().requires_grad_(True) for k, v in leaves.items()}
+        m2 = torch.zeros_like(fresh["means3D"], requires_grad=True)
+        color, radii, depth, acc = rasterizer.GaussianRasterizer(settings())(
+            fresh["means3D"], m2, fresh["opacities"], shs=fresh["shs"], scales=fresh["scales"],
+            rotations=fresh["rotations"])
+        loss = (color * wC).sum() + (acc * wS).sum()
+        loss.backward()
+        np.testing.assert_array_equal(helpers.bits(got_color), helpers.bits(color.detach().cpu().numpy()))
+        ref_loss = float(loss.detach())
+        assert abs(got_loss - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+        for k in leaves:
+            assert_grad(k, got[k], fresh[k].grad.cpu().numpy())
+    # the two cameras really differ
+    assert not np.array_equal(cams[0].numpy(), cams[1].numpy())
+
+
 def test_mark_visible_matches_oracle(built_library, cuda_device):
     import gs_livm_b200  # noqa: F401
     from gs_livm_b200 import rasterizer

@@ -52,11 +52,12 @@ def check_backward(ours, ref, case):
 
 
 # ------------------------------------------------------------------------------------------ (1) golden vectors
+@pytest.mark.parametrize("blend", helpers.BLENDS)
 @pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
 @pytest.mark.parametrize("name", helpers.GOLDEN_CASES)
-def test_golden_vectors(name, sort_path, built_library, cuda_device):
+def test_golden_vectors(name, sort_path, blend, built_library, cuda_device):
     case, ref = helpers.load_golden(name)
-    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path, blend=blend)
     check_forward_exact(ours, ref, case, vs_cuda_reference=True)
     check_backward(ours, ref, case)
 
@@ -71,11 +72,12 @@ def test_golden_vectors(name, sort_path, built_library, cuda_device):
     (1, 106, 3, SMALL, False, False),                                            # single Gaussian
     (37, 107, 3, dict(width=17, height=9, fx=10.0, fy=10.0), True, False),       # image smaller than two tiles
 ])
+@pytest.mark.parametrize("blend", helpers.BLENDS)
 @pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
-def test_against_cpu_oracle(P, seed, deg, intr, heavy, close, sort_path, built_library, cuda_device):
+def test_against_cpu_oracle(P, seed, deg, intr, heavy, close, sort_path, blend, built_library, cuda_device):
     case = helpers.scene_case(P, seed, deg, intr=intr, heavy=heavy, close_up=close)
     ref = helpers.run_oracle_cpu(case)
-    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path, blend=blend)
     check_forward_exact(ours, ref, case, vs_cuda_reference=False)
     if not (ref["fragile"] != 0).any():
         check_backward(ours, ref, case)
@@ -184,11 +186,12 @@ needs_ref = pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref/
     (100_000, 402, 0, HALF_NTU, False, False),
     (200_000, 403, 3, None, True, True),
 ])
+@pytest.mark.parametrize("blend", helpers.BLENDS)
 @pytest.mark.parametrize("sort_path", helpers.SORT_PATHS)
-def test_against_reference_cuda(P, seed, deg, intr, heavy, close, sort_path, built_library, cuda_device):
+def test_against_reference_cuda(P, seed, deg, intr, heavy, close, sort_path, blend, built_library, cuda_device):
     case = helpers.scene_case(P, seed, deg, intr=intr, heavy=heavy, close_up=close)
     ref = helpers.run_ref_cuda(case, cuda_device)
-    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path)
+    ours = helpers.run_ours(case, cuda_device, sort_path=sort_path, blend=blend)
     check_forward_exact(ours, ref, case, vs_cuda_reference=True)
     check_backward(ours, ref, case)
 
