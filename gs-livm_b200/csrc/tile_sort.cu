@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
                                                                int grid_y, const uint32_t* __restrict__ summary) {
   if (summary[3]) return;  // presized binning buffer too small for this frame: nothing may be written
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
   const int radius = idx < P ? radii[idx] : 0;
   int rminx = 0, rminy = 0, rw = 1;
   uint32_t ntiles = 0, depth_bits = 0;
@@ -132,34 +131,45 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
     rw = rmaxx - rminx;
     ntiles = (uint32_t)rw * (uint32_t)(rmaxy - rminy);
   }
-  // lanes that append to the same tile share one atomicAdd on its cursor (see preprocess.cu); two tiles per
-  // iteration so that two cursor round trips are in flight
   auto tile_of = [&](uint32_t k) -> uint32_t {
-    if (k >= ntiles) return 0xffffffffu;
     const int ry = (int)k / rw;
     return (uint32_t)((rminy + ry) * grid_x + rminx + ((int)k - ry * rw));
   };
-  const uint32_t most = __reduce_max_sync(kFull, ntiles);
-  for (uint32_t k = 0; k < most; k += 2) {
-    const uint32_t t0 = tile_of(k), t1 = tile_of(k + 1);
-    const uint32_t p0 = __match_any_sync(kFull, t0), p1 = __match_any_sync(kFull, t1);
-    const int l0 = __ffs(p0) - 1, l1 = __ffs(p1) - 1;
-    uint32_t b0 = 0, b1 = 0;
-    if (t0 != 0xffffffffu && lane == l0) b0 = atomicAdd(&cursor[t0], (uint32_t)__popc(p0));
-    if (t1 != 0xffffffffu && lane == l1) b1 = atomicAdd(&cursor[t1], (uint32_t)__popc(p1));
-    b0 = __shfl_sync(kFull, b0, l0);
-    b1 = __shfl_sync(kFull, b1, l1);
-    const uint32_t below = (1u << lane) - 1u;
-    if (t0 != 0xffffffffu) {
-      const uint32_t pos = b0 + __popc(p0 & below);
-      seg_keys[pos] = depth_bits;
-      seg_vals[pos] = (uint32_t)idx;
+  // The 256 Gaussians of a CTA are neighbours in the map and fall into a few dozen tiles, and L2 serialises
+  // returning atomics to one address (~15 ns each: a 10 000-instance list would cost its tile's cursor ~40 us even
+  // with warp-merged requests). So the CTA first counts its appends per tile in a shared-memory hash table, one
+  // thread per occupied slot then reserves the CTA's share of the tile's segment with ONE global atomic, and the
+  // appends take their positions from the slot's shared-memory cursor. An append whose tile found no slot within
+  // kProbes probes (never seen on real frames) goes to the global cursor directly; the table only grows, so the
+  // same probe sequence fails again in the second walk and nothing is counted twice.
+  constexpr uint32_t kSlots = 1024, kProbes = 16, kEmpty = 0xffffffffu;
+  __shared__ uint32_t h_key[kSlots], h_cnt[kSlots];
+  for (uint32_t i = threadIdx.x; i < kSlots; i += blockDim.x) h_key[i] = kEmpty, h_cnt[i] = 0;
+  __syncthreads();
+  auto find = [&](uint32_t t, bool insert) -> int {
+    uint32_t slot = (t * 2654435761u) >> 22;  // top 10 bits
+    for (uint32_t pr = 0; pr < kProbes; ++pr, slot = (slot + 1) & (kSlots - 1)) {
+      const uint32_t seen = insert ? atomicCAS(&h_key[slot], kEmpty, t) : h_key[slot];
+      if (seen == t || (insert && seen == kEmpty)) return (int)slot;
     }
-    if (t1 != 0xffffffffu) {
-      const uint32_t pos = b1 + __popc(p1 & below);
-      seg_keys[pos] = depth_bits;
-      seg_vals[pos] = (uint32_t)idx;
-    }
+    return -1;
+  };
+  for (uint32_t k = 0; k < ntiles; ++k) {
+    const int slot = find(tile_of(k), true);
+    if (slot >= 0) atomicAdd(&h_cnt[slot], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kSlots; i += blockDim.x) {
+    const uint32_t c = h_cnt[i];
+    if (c) h_cnt[i] = atomicAdd(&cursor[h_key[i]], c);  // from here on: the CTA's cursor inside the tile's segment
+  }
+  __syncthreads();
+  for (uint32_t k = 0; k < ntiles; ++k) {
+    const uint32_t t = tile_of(k);
+    const int slot = find(t, false);
+    const uint32_t pos = slot >= 0 ? atomicAdd(&h_cnt[slot], 1u) : atomicAdd(&cursor[t], 1u);
+    seg_keys[pos] = depth_bits;
+    seg_vals[pos] = (uint32_t)idx;
   }
 }
 
