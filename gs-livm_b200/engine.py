@@ -37,6 +37,21 @@ class _Arena:
         return self.buf.data_ptr()
 
 
+class CapturedFrame:
+    """One captured forward+backward of a RasterContext (RasterContext.capture_step)."""
+
+    def __init__(self, ctx, graph, slots, fwd_args, keep):
+        self.ctx, self.graph, self._slots, self._fwd_args, self._keep = ctx, graph, slots, fwd_args, keep
+
+    def replay(self) -> None:
+        ctx = self.ctx
+        if len(ctx._unchecked) + len(self._slots) >= ctx._status.shape[0] - 1:
+            ctx.check()  # status ring about to wrap (synchronises)
+        self.graph.replay()
+        ctx._unchecked.extend(s for s in self._slots if s not in ctx._unchecked)
+        ctx._fwd_args, ctx.num_rendered = self._fwd_args, ctx._capacity
+
+
 class RasterContext:
     """One (Gaussian set, image size) rasterization context on one device."""
 
@@ -158,6 +173,27 @@ class RasterContext:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.gsr_backward(C.byref(a), stream), "gsr_backward")
         return g
+
+    def capture_step(self, scene: Dict[str, torch.Tensor], cam: Camera, dL_dcolor: torch.Tensor,
+                     dL_dacc: torch.Tensor) -> "CapturedFrame":
+        """forward(scene, cam) + backward(dL_dcolor, dL_dacc) recorded once as a CUDA graph (ours; the reference
+        launches every kernel of every iteration from the host). All tensors are used by address: new parameter
+        values, a new camera or new upstream gradients are written INTO them before `replay()`. Needs the sync-free
+        path with a known capacity, i.e. one synchronous frame before; `check()` works as after eager frames."""
+        if not (self.sync_free and self._capacity > 0):
+            raise RuntimeError("capture_step: render one frame eagerly first (the binning arena must be sized)")
+        self.forward(scene, cam)  # eager once: one-time kernel attributes, arena growth
+        self.backward(dL_dcolor, dL_dacc)
+        if not self.check():
+            raise RuntimeError("capture_step: the frame does not fit the presized binning arena")
+        before = len(self._unchecked)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.forward(scene, cam)
+            self.backward(dL_dcolor, dL_dacc)
+        slots = self._unchecked[before:]
+        del self._unchecked[before:]
+        return CapturedFrame(self, graph, slots, self._fwd_args, (scene, cam, dL_dcolor, dL_dacc))
 
     def param_grads(self) -> torch.Tensor:
         """Flat view of the gradients of the optimised parameters (what a window all-reduces)."""
