@@ -91,16 +91,20 @@ __device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, flo
   bx[15] = kC3[6] * 3.f * (xx - yy), by[15] = kC3[6] * -6.f * xy;
 }
 
+// Gaussians per CTA. The kernel alternates between a memory phase (SH rows in, dL_dsh rows out) and ~1000
+// instructions of covariance / SH math; with 121 registers only 16 warps fit an SM, and eight 64-thread CTAs
+// interleave those phases better than two 256-thread ones (97 -> 91 us).
+constexpr int kBlock = 64;
 constexpr int kShRow = 13;  // float4 per staged SH row: 12 used + 1 pad -> conflict-free lane-strided LDS/STS.128
 
 // kVec16: M == 16 and shs / dL_dsh 16-byte aligned. SH rows of the block's visible Gaussians are staged into
 // shared memory with coalesced 16-byte cp.async transfers (issued first, so they overlap the covariance
 // math), and the dL_dsh rows leave the same way: written row-wise into shared memory, stored coalesced.
 template <bool kVec16>
-__global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
+__global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   __shared__ float s_view[16], s_proj[16], s_cam[3];
-  __shared__ uint8_t s_active[256];
-  extern __shared__ __align__(16) float4 s_sh[];  // [256][kShRow] when kVec16
+  __shared__ uint8_t s_active[kBlock];
+  extern __shared__ __align__(16) float4 s_sh[];  // [kBlock][kShRow] when kVec16
   const int tid = threadIdx.x;
   if (tid < 16) {
     s_view[tid] = __ldg(a.viewmatrix + tid);
@@ -109,15 +113,15 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   } else if (tid < 35) {
     s_cam[tid - 32] = __ldg(a.cam_pos + tid - 32);
   }
-  const int base = blockIdx.x * 256;
-  const int n = min(256, a.P - base);
+  const int base = blockIdx.x * kBlock;
+  const int n = min(kBlock, a.P - base);
   const int idx = base + tid;
   const bool active = tid < n && a.radii[idx] > 0;
   s_active[tid] = active;
   __syncthreads();
   if (kVec16) {
     const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += 256) {
+    for (int q = tid; q < n * 12; q += kBlock) {
       const int row = q / 12;
       if (s_active[row]) {
         const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(const GeomBwdArgs a) {
   if (kVec16) {  // coalesced store of the visible Gaussians' dL_dsh rows (culled rows stay at the caller's zeros)
     __syncthreads();
     float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += 256) {
+    for (int q = tid; q < n * 12; q += kBlock) {
       const int row = q / 12;
       if (s_active[row]) d4[q] = s_sh[row * kShRow + (q - row * 12)];
       else if (a.assign_all) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -387,9 +391,9 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
     return cudaErrorMisalignedAddress;
   a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && al16(f.dL_dsh);
   a.assign_all = (f.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) ? 1 : 0;
-  const int blocks = (f.P + 255) / 256;
+  const int blocks = (f.P + kBlock - 1) / kBlock;
   if (a.vec_sh) {
-    constexpr int kSmem = 256 * kShRow * (int)sizeof(float4);  // 53 248 B: needs the opt-in above 48 KB
+    constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -398,9 +402,9 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
       if (e != cudaSuccess) return e;
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    geom_bwd_kernel<true><<<blocks, 256, kSmem, s>>>(a);
+    geom_bwd_kernel<true><<<blocks, kBlock, kSmem, s>>>(a);
   } else {
-    geom_bwd_kernel<false><<<blocks, 256, 0, s>>>(a);
+    geom_bwd_kernel<false><<<blocks, kBlock, 0, s>>>(a);
   }
   return cudaGetLastError();
 }

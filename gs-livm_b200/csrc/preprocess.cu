@@ -98,22 +98,23 @@ __device__ __forceinline__ void eval_sh(int deg, float3 dir, Load sh, float out[
   }
 }
 
+constexpr int kBlock = 64;  // Gaussians per CTA: many small CTAs per SM interleave staging, math and SH phases better than three big ones
 constexpr int kShRow = 13;  // float4 per staged SH row: 12 used + 1 pad, so lane-strided LDS.128 are conflict-free
 
 // kVec16: M == 16 and shs 16-byte aligned. The 192-byte SH rows of the block's SURVIVING Gaussians are staged
 // into shared memory with coalesced 16-byte cp.async (LDGSTS) transfers and read back row-wise; rows of culled
 // Gaussians (behind the camera, oversized, off-screen) are never fetched.
 template <bool kVec16>
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
+__global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a) {
   __shared__ float s_view[16], s_proj[16], s_cam[3];
-  __shared__ __align__(16) float s_means[256 * 3];
-  __shared__ __align__(16) float s_scales[256 * 3];
-  __shared__ uint8_t s_survive[256];
-  extern __shared__ __align__(16) float4 s_sh[];  // [256][kShRow] when kVec16
+  __shared__ __align__(16) float s_means[kBlock * 3];
+  __shared__ __align__(16) float s_scales[kBlock * 3];
+  __shared__ uint8_t s_survive[kBlock];
+  extern __shared__ __align__(16) float4 s_sh[];  // [kBlock][kShRow] when kVec16
 
   const int tid = threadIdx.x;
-  const int base = blockIdx.x * 256;
-  const int n = min(256, a.P - base);
+  const int base = blockIdx.x * kBlock;
+  const int n = min(kBlock, a.P - base);
   if (tid < 16) {
     s_view[tid] = __ldg(a.viewmatrix + tid);
   } else if (tid < 32) {
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
     s_survive[tid] = prefetched;
     __syncthreads();
     const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += 256) {
+    for (int q = tid; q < n * 12; q += kBlock) {
       const int row = q / 12;
       if (s_survive[row]) {
         const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreArgs a) {
       s_survive[tid] = late;
       __syncthreads();
       const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-      for (int q = tid; q < n * 12; q += 256) {
+      for (int q = tid; q < n * 12; q += kBlock) {
         const int row = q / 12;
         if (s_survive[row]) {
           const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
@@ -434,10 +435,10 @@ cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int
   a.vec_ok = al16(f.means3D) && (!f.scales || al16(f.scales));
   const bool rot_ok = f.cov3D_precomp || al16(f.rotations);
   if (!rot_ok) return cudaErrorMisalignedAddress;
-  const int blocks = (f.P + 255) / 256;
+  const int blocks = (f.P + kBlock - 1) / kBlock;
   const bool vec16 = !f.colors_precomp && f.M == 16 && al16(f.shs);
   if (vec16) {
-    constexpr int kSmem = 256 * kShRow * (int)sizeof(float4);  // 53 248 B: needs the opt-in above 48 KB
+    constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -446,9 +447,9 @@ cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int
       if (e != cudaSuccess) return e;
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    preprocess_fwd_kernel<true><<<blocks, 256, kSmem, s>>>(a);
+    preprocess_fwd_kernel<true><<<blocks, kBlock, kSmem, s>>>(a);
   } else {
-    preprocess_fwd_kernel<false><<<blocks, 256, 0, s>>>(a);
+    preprocess_fwd_kernel<false><<<blocks, kBlock, 0, s>>>(a);
   }
   return cudaGetLastError();
 }
