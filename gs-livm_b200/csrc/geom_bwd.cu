@@ -121,12 +121,12 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   __syncthreads();
   if (kVec16) {
     const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += kBlock) {
-      const int row = q / 12;
+    for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {  // row = q / 12 without dividing
       if (s_active[row]) {
-        const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+        const uint32_t dst = smem_u32(&s_sh[row * kShRow + rem]);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
       }
+      { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -320,10 +320,10 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   if (kVec16) {  // coalesced store of the visible Gaussians' dL_dsh rows (culled rows stay at the caller's zeros)
     __syncthreads();
     float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += kBlock) {
-      const int row = q / 12;
-      if (s_active[row]) d4[q] = s_sh[row * kShRow + (q - row * 12)];
+    for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {
+      if (s_active[row]) d4[q] = s_sh[row * kShRow + rem];
       else if (a.assign_all) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }
     }
   }
   if (!active) {

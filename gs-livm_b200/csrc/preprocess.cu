@@ -170,12 +170,12 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
     s_survive[tid] = prefetched;
     __syncthreads();
     const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-    for (int q = tid; q < n * 12; q += kBlock) {
-      const int row = q / 12;
+    for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {  // row = q / 12 without dividing
       if (s_survive[row]) {
-        const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+        const uint32_t dst = smem_u32(&s_sh[row * kShRow + rem]);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
       }
+      { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -351,12 +351,12 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
       s_survive[tid] = late;
       __syncthreads();
       const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
-      for (int q = tid; q < n * 12; q += kBlock) {
-        const int row = q / 12;
+      for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {
         if (s_survive[row]) {
-          const uint32_t dst = smem_u32(&s_sh[row * kShRow + (q - row * 12)]);
+          const uint32_t dst = smem_u32(&s_sh[row * kShRow + rem]);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
         }
+        { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
