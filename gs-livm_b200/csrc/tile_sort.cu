@@ -259,7 +259,10 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
   __syncthreads();
 }
 
-template <int kCap, int kThreads>
+// kGather: also gather the 48-byte records into sorted order. The long-list classes leave that to
+// gather_long_kernel: ~1 MB of random 16-byte accesses per 10 000-instance list is bound by the bandwidth of the ONE
+// SM that sorts the list (~20 us of the CTA's ~60), while all SMs together do it for every long list in a few us.
+template <int kCap, int kThreads, bool kGather>
 __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t tile, unsigned char* smem_raw) {
   constexpr int kWarps = kThreads / 32;
   uint32_t* k0 = reinterpret_cast<uint32_t*>(smem_raw);
@@ -384,6 +387,7 @@ __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t ti
     a.keys_out[g] = hi_key | kc[i];
     a.vals_out[g] = vc[i];
   }
+  if (!kGather) return;
   auto emit = [&](int i, uint32_t id, const float4& q0, const float4& q1, const float4& q2) {
     const size_t g = (size_t)range.x + i;
     float4* dst = reinterpret_cast<float4*>(a.inst + g);
@@ -401,6 +405,42 @@ __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t ti
   }
 }
 
+// Record gather of the long lists (see sort_one_tile): work item = 1024 consecutive sorted instances of one of the
+// first summary[2] tiles of the order whose length lies in (min_len, max_len]; the CTAs stride over the items.
+constexpr int kGatherSlice = 1024, kGatherSlices = (kLargeCap + kGatherSlice - 1) / kGatherSlice;
+__global__ void __launch_bounds__(256) gather_long_kernel(const TileSortArgs a) {
+  const uint32_t work = a.summary[2] * kGatherSlices;
+  for (uint32_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const uint32_t p = w / kGatherSlices, sl = w % kGatherSlices;
+    const uint2 range = a.ranges[a.order[p]];
+    const uint32_t n = range.y - range.x;
+    if (n <= a.min_len || n > a.max_len || sl * kGatherSlice >= n) continue;
+    uint32_t id[4];
+    size_t g[4];
+    bool on[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t i = sl * kGatherSlice + u * 256 + threadIdx.x;
+      on[u] = i < n;
+      g[u] = (size_t)range.x + (on[u] ? i : 0u);
+      id[u] = a.vals_out[g[u]];
+    }
+    float4 q[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* src = reinterpret_cast<const float4*>(a.rec + id[u]);
+      q[u][0] = __ldg(src), q[u][1] = __ldg(src + 1), q[u][2] = __ldg(src + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (on[u]) {
+        float4* dst = reinterpret_cast<float4*>(a.inst + g[u]);
+        dst[0] = q[u][0], dst[1] = q[u][1], dst[2] = q[u][2];
+      }
+    }
+  }
+}
+
 // Short lists: one CTA per tile. Long lists: a few persistent CTAs (each takes a whole SM's shared memory) walk
 // the first summary[2] entries of the launch order.
 template <int kCap, int kThreads, bool kPersistent>
@@ -408,9 +448,10 @@ __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (kPersistent) {
     const uint32_t n_long = a.summary[2];
-    for (uint32_t t = blockIdx.x; t < n_long; t += gridDim.x) sort_one_tile<kCap, kThreads>(a, a.order[t], smem_raw);
+    for (uint32_t t = blockIdx.x; t < n_long; t += gridDim.x)
+      sort_one_tile<kCap, kThreads, false>(a, a.order[t], smem_raw);
   } else {
-    sort_one_tile<kCap, kThreads>(a, a.order[blockIdx.x], smem_raw);
+    sort_one_tile<kCap, kThreads, true>(a, a.order[blockIdx.x], smem_raw);
   }
 }
 
@@ -498,11 +539,14 @@ cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, cons
   if (n_large != 0) {
     const int cap = n_large > 0 ? n_large : tiles;
     a.min_len = (uint32_t)kMidCap - 1u, a.max_len = (uint32_t)kLargeCap;
+    const int gwork = cap * kGatherSlices, ggrid = gwork < 8 * sms ? gwork : 8 * sms;
     tile_sort_kernel<kLargeCap, kLargeThreads, true><<<cap < sms ? cap : sms, kLargeThreads, kSmemLarge, s>>>(a);
+    gather_long_kernel<<<ggrid, 256, 0, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     a.min_len = (uint32_t)kSmallMax, a.max_len = (uint32_t)kMidCap - 1u;
     tile_sort_kernel<kMidCap, kLargeThreads, true><<<cap < 2 * sms ? cap : 2 * sms, kLargeThreads, kSmemMid, mid_stream>>>(a);
+    gather_long_kernel<<<ggrid, 256, 0, mid_stream>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
