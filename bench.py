@@ -230,7 +230,10 @@ def run_ours(args, rank, world, dev):
     from gs_livm_b200 import window
     grad_floats = (3 + 16 * 3 + 3 + 4 + 1 + 3 + 4 + 3 + 6) * P_GAUSS  # RasterContext.GRAD_LAYOUT
     param_floats = (3 + 16 * 3 + 3 + 4 + 1) * P_GAUSS                 # what the window all-reduces: 236 B/Gaussian
-    exchange = window.GradExchange(grad_floats, param_floats, dev) if world > 1 else None
+    # dL_dsh (48 floats per Gaussian, behind the 3 floats of dL_dmean3D) is exchanged only for Gaussians some view of
+    # the step rendered: rows of the others are zero on every rank (window.GradExchange, sparse_rows)
+    exchange = window.GradExchange(grad_floats, param_floats, dev,
+                                   sparse_rows=(3 * P_GAUSS, P_GAUSS, 48)) if world > 1 else None
     ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE, grad_flat=exchange.flat if exchange else None)
     assert ctx.param_grads().numel() == param_floats
 
@@ -244,7 +247,7 @@ def run_ours(args, rank, world, dev):
             ctx.forward(sc, cams[k])
             ctx.backward(dC, dS)
         if exchange is not None:
-            exchange.allreduce_()  # libgsr_b200's own exchange over peer memory where available, else NCCL
+            exchange.allreduce_(radii=ctx.radii)  # own exchange over peer memory where available, else NCCL
 
     # ---- device-resident timing: W warm-up, K timed steps, CUDA events, max over ranks ----
     # RasterContext is sync-free after its first frame (gsr_forward_presized): the warm-up also walks the whole

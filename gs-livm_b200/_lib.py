@@ -50,6 +50,11 @@ class BwdArgs(C.Structure):
 BWD_OUTPUTS_UNINITIALIZED = 1
 
 
+class WindowRows(C.Structure):
+    _fields_ = [("union_words", C.c_void_p), ("first_float", C.c_size_t), ("n_rows", C.c_uint32),
+                ("floats_per_row", C.c_uint32)]
+
+
 class ArrayView(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("stride", C.c_size_t), ("count", C.c_size_t)]
 
@@ -91,6 +96,11 @@ SYMBOLS = {
     "gsr_backward": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
     "gsr_window_allreduce_multimem": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "gsr_window_allreduce_p2p": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gsr_window_visibility_words": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "gsr_window_union_words": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "gsr_window_allreduce_multimem_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "gsr_window_allreduce_p2p_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p]),
     "gsr_mark_visible": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_view_geom": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GeomView)]),
     "gsr_view_binning": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BinningView)]),

@@ -45,9 +45,20 @@ class GradExchange:
     best the system offers). Every rank ends up with the same bits in all modes (each slice is summed once, in
     one place, then distributed)."""
 
-    def __init__(self, numel_total: int, numel_reduce: int, device, group=None, prefer: str = "auto"):
+    def __init__(self, numel_total: int, numel_reduce: int, device, group=None, prefer: str = "auto",
+                 sparse_rows: Optional[tuple] = None):
+        """sparse_rows = (first_float, n_rows, floats_per_row): floats [first_float, first_float + n_rows *
+        floats_per_row) of the buffer are one row per Gaussian (dL_dsh) that is all zero on every rank whose view did
+        not render the Gaussian; `allreduce_(radii=...)` then exchanges only the rows rendered by some view."""
         self.group = group
         self.n = int(numel_reduce)
+        self.rows = None
+        if sparse_rows is not None:
+            first, n_rows, fpr = (int(v) for v in sparse_rows)
+            if first % 4 == 0 and fpr % 4 == 0 and fpr > 0 and first + n_rows * fpr <= self.n:
+                self.rows = (first, n_rows, fpr)
+        n_words = (self.rows[1] + 31) // 32 if self.rows else 0
+        words_at = (int(numel_total) + 3) // 4 * 4  # visibility words live behind the gradients, 16-byte aligned
         self.device = torch.device(device)
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -56,7 +67,7 @@ class GradExchange:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 grp = group if group is not None else dist.group.WORLD
-                flat = symm_mem.empty(int(numel_total), dtype=torch.float32, device=self.device)
+                flat = symm_mem.empty(words_at + n_words, dtype=torch.float32, device=self.device)
                 hdl = symm_mem.rendezvous(flat, grp)
                 flat.zero_()
                 self.flat, self.hdl = flat, hdl
@@ -79,6 +90,11 @@ class GradExchange:
             self._peers = (C.c_void_p * self.world)(*ptrs)
             if ptrs[self.rank] != self.flat.data_ptr():
                 raise RuntimeError("symmetric buffer pointer mismatch")
+            if self.rows is not None:
+                self._my_words = self.flat[words_at:words_at + n_words].view(torch.int32)
+                self._peer_words = (C.c_void_p * self.world)(*[p + 4 * words_at for p in ptrs])
+                self._union = torch.zeros(n_words, dtype=torch.int32, device=self.device)
+                self._rows_arg = _lib.WindowRows(self._union.data_ptr(), self.rows[0], self.rows[1], self.rows[2])
             if prefer == "auto":
                 self._calibrate()
 
@@ -103,22 +119,36 @@ class GradExchange:
         self.calibration_ms = dict(zip(modes, (float(v) for v in t.tolist())))
         self.mode = modes[int(torch.argmin(t).item())]
 
-    def allreduce_(self) -> torch.Tensor:
+    def allreduce_(self, radii: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """radii (int32 [n_rows], this rank's view: > 0 = rendered): exchange the sparse rows only where some rank
+        rendered the Gaussian (needs sparse_rows at construction and one of the peer-memory modes)."""
         if self.world <= 1:
             return self.flat
         if self.mode == "nccl":
             dist.all_reduce(self.flat[:self.n], op=dist.ReduceOp.SUM, group=self.group)
             return self.flat
+        import ctypes as C
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.hdl.barrier(channel=0)  # every rank's gradients are complete
+        rows = None
+        if radii is not None and self.rows is not None:
+            if radii.dtype != torch.int32 or radii.numel() != self.rows[1] or not radii.is_contiguous():
+                raise ValueError("radii must be a contiguous int32 tensor with one entry per sparse row")
+            st = self.lib.gsr_window_visibility_words(radii.data_ptr(), self.rows[1], self._my_words.data_ptr(), stream)
+            self._lib.check(st, "gsr_window_visibility_words")
+            rows = C.byref(self._rows_arg)
+        self.hdl.barrier(channel=0)  # every rank's gradients (and visibility words) are complete
+        if rows is not None:
+            st = self.lib.gsr_window_union_words(self._peer_words, self._union.numel(), self.world,
+                                                 self._union.data_ptr(), stream)
+            self._lib.check(st, "gsr_window_union_words")
         if self.mode == "multimem":
-            st = self.lib.gsr_window_allreduce_multimem(self._mc, self.n, self.rank, self.world, stream)
+            st = self.lib.gsr_window_allreduce_multimem_rows(self._mc, self.n, self.rank, self.world, rows, stream)
             self._lib.check(st, "gsr_window_allreduce_multimem")
         else:
-            st = self.lib.gsr_window_allreduce_p2p(self._peers, self.n, self.rank, self.world, 1, stream)
+            st = self.lib.gsr_window_allreduce_p2p_rows(self._peers, self.n, self.rank, self.world, 1, rows, stream)
             self._lib.check(st, "gsr_window_allreduce_p2p")
             self.hdl.barrier(channel=1)  # every slice is reduced
-            st = self.lib.gsr_window_allreduce_p2p(self._peers, self.n, self.rank, self.world, 2, stream)
+            st = self.lib.gsr_window_allreduce_p2p_rows(self._peers, self.n, self.rank, self.world, 2, rows, stream)
             self._lib.check(st, "gsr_window_allreduce_p2p")
         self.hdl.barrier(channel=2)  # every rank holds the sum; buffers may be rewritten
         return self.flat

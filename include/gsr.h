@@ -216,6 +216,28 @@ GSR_API int gsr_window_allreduce_multimem(void* multicast_buffer, size_t n_float
 GSR_API int gsr_window_allreduce_p2p(void* const* peer_buffers, size_t n_floats, int rank, int world, int phase,
                                      void* stream);
 
+/* Sparse variant of the exchange. Floats [first_float, first_float + n_rows * floats_per_row) of the buffer are rows
+ * of one Gaussian each (the 192-byte dL_dsh rows: 81 % of the gradient buffer) and row r is exchanged only if bit r
+ * of union_words is set: the union over the ranks of "Gaussian r was visible in my view". A Gaussian visible in no
+ * view of the window has an all-zero row on every rank, so the result is unchanged. first_float and floats_per_row
+ * must be multiples of 4. rows == NULL or union_words == NULL: dense exchange.
+ *   gsr_window_visibility_words: bit b of words[w] = radii[32 w + b] > 0, into THIS rank's part of a symmetric
+ *     allocation (ceil(P / 32) words);
+ *   gsr_window_union_words: out[w] = OR over ranks of peer_words[r][w] (after a barrier across the ranks);
+ *   gsr_window_allreduce_{multimem,p2p}_rows: as above with the row mask. */
+typedef struct gsr_window_rows {
+  const uint32_t* union_words; /* device pointer, local */
+  size_t first_float;
+  uint32_t n_rows;
+  uint32_t floats_per_row;
+} gsr_window_rows;
+GSR_API int gsr_window_visibility_words(const int* radii, int P, uint32_t* words, void* stream);
+GSR_API int gsr_window_union_words(void* const* peer_words, int n_words, int world, uint32_t* out, void* stream);
+GSR_API int gsr_window_allreduce_multimem_rows(void* multicast_buffer, size_t n_floats, int rank, int world,
+                                               const gsr_window_rows* rows, void* stream);
+GSR_API int gsr_window_allreduce_p2p_rows(void* const* peer_buffers, size_t n_floats, int rank, int world, int phase,
+                                          const gsr_window_rows* rows, void* stream);
+
 GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present, void* stream);
 

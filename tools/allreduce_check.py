@@ -34,4 +34,30 @@ for mode in ("multimem", "p2p", "nccl"):
         print(f"requested {mode:9s} -> mode {ex.mode:9s} {ex.why} max|err vs NCCL| {err:.3e} tail untouched {tail_ok} "
               f"ranks identical {same and same_sum}  {e0.elapsed_time(e1) / 10 * 1e3:8.1f} us per 236 MB exchange", flush=True)
     del ex
+# sparse rows: the layout of the bench (dL_dmean3D | dL_dsh | ...), every rank "renders" a different 55 % of the Gaussians
+# and the rows it did not render are zero, as geom_bwd leaves them
+P = 1_000_000
+for mode in ("multimem", "p2p"):
+    ex = window.GradExchange(n + 1024, n, dev, prefer=mode, sparse_rows=(3 * P, P, 48))
+    if ex.mode == "nccl":
+        continue
+    vis = torch.rand(P, device=dev, generator=g) < 0.55
+    radii = vis.to(torch.int32) * 3
+    mine = src.clone()
+    mine[3 * P:51 * P].view(P, 48)[~vis] = 0.0
+    want = mine.clone(); dist.all_reduce(want)
+    ex.flat[:n].copy_(mine)
+    ex.allreduce_(radii=radii); torch.cuda.synchronize()
+    err = (ex.flat[:n] - want).abs().max().item()
+    for _ in range(3): ex.allreduce_(radii=radii)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ex.allreduce_(radii=radii)
+    e1.record(); torch.cuda.synchronize()
+    uni = torch.zeros(P, device=dev); uni[vis] = 1; dist.all_reduce(uni, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"sparse rows, mode {ex.mode:9s}: max|err vs NCCL| {err:.3e}, union of rendered Gaussians {float(uni.mean()):.2f}, "
+              f"{e0.elapsed_time(e1) / 10 * 1e3:8.1f} us per exchange", flush=True)
+    del ex
 dist.barrier(); dist.destroy_process_group()
