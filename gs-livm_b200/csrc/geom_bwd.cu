@@ -106,12 +106,10 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   __shared__ uint8_t s_active[kBlock];
   extern __shared__ __align__(16) float4 s_sh[];  // [kBlock][kShRow] when kVec16
   const int tid = threadIdx.x;
-  if (tid < 16) {
-    s_view[tid] = __ldg(a.viewmatrix + tid);
-  } else if (tid < 32) {
-    s_proj[tid - 16] = __ldg(a.projmatrix + tid - 16);
-  } else if (tid < 35) {
-    s_cam[tid - 32] = __ldg(a.cam_pos + tid - 32);
+  for (int i = tid; i < 35; i += kBlock) {  // the camera: 16 + 16 + 3 floats
+    if (i < 16) s_view[i] = __ldg(a.viewmatrix + i);
+    else if (i < 32) s_proj[i - 16] = __ldg(a.projmatrix + i - 16);
+    else s_cam[i - 32] = __ldg(a.cam_pos + i - 32);
   }
   const int base = blockIdx.x * kBlock;
   const int n = min(kBlock, a.P - base);

@@ -115,12 +115,10 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
   const int tid = threadIdx.x;
   const int base = blockIdx.x * kBlock;
   const int n = min(kBlock, a.P - base);
-  if (tid < 16) {
-    s_view[tid] = __ldg(a.viewmatrix + tid);
-  } else if (tid < 32) {
-    s_proj[tid - 16] = __ldg(a.projmatrix + tid - 16);
-  } else if (tid < 35) {
-    s_cam[tid - 32] = __ldg(a.cam_pos + tid - 32);
+  for (int i = tid; i < 35; i += kBlock) {  // the camera: 16 + 16 + 3 floats
+    if (i < 16) s_view[i] = __ldg(a.viewmatrix + i);
+    else if (i < 32) s_proj[i - 16] = __ldg(a.projmatrix + i - 16);
+    else s_cam[i - 32] = __ldg(a.cam_pos + i - 32);
   }
   stage_floats(s_means, a.means3D + (size_t)base * 3, n * 3, a.vec_ok);
   if (a.scales) stage_floats(s_scales, a.scales + (size_t)base * 3, n * 3, a.vec_ok);
