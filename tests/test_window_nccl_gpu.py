@@ -1,6 +1,7 @@
 """The window's gradient exchange on real GPUs (needs >= 2 of them; the single-GPU box skips it): every mode of
 window.GradExchange — libgsr_b200's NVSwitch-multicast kernel, its two-shot peer-to-peer kernels, NCCL — gives the
-NCCL sum, leaves the rest of the buffer alone and ends with identical bits on every rank."""
+NCCL sum, leaves the rest of the buffer alone and ends with identical bits on every rank; the row-sparse exchange
+gives exactly the dense result."""
 import os
 import subprocess
 import sys
@@ -25,3 +26,8 @@ def test_grad_exchange_modes_agree_across_ranks(built_library):
         assert "tail untouched True" in ln and "ranks identical True" in ln, ln
         err = float(ln.split("max|err vs NCCL|")[1].split()[0])
         assert err <= 1e-4, ln
+    # the sparse exchange (rows of Gaussians no rank rendered are skipped) must give the dense sum exactly
+    sparse = [ln for ln in out.stdout.splitlines() if ln.startswith("sparse rows")]
+    assert sparse, out.stdout
+    for ln in sparse:
+        assert float(ln.split("max|err vs NCCL|")[1].split(",")[0]) == 0.0, ln
