@@ -95,6 +95,7 @@ class RenderArena:
         self._bufs = {k: torch.empty(0, dtype=torch.uint8, device=self.device) for k in ("geom", "binning", "image")}
         self._fns = {k: _lib.ALLOC_FN(lambda _ctx, n, _k=k: self._grow(_k, n)) for k in self._bufs}
         self.capacity = 0
+        self.param_grad_span = None  # after a backward: the contiguous span that holds the parameter gradients
         self._status = torch.zeros((16, 4), dtype=torch.int32).pin_memory()
         self._head = 0
         self._unchecked = []
@@ -254,7 +255,7 @@ def rasterize_gaussians_cuda(background, means3D, colors, opacity, scales, rotat
 def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                       cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                       dL_dout_acc, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer,
-                                      debug):
+                                      debug, arena: Optional["RenderArena"] = None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)."""
     lib = _lib.load()
     dev = means3D.device
@@ -265,16 +266,22 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
     # outputs are uninitialised instead (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element of what it
     # computes; only what it does not touch on this argument combination is zeroed here.
     have_cov = cov3D_precomp is not None and cov3D_precomp.numel() != 0
-    widths = (3, 3, NUM_CHANNELS, 4, 1, 6, M * 3, 3, 4)  # one allocation, nine 256-byte aligned views
-    starts, off = [], 0
-    for w in widths:
-        starts.append(off)
-        off += (P * w + 63) // 64 * 64
+    # one allocation, nine 256-byte aligned views; the gradients of the optimised parameters (mean3D, sh, scale,
+    # rotation, opacity) come first, so that a view-sharded window can sum them with ONE collective over a contiguous
+    # span (arena.param_grad_span) instead of one per tensor
+    order = ("means3D", "sh", "scales", "rotations", "opacity", "means2D", "colors", "conic", "cov3D")
+    width = dict(means3D=3, sh=M * 3, scales=3, rotations=4, opacity=1, means2D=3, colors=NUM_CHANNELS, conic=4, cov3D=6)
+    start, off = {}, 0
+    for k in order:
+        start[k] = off
+        off += (P * width[k] + 63) // 64 * 64
     flat = (torch.empty if P != 0 else torch.zeros)((off,), **opts)
-    views = [flat[st:st + P * w] for st, w in zip(starts, widths)]
-    dL_dmeans3D, dL_dmeans2D, dL_dcolors = views[0].view(P, 3), views[1].view(P, 3), views[2].view(P, NUM_CHANNELS)
-    dL_dconic, dL_dopacity, dL_dcov3D = views[3].view(P, 2, 2), views[4].view(P, 1), views[5].view(P, 6)
-    dL_dsh, dL_dscales, dL_drotations = views[6].view(P, M, 3), views[7].view(P, 3), views[8].view(P, 4)
+    view = {k: flat[start[k]:start[k] + P * width[k]] for k in order}
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors = view["means3D"].view(P, 3), view["means2D"].view(P, 3), view["colors"].view(P, NUM_CHANNELS)
+    dL_dconic, dL_dopacity, dL_dcov3D = view["conic"].view(P, 2, 2), view["opacity"].view(P, 1), view["cov3D"].view(P, 6)
+    dL_dsh, dL_dscales, dL_drotations = view["sh"].view(P, M, 3), view["scales"].view(P, 3), view["rotations"].view(P, 4)
+    if arena is not None:
+        arena.param_grad_span = flat[:start["means2D"]]
     if have_cov and P != 0:
         dL_dscales.zero_()
         dL_drotations.zero_()
@@ -331,6 +338,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                                      rs.image_height, rs.image_width, sh, rs.sh_degree, rs.camera_center,
                                      rs.prefiltered, False, arena)
         ctx.raster_settings = rs
+        ctx.arena = arena
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
                               binningBuffer, imgBuffer)
@@ -351,7 +359,7 @@ class _RasterizeGaussians(torch.autograd.Function):
          grad_rotations) = rasterize_gaussians_backward_cuda(
             rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
             rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_acc, sh, rs.sh_degree,
-            rs.camera_center, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, False)
+            rs.camera_center, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, False, ctx.arena)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
                 grad_cov3Ds_precomp, None, None)
 
