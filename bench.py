@@ -375,9 +375,9 @@ def run_ours(args, rank, world, dev):
             caps.append(arena.capacity)
         arena.capacity = max(caps)
     e2e_mode = "eager launches"
-    # one GPU: the step is captured once and replayed. Several GPUs: the step contains NCCL all-reduces; capturing
-    # those is possible but has not been validated on this pool, so it stays opt-in (GSR_BENCH_GRAPH=1).
-    if os.environ.get("GSR_BENCH_GRAPH", "1" if world == 1 else "0") != "0":
+    # the step is captured once and replayed; with several GPUs the graph contains the NCCL all-reduce of the
+    # parameter-gradient span (validated on this pool at N = 2 and N = 8). GSR_BENCH_GRAPH=0: eager launches.
+    if os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
         try:
             for j in range(2):
                 captured[j] = rasterizer.CapturedStep(lambda j=j: step_body(j), arena)
