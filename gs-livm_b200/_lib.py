@@ -48,6 +48,7 @@ class BwdArgs(C.Structure):
 
 
 BWD_OUTPUTS_UNINITIALIZED = 1
+ABI_VERSION = 3  # include/gsr.h GSR_ABI_VERSION this binding was written against
 
 
 class WindowRows(C.Structure):

@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol(built_library):
     for name in declared_symbols():
         assert hasattr(built_library, name), f"{name} declared in include/gsr.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in _lib.SYMBOLS"
-    assert built_library.gsr_abi_version() == 3
+    from gs_livm_b200 import _lib
+    assert built_library.gsr_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_ctypes_struct_layout_matches_the_library(built_library):
