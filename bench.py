@@ -259,8 +259,13 @@ def run_ours(args, rank, world, dev):
             ctx.check()
     resident_mode = "eager launches"
     if os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
-        captured_frames[:] = [ctx.capture_step(sc, cams[k], dC, dS) for k in range(WINDOW)]
-        resident_mode = "CUDA-graph replay (RasterContext.capture_step), one graph per pose"
+        try:
+            captured_frames[:] = [ctx.capture_step(sc, cams[k], dC, dS) for k in range(WINDOW)]
+            resident_mode = "CUDA-graph replay (RasterContext.capture_step), one graph per pose"
+        except Exception as exc:  # capture not possible here: the same launches, issued eagerly
+            captured_frames[:] = [None] * WINDOW
+            resident_mode = "eager launches (graph capture failed: %s)" % type(exc).__name__
+            torch.cuda.synchronize()
         for i in range(WINDOW):
             step_resident(i)
         if not ctx.check():
