@@ -48,7 +48,7 @@ struct BwdArgs {
   const SplatRecord* inst;
   const uint32_t* point_list;
   const uint2* blist;
-  const uint32_t* block_count;
+  const uint4* bdesc;
   const uint32_t* bhits;
   const uint32_t* tail_hits;
   const uint32_t* last_group;
@@ -109,17 +109,17 @@ __device__ __forceinline__ void pair_alpha(const float4 qa, const float4 qb, flo
 // pairs of their pixel at once, all replay the ordered recurrence, and the lane that evaluated a pair leaves
 // its (u, w) in the pair's slot.
 template <int SLOTS, int ILP>
-__device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, int tile, int block, int sub, int lane) {
+__device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, const uint4 desc, int block, int sub,
+                                                int lane) {
   constexpr int STRIDE = SLOTS == 1 ? kSlotStride : 9;  // slot row stride
-  const uint2 range = a.ranges[tile];
-  const int n = (int)(range.y - range.x);
-  if (n == 0) return;
-  const int cnt = (int)a.block_count[tile * 8 + block];
-  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)block * n;
-  const uint32_t* hits = a.bhits + (size_t)8 * range.x + (size_t)block * n;
+  // desc = {range start, list length, candidates of this block, tile} (block_lists.cu)
+  const int tile = (int)desc.w, n = (int)desc.y, cnt = (int)desc.z;
+  if (cnt == 0) return;
+  const uint2* list = a.blist + (size_t)8 * desc.x + (size_t)block * n;
+  const uint32_t* hits = a.bhits + (size_t)8 * desc.x + (size_t)block * n;
   const uint32_t* tail = a.tail_hits + (size_t)(tile * 8 + block) * 32;
-  const SplatRecord* src = a.inst + range.x;
-  const uint32_t* ids = a.point_list + range.x;
+  const SplatRecord* src = a.inst + desc.x;
+  const uint32_t* ids = a.point_list + desc.x;
 
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
   const int pix = SLOTS == 1 ? lane : (lane & 7), slot = SLOTS == 1 ? 0 : (lane >> 3);
@@ -290,17 +290,16 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
   WarpBuf& buf = reinterpret_cast<WarpBuf*>(smem_raw)[warp];
   const int b = (int)blockIdx.x;
   if (b < 8 * a.fine_tiles) {
-    const int tile = (int)a.tile_order[b >> 3];
-    const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) < a.heavy) return;
-    blend_bwd_block<4, 1>(a, buf, tile, b & 7, warp, lane);
+    const uint4 d = a.bdesc[b];  // (position b / 8, block b % 8)
+    if ((int)d.y < a.heavy) return;
+    blend_bwd_block<4, 1>(a, buf, d, b & 7, warp, lane);
   } else {
     const int c = b - 8 * a.fine_tiles;
-    const int tile = (int)a.tile_order[c >> 1];
-    const uint2 r = a.ranges[tile];
+    const int block = (c & 1) * 4 + warp;
+    const uint4 d = a.bdesc[(c >> 1) * 8 + block];
     // FINE CTAs exist for the first fine_tiles entries of the order only: a heavy tile beyond them is done here
-    if ((int)(r.y - r.x) >= a.heavy && (c >> 1) < a.fine_tiles) return;
-    blend_bwd_block<1, ILP>(a, buf, tile, (c & 1) * 4 + warp, 0, lane);
+    if ((int)d.y >= a.heavy && (c >> 1) < a.fine_tiles) return;
+    blend_bwd_block<1, ILP>(a, buf, d, block, 0, lane);
   }
 }
 
@@ -330,7 +329,7 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   }
   BwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
-  a.blist = b.blist, a.block_count = img.block_count;
+  a.blist = b.blist, a.bdesc = img.bdesc;
   a.bhits = b.bhits, a.tail_hits = img.tail_hits, a.last_group = img.last_group;
   a.W = width, a.H = height, a.grid_x = grid_x;
   a.heavy = blend_heavy_threshold();

@@ -41,7 +41,7 @@ struct FwdArgs {
   const uint32_t* tile_order;
   const SplatRecord* inst;
   const uint2* blist;
-  const uint32_t* block_count;
+  const uint4* bdesc;
   uint32_t* last_group;
   uint32_t* bhits;
   uint32_t* tail_hits;
@@ -80,13 +80,12 @@ __device__ __forceinline__ float pair_alpha(const float4 qa, const float4 qb, fl
 // and all replay the ordered transmittance recurrence; each lane accumulates one output channel (slot 0: S and
 // D, slots 1-3: R, G, B) so every channel still sees the reference's exact sequence of operations.
 template <int SLOTS, int ILP>
-__device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, int tile, int block, int sub, int lane) {
-  const uint2 range = a.ranges[tile];
-  const int n = (int)(range.y - range.x);
-  const int cnt = n ? (int)a.block_count[tile * 8 + block] : 0;
-  const uint2* list = a.blist + (size_t)8 * range.x + (size_t)block * n;
-  const SplatRecord* src = a.inst + range.x;
-  uint32_t* hits = a.bhits + (size_t)8 * range.x + (size_t)block * n;  // full groups; the partial last one: tail_hits
+__device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, const uint4 desc, int block, int sub, int lane) {
+  // desc = {range start, list length, candidates of this block, tile} (block_lists.cu)
+  const int tile = (int)desc.w, n = (int)desc.y, cnt = (int)desc.z;
+  const uint2* list = a.blist + (size_t)8 * desc.x + (size_t)block * n;
+  const SplatRecord* src = a.inst + desc.x;
+  uint32_t* hits = a.bhits + (size_t)8 * desc.x + (size_t)block * n;  // full groups; the partial last one: tail_hits
 
   const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
   const int pix = SLOTS == 1 ? lane : (lane & 7), slot = SLOTS == 1 ? 0 : (lane >> 3);
@@ -255,16 +254,16 @@ __global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const Fwd
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = (int)blockIdx.x;
   if (b < 4 * a.fine_tiles) {
-    const int tile = (int)a.tile_order[b >> 2];
-    const uint2 r = a.ranges[tile];
-    if ((int)(r.y - r.x) < a.heavy) return;
-    blend_block<4, 1>(a, bufs[warp], tile, 2 * (b & 3) + (warp >> 2), warp & 3, lane);
+    const int block = 2 * (b & 3) + (warp >> 2);
+    const uint4 d = a.bdesc[(b >> 2) * 8 + block];
+    if ((int)d.y < a.heavy) return;
+    blend_block<4, 1>(a, bufs[warp], d, block, warp & 3, lane);
   } else {
-    const int tile = (int)a.tile_order[b - 4 * a.fine_tiles];
-    const uint2 r = a.ranges[tile];
+    const int pos = b - 4 * a.fine_tiles;
+    const uint4 d = a.bdesc[pos * 8 + warp];
     // FINE CTAs exist for the first fine_tiles entries of the order only: a heavy tile beyond them is done here
-    if ((int)(r.y - r.x) >= a.heavy && b - 4 * a.fine_tiles < a.fine_tiles) return;
-    blend_block<1, ILP>(a, bufs[warp], tile, warp, 0, lane);
+    if ((int)d.y >= a.heavy && pos < a.fine_tiles) return;
+    blend_block<1, ILP>(a, bufs[warp], d, warp, 0, lane);
   }
 }
 
@@ -284,7 +283,7 @@ cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img
   const int tiles = grid_x * grid_y;
   FwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.blist = b.blist;
-  a.block_count = img.block_count, a.last_group = img.last_group;
+  a.bdesc = img.bdesc, a.last_group = img.last_group;
   a.bhits = b.bhits, a.tail_hits = img.tail_hits;
   a.W = width, a.H = height, a.grid_x = grid_x;
   a.heavy = blend_heavy_threshold();

@@ -28,6 +28,7 @@ struct BlockListArgs {
   const SplatRecord* inst;
   uint2* blist;
   uint32_t* block_count;
+  uint4* bdesc;
   int grid_x;
 };
 
@@ -60,7 +61,10 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
   const uint2 range = a.ranges[tile];
   const int n = (int)(range.y - range.x);
   if (n == 0) {
-    if (threadIdx.x < 8) a.block_count[tile * 8 + threadIdx.x] = 0;
+    if (threadIdx.x < 8) {
+      a.block_count[tile * 8 + threadIdx.x] = 0;
+      a.bdesc[blockIdx.x * 8 + threadIdx.x] = make_uint4(0u, 0u, 0u, (uint32_t)tile);
+    }
     return;
   }
   const float tx0 = (float)((tile % a.grid_x) * kTile), ty0 = (float)((tile / a.grid_x) * kTile);
@@ -106,7 +110,10 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
     run += total;
     // counts[it & 1] is rewritten two iterations from now, behind the next iteration's barrier
   }
-  if (warp == 0 && lane < 8) a.block_count[tile * 8 + lane] = run;
+  if (warp == 0 && lane < 8) {
+    a.block_count[tile * 8 + lane] = run;
+    a.bdesc[blockIdx.x * 8 + lane] = make_uint4(range.x, (uint32_t)n, run, (uint32_t)tile);
+  }
 }
 
 }  // namespace
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
 cudaError_t launch_block_lists(int tiles, const ImageState& img, const BinningState& b, int grid_x, cudaStream_t s) {
   BlockListArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.blist = b.blist;
-  a.block_count = img.block_count, a.grid_x = grid_x;
+  a.block_count = img.block_count, a.bdesc = img.bdesc, a.grid_x = grid_x;
   block_lists_kernel<<<tiles, kWarps * 32, 0, s>>>(a);
   return cudaGetLastError();
 }

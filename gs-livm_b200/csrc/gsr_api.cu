@@ -93,6 +93,7 @@ ImageState carve_image(char* chunk, int width, int height) {
   carve(chunk, s.tile_count, tiles);
   carve(chunk, s.summary, 4);
   carve(chunk, s.block_count, tiles * 8);
+  carve(chunk, s.bdesc, tiles * 8);
   carve(chunk, s.last_group, N);
   carve(chunk, s.tail_hits, tiles * 8 * 32);
   return s;

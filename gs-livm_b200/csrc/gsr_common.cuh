@@ -48,6 +48,8 @@ struct ImageState {
   uint32_t* tile_count; // [tiles] instances per tile (preprocess), then the tile's scatter cursor (tile_sort.cu)
   uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, overflow code (sync-free forward)}
   uint32_t* block_count;  // [tiles*8] candidates per 8x4 pixel block (block_lists.cu)
+  uint4* bdesc;           // [tiles*8] by (position in tile_order, block): {range start, list length, candidates, tile} --
+                          //           one load tells a blend warp everything it needs to find its list
   uint32_t* last_group;   // [W*H] 1 + the group (of 32 candidates of its block's list) of the pixel's last contributor
   uint32_t* tail_hits;    // [tiles*8][32] hit masks of each block's last, partial group (see BinningState::bhits)
 };
