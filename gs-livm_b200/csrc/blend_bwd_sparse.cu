@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
 
 }  // namespace
 
-int blend_heavy_threshold();  // blend_fwd_sparse.cu
+int blend_heavy_threshold(bool forward);  // blend_fwd_sparse.cu
 
 cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
                                     const float* background, const float* dL_dpix, const float* dL_dacc,
@@ -332,7 +332,7 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   a.blist = b.blist, a.bdesc = img.bdesc;
   a.bhits = b.bhits, a.tail_hits = img.tail_hits, a.last_group = img.last_group;
   a.W = width, a.H = height, a.grid_x = grid_x;
-  a.heavy = blend_heavy_threshold();
+  a.heavy = blend_heavy_threshold(false);
   a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;
   a.bg = background, a.final_T = img.final_T;
   a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;

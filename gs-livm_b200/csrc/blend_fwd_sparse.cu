@@ -26,7 +26,6 @@ namespace gsr {
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kHeavy = 4096;   // tiles with at least this many instances use the FINE shape
 constexpr int kFineCap = 384;  // FINE candidates: the first kFineCap tiles of tile_order (longest lists)
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -270,10 +269,11 @@ __global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const Fwd
 }  // namespace
 
 // List length from which a tile's warps take the FINE shape. The hit masks and last_group the forward leaves are
-// laid out per pixel, independent of the shape, so the two kernels need not agree; one knob is simply enough.
-int blend_heavy_threshold() {
-  const char* e = getenv("GSR_BLEND_HEAVY");  // tuning / test knob, read per call
-  return e ? atoi(e) : kHeavy;
+// laid out per pixel, independent of the shape, so the two kernels need not agree: the forward gains from FINE a
+// little earlier (3072) than the backward (4096), whose FINE warps also pay four phase-C passes per group.
+int blend_heavy_threshold(bool forward) {
+  const char* e = getenv("GSR_BLEND_HEAVY");  // tuning / test knob for both kernels, read per call
+  return e ? atoi(e) : (forward ? 3072 : 4096);
 }
 
 cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
@@ -286,7 +286,7 @@ cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img
   a.bdesc = img.bdesc, a.last_group = img.last_group;
   a.bhits = b.bhits, a.tail_hits = img.tail_hits;
   a.W = width, a.H = height, a.grid_x = grid_x;
-  a.heavy = blend_heavy_threshold();
+  a.heavy = blend_heavy_threshold(true);
   a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;  // only the longest kFineCap lists can be FINE
   a.bg = background, a.out_color = out_color, a.out_depth = out_depth, a.out_acc = out_acc;
   a.final_T = img.final_T, a.n_contrib = img.n_contrib, a.tile_last = img.tile_last;
