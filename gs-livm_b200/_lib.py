@@ -48,6 +48,7 @@ class BwdArgs(C.Structure):
 
 
 BWD_OUTPUTS_UNINITIALIZED = 1
+BWD_ACCUMULATORS_ZEROED = 2
 ABI_VERSION = 3  # include/gsr.h GSR_ABI_VERSION this binding was written against
 
 
@@ -95,6 +96,7 @@ SYMBOLS = {
     "gsr_forward_presized": (C.c_int, [C.POINTER(FwdArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "gsr_backward": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
+    "gsr_backward_prepare": (C.c_int, [C.POINTER(BwdArgs), C.c_void_p]),
     "gsr_window_allreduce_multimem": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "gsr_window_allreduce_p2p": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gsr_window_visibility_words": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -340,6 +340,39 @@ int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, char* binn
   return launch_blend_forward(a, img, bin, tiles, grid_x, debug, stream);
 }
 
+// The four outputs blend_bwd accumulates into with atomics start from zero; adjacent arrays (one flat gradient buffer,
+// as gs_livm_b200.engine lays them out) are cleared by one memset.
+static int zero_accumulators(const gsr_bwd_args& a, cudaStream_t stream) {
+  struct Span {
+    char* p;
+    size_t n;
+  } spans[4] = {{reinterpret_cast<char*>(a.dL_dmean2D), 3 * (size_t)a.P * sizeof(float)},
+                {reinterpret_cast<char*>(a.dL_dconic), 4 * (size_t)a.P * sizeof(float)},
+                {reinterpret_cast<char*>(a.dL_dopacity), (size_t)a.P * sizeof(float)},
+                {reinterpret_cast<char*>(a.dL_dcolor), 3 * (size_t)a.P * sizeof(float)}};
+  for (int i = 0; i < 4; ++i)
+    for (int j = i + 1; j < 4; ++j)
+      if (spans[j].p < spans[i].p) {
+        Span t = spans[i];
+        spans[i] = spans[j], spans[j] = t;
+      }
+  for (int i = 0; i < 4;) {
+    char* p = spans[i].p;
+    size_t n = spans[i].n;
+    int j = i + 1;
+    while (j < 4 && spans[j].p == p + n) n += spans[j++].n;
+    GSR_CUDA(cudaMemsetAsync(p, 0, n, stream), "zero accumulated gradients");
+    i = j;
+  }
+  return GSR_OK;
+}
+
+int gsr_backward_prepare(const gsr_bwd_args* args, void* stream_v) {
+  if (!args || args->P <= 0 || !args->dL_dmean2D || !args->dL_dconic || !args->dL_dopacity || !args->dL_dcolor)
+    return fail(GSR_ERR_INVALID, "gsr_backward_prepare: bad argument");
+  return zero_accumulators(*args, static_cast<cudaStream_t>(stream_v));
+}
+
 int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   if (!args) return fail(GSR_ERR_INVALID, "gsr_backward: null argument");
   const gsr_bwd_args& a = *args;
@@ -361,30 +394,8 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   const float focal_y = a.height / (2.0f * a.tan_fovy);
   const float focal_x = a.width / (2.0f * a.tan_fovx);
 
-  if (a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) {  // the four accumulated outputs start from zero
-    // adjacent arrays (one flat gradient buffer, as gs_livm_b200.engine lays them out) are cleared by one memset
-    struct Span {
-      char* p;
-      size_t n;
-    } spans[4] = {{reinterpret_cast<char*>(a.dL_dmean2D), 3 * (size_t)a.P * sizeof(float)},
-                  {reinterpret_cast<char*>(a.dL_dconic), 4 * (size_t)a.P * sizeof(float)},
-                  {reinterpret_cast<char*>(a.dL_dopacity), (size_t)a.P * sizeof(float)},
-                  {reinterpret_cast<char*>(a.dL_dcolor), 3 * (size_t)a.P * sizeof(float)}};
-    for (int i = 0; i < 4; ++i)
-      for (int j = i + 1; j < 4; ++j)
-        if (spans[j].p < spans[i].p) {
-          Span t = spans[i];
-          spans[i] = spans[j], spans[j] = t;
-        }
-    for (int i = 0; i < 4;) {
-      char* p = spans[i].p;
-      size_t n = spans[i].n;
-      int j = i + 1;
-      while (j < 4 && spans[j].p == p + n) n += spans[j++].n;
-      GSR_CUDA(cudaMemsetAsync(p, 0, n, stream), "zero accumulated gradients");
-      i = j;
-    }
-  }
+  if ((a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) && !(a.flags & GSR_BWD_ACCUMULATORS_ZEROED))
+    if (int st = zero_accumulators(a, stream)) return st;
   if (a.R > 0) {
     const BlendImpl impl = bwd_impl();
     auto fn = impl == kBlendSparse ? launch_blend_bwd_sparse : launch_blend_bwd;

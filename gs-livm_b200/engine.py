@@ -148,7 +148,20 @@ class RasterContext:
             self._capacity = 0 if bool((st[:, 3] == 2).any()) else int(st[:, 0].max().item() * 1.3) + 65536
         return ok
 
-    def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False) -> Dict[str, torch.Tensor]:
+    def prepare_backward(self) -> None:
+        """Clears the four gradient arrays the blend backward accumulates into (gsr_backward_prepare) on the current
+        stream. Independent of the forward: issue it on a side stream beside the forward, then call
+        backward(..., accumulators_zeroed=True)."""
+        g = self.grads
+        a = _lib.BwdArgs()
+        a.P = self.P
+        a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = g["dL_dmean2D"].data_ptr(), g["dL_dconic"].data_ptr(), g["dL_dopacity"].data_ptr()
+        a.dL_dcolor = g["dL_dcolor"].data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.gsr_backward_prepare(C.byref(a), stream), "gsr_backward_prepare")
+
+    def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False,
+                 accumulators_zeroed: bool = False) -> Dict[str, torch.Tensor]:
         """Gradients of the last forward. The reference's caller zero-fills all nine outputs before every
         backward (rasterize_points.cu:173-181); here the library is told they are uninitialised
         (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element itself, inside whatever region the caller is
@@ -169,7 +182,8 @@ class RasterContext:
         a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = g["dL_dmean2D"].data_ptr(), g["dL_dconic"].data_ptr(), g["dL_dopacity"].data_ptr()
         a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D = g["dL_dcolor"].data_ptr(), g["dL_dmean3D"].data_ptr(), g["dL_dcov3D"].data_ptr()
         a.dL_dsh, a.dL_dscale, a.dL_drot = g["dL_dsh"].data_ptr(), g["dL_dscale"].data_ptr(), g["dL_drot"].data_ptr()
-        a.debug, a.flags = int(debug), _lib.BWD_OUTPUTS_UNINITIALIZED
+        a.debug = int(debug)
+        a.flags = _lib.BWD_OUTPUTS_UNINITIALIZED | (_lib.BWD_ACCUMULATORS_ZEROED if accumulators_zeroed else 0)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.gsr_backward(C.byref(a), stream), "gsr_backward")
         return g
@@ -188,9 +202,15 @@ class RasterContext:
             raise RuntimeError("capture_step: the frame does not fit the presized binning arena")
         before = len(self._unchecked)
         graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
         with torch.cuda.graph(graph):
+            main = torch.cuda.current_stream(self.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):  # the 44 B/Gaussian of memsets the backward starts with run beside the forward
+                self.prepare_backward()
             self.forward(scene, cam)
-            self.backward(dL_dcolor, dL_dacc)
+            main.wait_stream(side)
+            self.backward(dL_dcolor, dL_dacc, accumulators_zeroed=True)
         slots = self._unchecked[before:]
         del self._unchecked[before:]
         return CapturedFrame(self, graph, slots, self._fwd_args, (scene, cam, dL_dcolor, dL_dacc))

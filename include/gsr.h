@@ -128,6 +128,9 @@ typedef struct gsr_bwd_args {
  * Gaussians with radii <= 0) and zero-fills the four accumulated ones (dL_dmean2D, dL_dconic, dL_dopacity,
  * dL_dcolor) itself on `stream`. Same results, 256 B per Gaussian less memset traffic. */
 #define GSR_BWD_OUTPUTS_UNINITIALIZED 1
+/* with the flag above: the caller already ran gsr_backward_prepare() on these outputs (e.g. on another stream, beside
+ * the forward), so gsr_backward() must not clear the accumulated arrays again */
+#define GSR_BWD_ACCUMULATORS_ZEROED 2
 
 /* Debug / parity view of the opaque buffers. Strides are in BYTES; count = number of elements. */
 typedef struct gsr_array_view {
@@ -202,6 +205,11 @@ GSR_API int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, ch
                                  char* image_buffer, void* stream, gsr_async_status* status);
 
 GSR_API int gsr_backward(const gsr_bwd_args* args, void* stream);
+/* Only the clearing of the four accumulated outputs (dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor: 44 B per
+ * Gaussian) that gsr_backward() does first under GSR_BWD_OUTPUTS_UNINITIALIZED. It does not depend on the forward, so a
+ * caller may issue it on a side stream while the forward runs and then pass GSR_BWD_ACCUMULATORS_ZEROED. Reads only
+ * P and the four pointers of `args`. */
+GSR_API int gsr_backward_prepare(const gsr_bwd_args* args, void* stream);
 
 /* Gradient exchange of the view-sharded keyframe window (no counterpart in the reference, which is single-GPU;
  * SURVEY.md 8e): all-reduce (sum, FP32) of the flat per-Gaussian parameter-gradient buffer, written against peer

@@ -195,6 +195,20 @@ def test_raster_context_matches_operator_and_reuses_memory(built_library, cuda_d
     times = ctx.stage_times()
     ctx.stage_timing(False)
     assert all(times[k] > 0 for k in ("preprocess", "sort", "blend_fwd", "blend_bwd", "geom_bwd"))
+    # the same forward + backward as ONE captured graph (the gradient memsets run beside the forward): replays give
+    # the eager results, also after the upstream gradients changed in place
+    dC, dS = case.dL_dcolor.to(dev).clone(), case.dL_dacc.to(dev).clone()
+    frame = ctx.capture_step(sc, cam, dC, dS)
+    for scale in (1.0, -0.5):
+        dC.copy_(case.dL_dcolor.to(dev) * scale)
+        dS.copy_(case.dL_dacc.to(dev) * scale)
+        ctx.grad_flat.fill_(float("nan"))  # every element must be rewritten by the replay
+        frame.replay()
+        torch.cuda.synchronize()
+        assert ctx.check()
+        np.testing.assert_array_equal(helpers.bits(ctx.out_color.cpu().numpy()), helpers.bits(raw["out_color"]))
+        for n in helpers.GRAD_NAMES:
+            assert_grad(n, ctx.grads[n].cpu().numpy().reshape(raw[n].shape), raw[n] * scale)
 
 
 def test_sync_free_forward_reports_a_frame_that_does_not_fit(built_library, cuda_device):
