@@ -92,6 +92,7 @@ class RasterContext:
         self.sync_free = bool(sync_free)
         self._capacity = 0  # instances the binning arena is carved for (0: not known yet)
         self._status = torch.zeros((16, 4), dtype=torch.int32).pin_memory()  # ring of gsr_async_status
+        self._status_np = self._status.numpy()  # same memory
         self._status_head = 0
         self._unchecked = []  # ring slots written since the last check()
 
@@ -139,13 +140,19 @@ class RasterContext:
         if not self._unchecked:
             return True
         torch.cuda.current_stream(self.device).synchronize()
-        st = self._status[self._unchecked]
-        self._unchecked = []
-        ok = bool((st[:, 3] == 0).all())
+        words = self._status_np  # numpy view of the pinned ring: no torch CPU ops between two GPU launches
+        ok, worst, too_long = True, 0, False
+        for slot in self._unchecked:
+            code = int(words[slot, 3])
+            if code != 0:
+                ok = False
+                worst = max(worst, int(words[slot, 0]))
+                too_long = too_long or code == 2
         if ok:
-            self.last_rendered = int(st[-1, 0])
+            self.last_rendered = int(words[self._unchecked[-1], 0])
         else:
-            self._capacity = 0 if bool((st[:, 3] == 2).any()) else int(st[:, 0].max().item() * 1.3) + 65536
+            self._capacity = 0 if too_long else int(worst * 1.3) + 65536
+        self._unchecked = []
         return ok
 
     def prepare_backward(self) -> None:

@@ -97,6 +97,7 @@ class RenderArena:
         self.capacity = 0
         self.param_grad_span = None  # after a backward: the contiguous span that holds the parameter gradients
         self._status = torch.zeros((16, 4), dtype=torch.int32).pin_memory()
+        self._status_np = self._status.numpy()  # same memory
         self._head = 0
         self._unchecked = []
 
@@ -131,11 +132,19 @@ class RenderArena:
         if not self._unchecked:
             return True
         torch.cuda.current_stream(self.device).synchronize()
-        st = self._status[self._unchecked]
+        # (numpy view of the pinned words: this runs once per step between two GPU launches, and a handful of torch
+        # CPU ops here cost more than the camera upload)
+        words = self._status_np
+        ok, worst, too_long = True, 0, False
+        for slot in self._unchecked:
+            code = int(words[slot, 3])
+            if code != 0:
+                ok = False
+                worst = max(worst, int(words[slot, 0]))
+                too_long = too_long or code == 2
         self._unchecked = []
-        ok = bool((st[:, 3] == 0).all())
         if not ok:
-            self.capacity = 0 if bool((st[:, 3] == 2).any()) else int(st[:, 0].max().item() * 1.3) + 65536
+            self.capacity = 0 if too_long else int(worst * 1.3) + 65536
         return ok
 
 
