@@ -187,36 +187,49 @@ struct TileSortArgs {
   uint32_t min_len, max_len;  // this launch handles lists with min_len < length <= max_len
 };
 
-// Stable LSD pass over bits [lo, lo + nbits) of `kin` (nbits <= 8): (kin, vin) -> (kout, vout).
+template <int kBits>
+struct DigitCount {
+  using type = uint32_t;
+};
+template <>
+struct DigitCount<9> {
+  using type = uint16_t;
+};
+
+// Stable LSD pass over bits [lo, lo + nbits) of `kin` (nbits <= kBits): (kin, vin) -> (kout, vout).
 // Every warp owns a contiguous chunk; ranks inside a chunk come from match_any peers, ranks across chunks
-// from the digit-major scan of the per-warp histograms.
-template <int kWarps>
+// from the digit-major scan of the per-warp histograms. The 1024-thread classes use 9-bit digits with 16-bit
+// counters (positions stay below kLargeCap < 65536): 27 depth bits in three passes instead of four, in the same
+// 32 KB of histograms.
+template <int kWarps, int kBits, typename Count>
 __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* vin, uint32_t* kout, uint32_t* vout,
-                                           int n, int lo, int nbits, bool by_val, uint32_t (*hist)[256],
+                                           int n, int lo, int nbits, bool by_val, Count (*hist)[1 << kBits],
                                            uint32_t* s_scan) {
+  constexpr int kDigits = 1 << kBits;
+  static_assert(kDigits <= kWarps * 32, "one thread per digit in the scan");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t dmask = (1u << nbits) - 1u;
   const int chunk = (((n + kWarps - 1) / kWarps) + 31) & ~31;
   const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
   const uint32_t* src = by_val ? vin : kin;
-  for (int i = tid; i < kWarps * 256; i += kWarps * 32) hist[0][i] = 0;
+  for (int i = tid; i < kWarps * kDigits; i += kWarps * 32) hist[0][i] = 0;
   __syncthreads();
   // count
   for (int i = beg + lane; i - lane < end; i += 32) {
     const bool valid = i < end;
     const uint32_t d = valid ? ((src[i] >> lo) & dmask) : 0xffffffffu;
     const uint32_t peers = __match_any_sync(kFull, d);
-    if (valid && lane == __ffs(peers) - 1) hist[warp][d] += __popc(peers);
+    if (valid && lane == __ffs(peers) - 1) hist[warp][d] = (Count)(hist[warp][d] + __popc(peers));
     __syncwarp();
   }
   __syncthreads();
   // digit-major exclusive scan: thread d walks the warps of digit d, then the digit totals are scanned
-  if (tid < 256) {
+  if (tid < kDigits) {
     uint32_t s = 0;
 #pragma unroll 4
     for (int w = 0; w < kWarps; ++w) {
       const uint32_t c = hist[w][tid];
-      hist[w][tid] = s;
+      hist[w][tid] = (Count)s;
       s += c;
     }
     uint32_t incl = s;
@@ -229,11 +242,11 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
     s_scan[32 + tid] = incl - s;  // exclusive inside the warp
   }
   __syncthreads();
-  if (tid < 256) {
+  if (tid < kDigits) {
     uint32_t base = s_scan[32 + tid];
-    for (int w = 0; w < warp; ++w) base += s_scan[w];  // warp < 8
+    for (int w = 0; w < warp; ++w) base += s_scan[w];  // warp < kDigits / 32
 #pragma unroll 4
-    for (int w = 0; w < kWarps; ++w) hist[w][tid] += base;
+    for (int w = 0; w < kWarps; ++w) hist[w][tid] = (Count)(hist[w][tid] + base);
   }
   __syncthreads();
   // scatter
@@ -246,7 +259,7 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
     uint32_t base = 0;
     if (valid && lane == leader) {
       base = hist[warp][d];
-      hist[warp][d] = base + __popc(peers);
+      hist[warp][d] = (Count)(base + __popc(peers));
     }
     base = __shfl_sync(kFull, base, leader);
     if (valid) {
@@ -265,12 +278,14 @@ __device__ __forceinline__ void radix_pass(const uint32_t* kin, const uint32_t* 
 template <int kCap, int kThreads, bool kGather>
 __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t tile, unsigned char* smem_raw) {
   constexpr int kWarps = kThreads / 32;
+  constexpr int kBits = kThreads >= 512 ? 9 : 8;  // digit width (see radix_pass)
+  using Count = typename DigitCount<kBits>::type;
   uint32_t* k0 = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* v0 = k0 + kCap;
   uint32_t* k1 = v0 + kCap;
   uint32_t* v1 = k1 + kCap;
-  uint32_t(*hist)[256] = reinterpret_cast<uint32_t(*)[256]>(v1 + kCap);
-  __shared__ uint32_t s_scan[32 + 256];
+  Count(*hist)[1 << kBits] = reinterpret_cast<Count(*)[1 << kBits]>(v1 + kCap);
+  __shared__ uint32_t s_scan[32 + (1 << kBits)];
   __shared__ uint32_t s_or_k, s_or_v, s_flag;
 
   const int tid = threadIdx.x;
@@ -302,10 +317,10 @@ __device__ __forceinline__ void sort_one_tile(const TileSortArgs& a, uint32_t ti
   auto sort_bits = [&](uint32_t diff, bool by_val) {  // LSD over the bits that differ inside the segment
     if (diff == 0) return;
     const int lo0 = __ffs(diff) - 1, hi = 32 - __clz(diff);
-    const int passes = (hi - lo0 + 7) / 8;
+    const int passes = (hi - lo0 + kBits - 1) / kBits;
     const int width = (hi - lo0 + passes - 1) / passes;
     for (int p = 0, lo = lo0; p < passes; ++p, lo += width) {
-      radix_pass<kWarps>(kc, vc, kn, vn, n, lo, min(width, hi - lo), by_val, hist, s_scan);
+      radix_pass<kWarps, kBits, Count>(kc, vc, kn, vn, n, lo, min(width, hi - lo), by_val, hist, s_scan);
       uint32_t* t = kc;
       kc = kn, kn = t;
       t = vc, vc = vn, vn = t;
@@ -456,7 +471,9 @@ __global__ void __launch_bounds__(kThreads) tile_sort_kernel(const TileSortArgs 
 }
 
 constexpr int kSmallThreads = 256, kLargeThreads = 1024;
-constexpr size_t sort_smem(int cap, int threads) { return (size_t)cap * 16 + (size_t)(threads / 32) * 256 * 4; }
+constexpr size_t sort_smem(int cap, int threads) {  // keys/ids ping-pong + per-warp histograms (sort_one_tile)
+  return (size_t)cap * 16 + (size_t)(threads / 32) * (threads >= 512 ? 512 * 2 : 256 * 4);
+}
 
 }  // namespace
 
