@@ -43,9 +43,9 @@ P_GAUSS = 1_000_000
 SH_DEGREE = 3
 SEED = 20241017 + 2
 WINDOW = 8
-MY_KERNELS_PER_STEP = 12  # preprocess, tile_scan, scatter_instances, tile_sort x3 (4096+, 2048.., short lists), gather_long x2, block_lists, blend_fwd, blend_bwd, geom_bwd
-LIB_KERNELS_PER_STEP = ("none on the per-tile binning path (cub scan + radix sort only when a tile list exceeds 12032 "
-                        "instances); cudaMemsetAsync: tile counters + the 4 accumulated gradient arrays (44 B/Gaussian)")
+MY_KERNELS_PER_STEP = 10  # preprocess, tile_scan, scatter_instances, partition_long, segment_sort x2 (depth buckets, short lists), block_lists, blend_fwd, blend_bwd, geom_bwd
+LIB_KERNELS_PER_STEP = ("none (cub only behind the parity-test knob sort_device); cudaMemsetAsync: tile counters + the "
+                        "4 accumulated gradient arrays (44 B/Gaussian)")
 
 
 # ----------------------------------------------------------------------------------------------------------

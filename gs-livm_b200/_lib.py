@@ -49,12 +49,16 @@ class BwdArgs(C.Structure):
 
 BWD_OUTPUTS_UNINITIALIZED = 1
 BWD_ACCUMULATORS_ZEROED = 2
-ABI_VERSION = 3  # include/gsr.h GSR_ABI_VERSION this binding was written against
+ABI_VERSION = 4  # include/gsr.h GSR_ABI_VERSION this binding was written against
 
 
 class WindowRows(C.Structure):
     _fields_ = [("union_words", C.c_void_p), ("first_float", C.c_size_t), ("n_rows", C.c_uint32),
                 ("floats_per_row", C.c_uint32)]
+
+
+class AdamGroup(C.Structure):
+    _fields_ = [("first", C.c_size_t), ("count", C.c_size_t), ("lr", C.c_float)]
 
 
 class ArrayView(C.Structure):
@@ -75,7 +79,7 @@ class BinningView(C.Structure):
 
 class ImageView(C.Structure):
     _fields_ = [(n, ArrayView) for n in ("accum_alpha", "n_contrib", "ranges", "tile_last", "tile_order", "block_count",
-                                         "last_group")]
+                                         "last_group", "summary")]
 
 
 class AsyncStatus(C.Structure):
@@ -104,10 +108,17 @@ SYMBOLS = {
     "gsr_window_allreduce_multimem_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsr_window_allreduce_p2p_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p]),
+    "gsr_image_loss_scratch_floats": (C.c_size_t, [C.c_int, C.c_int]),
+    "gsr_image_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "gsr_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamGroup), C.c_int, C.c_float,
+                                C.c_float, C.c_float, C.c_int, C.c_void_p]),
     "gsr_mark_visible": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_view_geom": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GeomView)]),
     "gsr_view_binning": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BinningView)]),
     "gsr_view_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ImageView)]),
+    "gsr_configure": (C.c_int, [C.c_char_p, C.c_int]),
+    "gsr_config_get": (C.c_int, [C.c_char_p, c_int_p]),
     "gsr_stage_timing_enable": (None, [C.c_int]),
     "gsr_stage_times": (C.c_int, [c_float_p, C.c_int]),
     "gsr_shim_set_stream": (None, [C.c_void_p]),
@@ -134,6 +145,13 @@ def load() -> C.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def configure(**knobs: int) -> None:
+    """gsr_configure for every keyword (include/gsr.h lists the knobs); a negative value restores the default."""
+    lib = load()
+    for name, value in knobs.items():
+        check(lib.gsr_configure(name.encode(), int(value)), "gsr_configure(%s)" % name)
 
 
 def check(status: int, where: str) -> None:

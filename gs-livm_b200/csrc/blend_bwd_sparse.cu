@@ -22,8 +22,6 @@
 //     blended nowhere in the block are never fetched.
 // The sums are the reference's sums in another order and association (as between two runs of the
 // reference itself): compared at 1e-4 relative, not bitwise.
-#include <cstdlib>
-
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -305,8 +303,6 @@ __global__ void __launch_bounds__(kWarps * 32) blend_bwd_sparse_kernel(const Bwd
 
 }  // namespace
 
-int blend_heavy_threshold(bool forward);  // blend_fwd_sparse.cu
-
 cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
                                     const float* background, const float* dL_dpix, const float* dL_dacc,
                                     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
@@ -314,25 +310,15 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
   const int grid_x = (width + kTile - 1) / kTile, grid_y = (height + kTile - 1) / kTile;
   const int tiles = grid_x * grid_y;
   constexpr int kSmem = (int)sizeof(WarpBuf) * kWarps;
-  static const int ilp = [] {
-    const char* e = getenv("GSR_BWD_ILP");  // tuning knob: pairs evaluated per lane per step, COARSE shape (1 or 2)
-    return e ? atoi(e) : 2;
-  }();
-  auto kernel = ilp == 1 ? blend_bwd_sparse_kernel<1> : blend_bwd_sparse_kernel<2>;
-  static bool configured[64][2] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !configured[dev][ilp == 1]) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) configured[dev][ilp == 1] = true;
-  }
+  const Tuning t = tuning();
+  auto kernel = t.bwd_ilp == 1 ? blend_bwd_sparse_kernel<1> : blend_bwd_sparse_kernel<2>;  // pairs per lane per step
+  if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem)) return e;
   BwdArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.point_list = b.vals;
   a.blist = b.blist, a.bdesc = img.bdesc;
   a.bhits = b.bhits, a.tail_hits = img.tail_hits, a.last_group = img.last_group;
   a.W = width, a.H = height, a.grid_x = grid_x;
-  a.heavy = blend_heavy_threshold(false);
+  a.heavy = t.heavy_bwd;
   a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;
   a.bg = background, a.final_T = img.final_T;
   a.dL_dpix = dL_dpix, a.dL_dacc = dL_dacc;

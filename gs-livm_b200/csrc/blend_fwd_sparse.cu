@@ -18,8 +18,6 @@
 // Pairs outside a box are pairs the reference `continue`s on, and the per-pair operation DAG (which
 // product is fused, order of accumulation) mirrors the reference's sm_100a SASS through explicit _rn
 // intrinsics, so C, D, S, final_T and n_contrib are bit-identical to blend_fwd.cu and to the reference.
-#include <cstdlib>
-
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -48,6 +46,7 @@ struct FwdArgs {
   const float* bg;
   float *out_color, *out_depth, *out_acc, *final_T;
   uint32_t *n_contrib, *tile_last;
+  unsigned long long* work;  // pairs blended, accumulated per warp (bench.py's executed-work figure)
 };
 
 // 32x32 bit transpose across the warp: lane = candidate, bit = pixel  ->  lane = pixel, bit = candidate
@@ -98,6 +97,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, cons
 
   float T = 1.0f, A = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;  // COARSE: D, R, G, B; FINE: acc0 = own channel
   uint32_t last_contributor = 0;
+  uint32_t n_hit = 0;  // this lane's blended pairs (FINE: slot 0 counts)
   bool done = !inside;
   int last_group = 0;  // 1 + group of this pixel's last contributor
   // FINE: which word of a parked record this lane's channel is (slot 0: depth, 1-3: r, g, b)
@@ -212,6 +212,7 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, cons
       }
     }
     if (slot == 0) {  // the backward walks exactly the blended pairs: word = pixel (bit order of the coverage masks)
+      n_hit += __popc(hm);
       uint32_t* dst = ((g + 1) * 32 <= cnt) ? hits + g * 32 : a.tail_hits + (size_t)(tile * 8 + block) * 32;
       dst[8 * by + bx] = hm;
     }
@@ -243,6 +244,8 @@ __device__ __forceinline__ void blend_block(const FwdArgs& a, WarpBuf& buf, cons
   }
   const uint32_t wmax = __reduce_max_sync(kFull, last_contributor);
   if (lane == 0 && wmax) atomicMax(&a.tile_last[tile], wmax);  // tile_last is zeroed by order_tiles
+  const uint32_t w_hit = __reduce_add_sync(kFull, n_hit);
+  if (lane == 0 && w_hit) atomicAdd(a.work, (unsigned long long)w_hit);
 }
 
 // grid = 4*fine_tiles FINE candidates (tile_order[b/4], two blocks b%4 per CTA) followed by `tiles` COARSE candidates;
@@ -268,13 +271,10 @@ __global__ void __launch_bounds__(kWarps * 32) blend_fwd_sparse_kernel(const Fwd
 
 }  // namespace
 
-// List length from which a tile's warps take the FINE shape. The hit masks and last_group the forward leaves are
-// laid out per pixel, independent of the shape, so the two kernels need not agree: the forward gains from FINE a
-// little earlier (3072) than the backward (4096), whose FINE warps also pay four phase-C passes per group.
-int blend_heavy_threshold(bool forward) {
-  const char* e = getenv("GSR_BLEND_HEAVY");  // tuning / test knob for both kernels, read per call
-  return e ? atoi(e) : (forward ? 3072 : 4096);
-}
+// List length from which a tile's warps take the FINE shape (Tuning::heavy_fwd / heavy_bwd). The hit masks and
+// last_group the forward leaves are laid out per pixel, independent of the shape, so the two kernels need not agree:
+// the forward gains from FINE a little earlier (3072) than the backward (4096), whose FINE warps also pay four
+// phase-C passes per group.
 
 cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img, const BinningState& b,
                                     const float* background, float* out_color, float* out_depth, float* out_acc,
@@ -286,14 +286,13 @@ cudaError_t launch_blend_fwd_sparse(int width, int height, const ImageState& img
   a.bdesc = img.bdesc, a.last_group = img.last_group;
   a.bhits = b.bhits, a.tail_hits = img.tail_hits;
   a.W = width, a.H = height, a.grid_x = grid_x;
-  a.heavy = blend_heavy_threshold(true);
+  const Tuning t = tuning();
+  a.heavy = t.heavy_fwd;
   a.fine_tiles = tiles < kFineCap ? tiles : kFineCap;  // only the longest kFineCap lists can be FINE
   a.bg = background, a.out_color = out_color, a.out_depth = out_depth, a.out_acc = out_acc;
   a.final_T = img.final_T, a.n_contrib = img.n_contrib, a.tile_last = img.tile_last;
-  static const int ilp = [] {
-    const char* e = getenv("GSR_FWD_ILP");  // tuning knob: alphas evaluated per lane per step, COARSE shape (1, 2 or 4)
-    return e ? atoi(e) : 4;
-  }();
+  a.work = reinterpret_cast<unsigned long long*>(img.summary + 8);
+  const int ilp = t.fwd_ilp;  // alphas evaluated per lane per step, COARSE shape (1, 2 or 4)
   const int grid = 4 * a.fine_tiles + tiles;
   if (ilp == 1) blend_fwd_sparse_kernel<1><<<grid, kWarps * 32, 0, s>>>(a);
   else if (ilp == 2) blend_fwd_sparse_kernel<2><<<grid, kWarps * 32, 0, s>>>(a);

@@ -29,6 +29,7 @@ struct BlockListArgs {
   uint2* blist;
   uint32_t* block_count;
   uint4* bdesc;
+  unsigned long long* work;  // (pixel, candidate) pairs inside the candidates' boxes: the alphas the blend evaluates
   int grid_x;
 };
 
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
   const int b_mine = lane & 7, w_lo = lane >> 3;  // this lane sums block b_mine over warps w_lo and w_lo + 4
 
   uint32_t run = 0;  // entries written so far to block (lane & 7), identical in every warp
+  uint32_t pairs = 0;  // this thread's share of the tile's (pixel, candidate) pairs
   const float4 none = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
   float4 q_next = (int)threadIdx.x < n ? src[threadIdx.x].q0 : none;
   for (int base = 0, it = 0; base < n; base += kWarps * 32, ++it) {
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
     block_masks(q, tx0, ty0, cov);
     uint32_t m[8];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) m[b] = __ballot_sync(kFull, cov[b] != 0);
+    for (int b = 0; b < 8; ++b) m[b] = __ballot_sync(kFull, cov[b] != 0), pairs += __popc(cov[b]);
     uint32_t* cnt = counts[it & 1];
     if (lane < 8) {
       uint32_t mine = m[0];
@@ -110,6 +112,8 @@ __global__ void __launch_bounds__(kWarps * 32) block_lists_kernel(const BlockLis
     run += total;
     // counts[it & 1] is rewritten two iterations from now, behind the next iteration's barrier
   }
+  pairs = __reduce_add_sync(kFull, pairs);
+  if (lane == 0 && pairs) atomicAdd(a.work, (unsigned long long)pairs);
   if (warp == 0 && lane < 8) {
     a.block_count[tile * 8 + lane] = run;
     a.bdesc[blockIdx.x * 8 + lane] = make_uint4(range.x, (uint32_t)n, run, (uint32_t)tile);
@@ -122,6 +126,7 @@ cudaError_t launch_block_lists(int tiles, const ImageState& img, const BinningSt
   BlockListArgs a;
   a.ranges = img.ranges, a.tile_order = img.tile_order, a.inst = b.inst, a.blist = b.blist;
   a.block_count = img.block_count, a.bdesc = img.bdesc, a.grid_x = grid_x;
+  a.work = reinterpret_cast<unsigned long long*>(img.summary + 6);
   block_lists_kernel<<<tiles, kWarps * 32, 0, s>>>(a);
   return cudaGetLastError();
 }

@@ -392,14 +392,7 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
   const int blocks = (f.P + kBlock - 1) / kBlock;
   if (a.vec_sh) {
     constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(geom_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-      if (e != cudaSuccess) return e;
-      if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(geom_bwd_kernel<true>), kSmem)) return e;
     geom_bwd_kernel<true><<<blocks, kBlock, kSmem, s>>>(a);
   } else {
     geom_bwd_kernel<false><<<blocks, kBlock, 0, s>>>(a);

@@ -2,11 +2,13 @@
 // error handling for one forward / backward. Mirrors the control flow of the reference's
 // CudaRasterizer::Rasterizer::forward/backward (src/cuda_rasterizer/rasterizer_impl.cu:181-457)
 // with our kernels; nothing here touches the CPU oracle and there is no fallback path.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "gsr_common.cuh"
 
@@ -69,6 +71,90 @@ struct StageScope {
     if (debug) GSR_CUDA(cudaStreamSynchronize(stream), what);                                     \
   } while (0)
 
+// ---- tuning knobs: atomics initialised once from the environment, changed with gsr_configure() ---------------
+namespace {
+struct Knob {
+  const char* name;
+  const char* env;
+  int def, lo, hi;
+  std::atomic<int> value;
+};
+enum { K_SORT_DEVICE, K_HEAVY_FWD, K_HEAVY_BWD, K_FWD_ILP, K_BWD_ILP, K_SPLIT, K_BUCKET, K_AR_GRID, K_COUNT };
+Knob g_knobs[K_COUNT] = {
+    {"sort_device", "GSR_SORT", 0, 0, 1, {0}},          {"heavy_fwd", "GSR_BLEND_HEAVY", 3072, 1, 1 << 30, {3072}},
+    {"heavy_bwd", "GSR_BLEND_HEAVY", 4096, 1, 1 << 30, {4096}}, {"fwd_ilp", "GSR_FWD_ILP", 4, 1, 4, {4}},
+    {"bwd_ilp", "GSR_BWD_ILP", 2, 1, 2, {2}},            {"split_len", "GSR_SORT_SPLIT", 2047, 255, kSegCap - 1, {2047}},
+    {"bucket_target", "GSR_SORT_BUCKET", 640, kMinBucketTarget, kSegCap, {640}},
+    {"ar_grid", "GSR_AR_GRID", 2, 1, 16, {2}},
+};
+std::once_flag g_knobs_once;
+
+int sanitize(int k, int v) {
+  v = v < g_knobs[k].lo ? g_knobs[k].lo : (v > g_knobs[k].hi ? g_knobs[k].hi : v);
+  if (k == K_SPLIT) {  // 2^j - 1: the long-list class must be a prefix of tile_order's log2 buckets
+    int p = 256;
+    while (p * 2 - 1 <= v) p *= 2;
+    v = p - 1;
+  }
+  return v;
+}
+
+void knobs_from_env() {
+  for (int k = 0; k < K_COUNT; ++k) {
+    const char* e = getenv(g_knobs[k].env);
+    if (!e || !*e) continue;
+    int v;
+    if (k == K_SORT_DEVICE) v = !strcmp(e, "device") ? 1 : 0;
+    else v = atoi(e);
+    g_knobs[k].value.store(sanitize(k, v), std::memory_order_relaxed);
+  }
+}
+int knob(int k) {
+  std::call_once(g_knobs_once, knobs_from_env);
+  return g_knobs[k].value.load(std::memory_order_relaxed);
+}
+}  // namespace
+
+Tuning tuning() {
+  Tuning t;
+  t.sort_device = knob(K_SORT_DEVICE);
+  t.heavy_fwd = knob(K_HEAVY_FWD), t.heavy_bwd = knob(K_HEAVY_BWD), t.fwd_ilp = knob(K_FWD_ILP), t.bwd_ilp = knob(K_BWD_ILP);
+  t.split_len = knob(K_SPLIT), t.bucket_target = knob(K_BUCKET), t.ar_grid = knob(K_AR_GRID);
+  return t;
+}
+
+// ---- per-device caches, one mutex (the forward runs on the mapping thread, the backward on an autograd worker) -----
+namespace {
+std::mutex g_dev_mutex;
+int g_sm_count[64] = {};
+struct SmemAttr {
+  const void* kernel;
+  int dev, bytes;
+};
+std::vector<SmemAttr> g_smem_attrs;
+}  // namespace
+
+int device_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (!g_sm_count[dev] && cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    g_sm_count[dev] = 148;
+  return g_sm_count[dev];
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  for (const SmemAttr& a : g_smem_attrs)
+    if (a.kernel == kernel && a.dev == dev && a.bytes >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) g_smem_attrs.push_back({kernel, dev, bytes});
+  return e;
+}
+
 GeomState carve_geom(char* chunk, int P) {
   GeomState g;
   carve(chunk, g.rec, (size_t)P);
@@ -91,7 +177,8 @@ ImageState carve_image(char* chunk, int width, int height) {
   carve(chunk, s.tile_last, tiles);
   carve(chunk, s.tile_order, tiles);
   carve(chunk, s.tile_count, tiles);
-  carve(chunk, s.summary, 4);
+  carve(chunk, s.bucket_base, tiles);
+  carve(chunk, s.summary, 12);
   carve(chunk, s.block_count, tiles * 8);
   carve(chunk, s.bdesc, tiles * 8);
   carve(chunk, s.last_group, N);
@@ -107,6 +194,8 @@ BinningState carve_binning(char* chunk, int R) {
   carve(chunk, b.keys, n);
   carve(chunk, b.vals_unsorted, n);
   carve(chunk, b.vals, n + 4);  // +16 B: blend_bwd bulk-copies ids from an aligned-down start
+  carve(chunk, b.vals_tmp, n);
+  carve(chunk, b.seg_desc, max_depth_buckets(n));
   carve(chunk, b.blist, 8 * n);
   carve(chunk, b.bhits, 8 * n);
   b.sort_temp_bytes = sort_temp_bytes(R);
@@ -121,12 +210,12 @@ static size_t required_bytes(F carve_fn) {
   return carve_fn() + kAlign;
 }
 
-// Four pinned words per host thread for the {R, longest list, #large lists} read-back (reference: blocking cudaMemcpy D2H,
-// rasterizer_impl.cu:277).
+// Eight pinned words per host thread for the {R, longest list, #long lists, -, #depth buckets} read-back (reference:
+// blocking cudaMemcpy D2H, rasterizer_impl.cu:277).
 static uint32_t* pinned_summary() {
   static thread_local uint32_t* p = nullptr;
   if (!p) {
-    if (cudaMallocHost(reinterpret_cast<void**>(&p), 4 * sizeof(uint32_t)) != cudaSuccess) p = nullptr;
+    if (cudaMallocHost(reinterpret_cast<void**>(&p), 8 * sizeof(uint32_t)) != cudaSuccess) p = nullptr;
   }
   return p;
 }
@@ -150,6 +239,27 @@ size_t gsr_sizeof(int which) {
     case 5: return sizeof(gsr_image_view);
     default: return 0;
   }
+}
+
+int gsr_configure(const char* name, int value) {
+  if (!name) return fail(GSR_ERR_INVALID, "gsr_configure: null knob name");
+  for (int k = 0; k < K_COUNT; ++k)
+    if (!strcmp(name, g_knobs[k].name)) {
+      (void)knob(k);  // the environment is read first, once; an explicit setting then wins
+      g_knobs[k].value.store(value < 0 ? g_knobs[k].def : sanitize(k, value), std::memory_order_relaxed);
+      return GSR_OK;
+    }
+  return fail(GSR_ERR_INVALID, "gsr_configure: unknown knob '%s'", name);
+}
+
+int gsr_config_get(const char* name, int* value) {
+  if (!name || !value) return fail(GSR_ERR_INVALID, "gsr_config_get: null argument");
+  for (int k = 0; k < K_COUNT; ++k)
+    if (!strcmp(name, g_knobs[k].name)) {
+      *value = knob(k);
+      return GSR_OK;
+    }
+  return fail(GSR_ERR_INVALID, "gsr_config_get: unknown knob '%s'", name);
 }
 
 void gsr_stage_timing_enable(int on) { t_timer.enabled = on != 0; }
@@ -206,31 +316,13 @@ static int validate_fwd(const gsr_fwd_args& a, const char* who) {
   return GSR_OK;
 }
 
-// Blend implementations: "sparse" (default; per-block candidate lists, blend_*_sparse.cu) and "warp" (lock-step
-// warps over the whole tile list, blend_fwd.cu / blend_bwd.cu; the round-1 kernels, kept for A/B). The sparse backward
-// needs the sparse forward's hit masks, so it is only taken when the forward was sparse as well.
-enum BlendImpl { kBlendSparse = 0, kBlendWarp = 1 };
-static BlendImpl blend_impl(const char* var) {
-  const char* e = getenv(var);
-  if (e && !strcmp(e, "warp")) return kBlendWarp;
-  return kBlendSparse;
-}
-// read per call (a getenv costs ~100 ns), so one process can compare the implementations (tests)
-static BlendImpl fwd_impl() { return blend_impl("GSR_FWD_IMPL"); }
-static BlendImpl bwd_impl() {
-  const BlendImpl v = blend_impl("GSR_BWD_IMPL");
-  return (v == kBlendSparse && fwd_impl() != kBlendSparse) ? kBlendWarp : v;
-}
-
 static int launch_blend_forward(const gsr_fwd_args& a, const ImageState& img, const BinningState& bin, int tiles,
                                 int grid_x, int debug, cudaStream_t stream) {
-  const BlendImpl impl = fwd_impl();
-  if (impl == kBlendSparse)
-    GSR_STAGE(GSR_STAGE_FINALIZE, launch_block_lists(tiles, img, bin, grid_x, stream), "block_lists", debug, stream);
-  auto fn = impl == kBlendSparse ? launch_blend_fwd_sparse : launch_blend_fwd;
+  GSR_STAGE(GSR_STAGE_FINALIZE, launch_block_lists(tiles, img, bin, grid_x, stream), "block_lists", debug, stream);
   GSR_STAGE(GSR_STAGE_BLEND_FWD,
-            fn(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc, stream), "blend_fwd",
-            debug, stream);
+            launch_blend_fwd_sparse(a.width, a.height, img, bin, a.background, a.out_color, a.out_depth, a.out_acc,
+                                    stream),
+            "blend_fwd", debug, stream);
   return GSR_OK;
 }
 
@@ -269,27 +361,27 @@ int gsr_forward(const gsr_fwd_args* args, gsr_alloc_fn geom_alloc, void* geom_ct
   // rasterizer_impl.cu:277)
   uint32_t* h_summary = pinned_summary();
   if (!h_summary) return fail(GSR_ERR_CUDA, "gsr_forward: cudaMallocHost failed");
-  GSR_CUDA(cudaMemcpyAsync(h_summary, img.summary, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream),
+  GSR_CUDA(cudaMemcpyAsync(h_summary, img.summary, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream),
            "read num_rendered");
   GSR_CUDA(cudaStreamSynchronize(stream), "read num_rendered");
   if (h_summary[0] > 0x7fffffffu) return fail(GSR_ERR_INVALID, "gsr_forward: instance count overflows int32");
   const int R = (int)h_summary[0];
-  const uint32_t longest = h_summary[1];
-  const int n_large = (int)h_summary[2];
+  const int n_long = (int)h_summary[2], n_buckets = (int)h_summary[4];
 
   char* bin_chunk = binning_alloc(binning_ctx, gsr_required_binning(R));
   if (!bin_chunk) return fail(GSR_ERR_ALLOC, "gsr_forward: binning allocator returned NULL");
   BinningState bin = carve_binning(bin_chunk, R);
 
   if (R > 0) {
-    const char* force = getenv("GSR_SORT");  // "device": always take the device-wide path (parity tests)
-    if (longest <= (uint32_t)kLargeCap && !(force && !strcmp(force, "device"))) {
-      // per-tile path: bucket by tile, sort every tile's segment inside one CTA (tile_sort.cu)
+    if (!tuning().sort_device) {
+      // per-tile path: bucket by tile, long lists cut into depth buckets, every segment sorted inside one CTA
+      // (tile_sort.cu); any list length
       GSR_STAGE(GSR_STAGE_DUPLICATE, launch_scatter_instances(a.P, geom, radii, img, bin, grid_x, grid_y, stream),
                 "scatter_instances", debug, stream);
-      GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, n_large, img, bin, geom, grid_x, stream), "tile_sort", debug,
-                stream);
+      GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, n_long, n_buckets, R, img, bin, geom, grid_x, stream),
+                "tile_sort", debug, stream);
     } else {
+      // (parity tests only: GSR_SORT=device / gsr_configure("sort_device", 1))
       // device-wide path, the reference's own sequence: scan -> duplicateWithKeys -> radix sort -> ranges
       GSR_STAGE(GSR_STAGE_DUPLICATE,
                 [&] {
@@ -336,7 +428,8 @@ int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, char* binn
              "copy status");
   GSR_STAGE(GSR_STAGE_DUPLICATE, launch_scatter_instances(a.P, geom, radii, img, bin, grid_x, grid_y, stream),
             "scatter_instances", debug, stream);
-  GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, -1, img, bin, geom, grid_x, stream), "tile_sort", debug, stream);
+  GSR_STAGE(GSR_STAGE_SORT, launch_tile_sort(tiles, -1, -1, R_capacity, img, bin, geom, grid_x, stream), "tile_sort",
+            debug, stream);
   return launch_blend_forward(a, img, bin, tiles, grid_x, debug, stream);
 }
 
@@ -397,11 +490,9 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   if ((a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) && !(a.flags & GSR_BWD_ACCUMULATORS_ZEROED))
     if (int st = zero_accumulators(a, stream)) return st;
   if (a.R > 0) {
-    const BlendImpl impl = bwd_impl();
-    auto fn = impl == kBlendSparse ? launch_blend_bwd_sparse : launch_blend_bwd;
     GSR_STAGE(GSR_STAGE_BLEND_BWD,
-              fn(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D, a.dL_dconic,
-                 a.dL_dopacity, a.dL_dcolor, stream),
+              launch_blend_bwd_sparse(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
+                                      a.dL_dconic, a.dL_dopacity, a.dL_dcolor, stream),
               "blend_bwd", debug, stream);
   }
   GSR_STAGE(GSR_STAGE_GEOM_BWD, launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);
@@ -464,6 +555,7 @@ int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* ou
   out->tile_order = view_of(s.tile_order, 4, tiles);
   out->block_count = view_of(s.block_count, 4, tiles * 8);
   out->last_group = view_of(s.last_group, 4, N);
+  out->summary = view_of(s.summary, 4, 12);
   return GSR_OK;
 }
 

@@ -46,7 +46,11 @@ struct ImageState {
   uint32_t* tile_last;  // [tiles] max n_contrib in the tile: where the backward starts
   uint32_t* tile_order; // [tiles] tile ids, longest instance lists first (launch order of the blend CTAs)
   uint32_t* tile_count; // [tiles] instances per tile (preprocess), then the tile's scatter cursor (tile_sort.cu)
-  uint32_t* summary;    // [4] {R, longest list, lists longer than kSmallMax, overflow code (sync-free forward)}
+  uint32_t* bucket_base; // [tiles] first depth-bucket descriptor of the tile's list, if it is a long one (tile_sort.cu)
+  uint32_t* summary;    // [12] {R, longest list, lists longer than split_len, overflow code (sync-free forward),
+                        //       depth buckets of the long lists, -, then two 64-bit work counters of the blend forward:
+                        //       [6,7] (pixel, candidate) pairs inside the candidates' boxes = alphas evaluated,
+                        //       [8,9] pairs blended = what the backward visits; [10,11] -}
   uint32_t* block_count;  // [tiles*8] candidates per 8x4 pixel block (block_lists.cu)
   uint4* bdesc;           // [tiles*8] by (position in tile_order, block): {range start, list length, candidates, tile} --
                           //           one load tells a blend warp everything it needs to find its list
@@ -54,10 +58,22 @@ struct ImageState {
   uint32_t* tail_hits;    // [tiles*8][32] hit masks of each block's last, partial group (see BinningState::bhits)
 };
 
-// tile_sort.cu: lists up to kSmallMax instances are sorted by a 256-thread CTA (kSmallCap slots of shared
-// memory), lists up to kLargeCap by a 1024-thread CTA; a frame with a longer list takes the device-wide sort.
-constexpr int kSmallCap = 2048, kSmallMax = kSmallCap - 1;  // kSmallMax + 1 is a power of two: see tile_order
-constexpr int kLargeCap = 12032;  // 12032 x 16 B of keys/values + 32 warps x 1 KB of histograms = 220 KB
+// tile_sort.cu: a segment (a whole short list, or one depth bucket of a long list) of up to kSegCap instances is
+// sorted by a 256-thread CTA in shared memory. Lists longer than Tuning::split_len (2^k - 1 <= kSegCap - 1: the class
+// boundary then coincides with tile_order's buckets) are first cut into depth buckets of ~Tuning::bucket_target
+// instances, at most kMaxBuckets per list. No list-length ceiling: work is linear in the length.
+constexpr int kSegCap = 2048;
+constexpr int kMaxBuckets = 256;
+constexpr int kMinBucketTarget = 256;
+// depth buckets a list of n instances is cut into (0: sorted whole); shared by tile_scan and partition_long
+__host__ __device__ inline uint32_t bucket_count(uint32_t n, uint32_t split_len, uint32_t target) {
+  if (n <= split_len) return 0u;
+  const uint32_t k = (n + target - 1u) / target;
+  return k < (uint32_t)kMaxBuckets ? k : (uint32_t)kMaxBuckets;
+}
+// upper bound of the number of depth buckets of a frame with R instances: a long list has more than
+// split_len >= kMinBucketTarget - 1 instances and at most n / target + 1 <= 2 n / kMinBucketTarget buckets
+inline size_t max_depth_buckets(size_t R) { return 2 * R / kMinBucketTarget + 1; }
 
 struct BinningState {
   uint64_t* keys_unsorted;  // [R]
@@ -70,6 +86,9 @@ struct BinningState {
   uint32_t* bhits;          // [8R] same indexing: word 32g + p of a block = which candidates of the block's group g
                             //      were blended into pixel p (bit 8*row + col order) by the forward; the backward walks
                             //      exactly those pairs. A last group of fewer than 32 candidates lives in tail_hits.
+  uint32_t* vals_tmp;       // [R] ids of the long lists after the depth partition (their depths: second half of
+                            //     keys_unsorted, which holds 32-bit depth words on the per-tile path)
+  uint4* seg_desc;          // [max_depth_buckets(R)] {first instance, instances, tile, -} per depth bucket
   char* sort_temp;
   size_t sort_temp_bytes;
 };
@@ -107,8 +126,9 @@ cudaError_t launch_finalize_binning(int R, const BinningState& b, const GeomStat
 cudaError_t launch_tile_scan(int tiles, const ImageState& img, uint32_t r_cap, cudaStream_t s);
 cudaError_t launch_scatter_instances(int P, const GeomState& g, const int* radii, const ImageState& img,
                                      const BinningState& b, int grid_x, int grid_y, cudaStream_t s);
-cudaError_t launch_tile_sort(int tiles, int n_large, const ImageState& img, const BinningState& b, const GeomState& g,
-                             int grid_x, cudaStream_t s);
+// n_long / n_buckets < 0: not known on the host (sync-free forward); r_cap = instances the binning state is carved for
+cudaError_t launch_tile_sort(int tiles, int n_long, int n_buckets, int r_cap, const ImageState& img,
+                             const BinningState& b, const GeomState& g, int grid_x, cudaStream_t s);
 cudaError_t launch_order_tiles(int tiles, const uint2* ranges, uint32_t* tile_order, uint32_t* tile_last,
                                cudaStream_t s);
 cudaError_t launch_block_lists(int tiles, const ImageState& img, const BinningState& b, int grid_x, cudaStream_t s);
@@ -119,16 +139,27 @@ cudaError_t launch_blend_bwd_sparse(int width, int height, const ImageState& img
                                     const float* background, const float* dL_dpix, const float* dL_dacc,
                                     float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
                                     cudaStream_t s);
-cudaError_t launch_blend_fwd(int width, int height, const ImageState& img, const BinningState& b,
-                             const float* background, float* out_color, float* out_depth, float* out_acc,
-                             cudaStream_t s);
-cudaError_t launch_blend_bwd(int width, int height, const ImageState& img, const BinningState& b,
-                             const float* background, const float* dL_dpix, const float* dL_dacc, float* dL_dmean2D,
-                             float* dL_dconic, float* dL_dopacity, float* dL_dcolor, cudaStream_t s);
 cudaError_t launch_geom_bwd(const gsr_bwd_args& a, const GeomState& g, const int* radii, float focal_x, float focal_y,
                             cudaStream_t s);
 
 uint32_t higher_msb(uint32_t n);  // reference getHigherMsb, rasterizer_impl.cu:35-48
+
+// ---- process-wide tuning / A-B knobs (gsr_configure; initial values from the environment, read ONCE) ----------
+struct Tuning {
+  int sort_device;    // 1 = always the device-wide binning path (the reference's sequence)     GSR_SORT=device
+  int heavy_fwd;      // list length from which a tile's blend warps take the FINE shape         GSR_BLEND_HEAVY
+  int heavy_bwd;
+  int fwd_ilp;        // pairs evaluated per lane per step, COARSE shape                         GSR_FWD_ILP
+  int bwd_ilp;        //                                                                         GSR_BWD_ILP
+  int split_len;      // lists longer than this are cut into depth buckets (2^k - 1)             GSR_SORT_SPLIT
+  int bucket_target;  // instances per depth bucket                                              GSR_SORT_BUCKET
+  int ar_grid;        // CTAs per SM of the window exchange kernels                              GSR_AR_GRID
+};
+Tuning tuning();  // snapshot (each field is read atomically)
+
+// per-device caches behind one mutex (forward on the mapping thread, backward on an autograd worker: SURVEY 8b)
+int device_sm_count();                                            // of the current device
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);   // cudaFuncSetAttribute once per (kernel, device)
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

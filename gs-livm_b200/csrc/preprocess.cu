@@ -100,6 +100,7 @@ __device__ __forceinline__ void eval_sh(int deg, float3 dir, Load sh, float out[
 
 constexpr int kBlock = 64;  // Gaussians per CTA: many small CTAs per SM interleave staging, math and SH phases better than three big ones
 constexpr int kShRow = 13;  // float4 per staged SH row: 12 used + 1 pad, so lane-strided LDS.128 are conflict-free
+constexpr uint32_t kTileSlotBits = 8, kTileSlots = 1u << kTileSlotBits, kTileProbes = 8;
 
 // kVec16: M == 16 and shs 16-byte aligned. The 192-byte SH rows of the block's SURVIVING Gaussians are staged
 // into shared memory with coalesced 16-byte cp.async (LDGSTS) transfers and read back row-wise; rows of culled
@@ -110,9 +111,11 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
   __shared__ __align__(16) float s_means[kBlock * 3];
   __shared__ __align__(16) float s_scales[kBlock * 3];
   __shared__ uint8_t s_survive[kBlock];
+  __shared__ uint32_t s_tile_key[kTileSlots], s_tile_cnt[kTileSlots];  // per-CTA tile -> instance count (see below)
   extern __shared__ __align__(16) float4 s_sh[];  // [kBlock][kShRow] when kVec16
 
   const int tid = threadIdx.x;
+  for (int i = tid; i < (int)kTileSlots; i += kBlock) s_tile_key[i] = 0xffffffffu, s_tile_cnt[i] = 0u;
   const int base = blockIdx.x * kBlock;
   const int n = min(kBlock, a.P - base);
   for (int i = tid; i < 35; i += kBlock) {  // the camera: 16 + 16 + 3 floats
@@ -327,19 +330,30 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
     survive = true;
   } while (false);
 
-  // Instances per tile (tile_sort.cu). Neighbouring Gaussians mostly fall into the same tile, and L2 serialises
-  // atomics to one address (~15 ns each across warps): lanes that hit the same tile are merged with match_any
-  // and only their leader issues the RED.
+  // Instances per tile (tile_sort.cu). The Gaussians of a CTA are neighbours in the map and fall into a few dozen
+  // tiles, and L2 serialises atomics to one address: the CTA counts per tile in a small shared-memory hash table
+  // (shared-memory atomics cost ~4 SM-cycles per warp; merging lanes with MATCH.ANY costs ~58 and was a third of
+  // this kernel's time) and sends ONE global atomic per tile it touched. A tile that finds no slot within kProbes
+  // probes is counted in global memory directly.
   {
-    const uint32_t most = __reduce_max_sync(0xffffffffu, out_tiles);
-    for (uint32_t k = 0; k < most; ++k) {
-      uint32_t t = 0xffffffffu;
-      if (k < out_tiles) {
-        const int ry = (int)k / rect_w;
-        t = (uint32_t)((rect_y0 + ry) * a.grid_x + rect_x0 + ((int)k - ry * rect_w));
+    for (uint32_t k = 0; k < out_tiles; ++k) {
+      const int ry = (int)k / rect_w;
+      const uint32_t t = (uint32_t)((rect_y0 + ry) * a.grid_x + rect_x0 + ((int)k - ry * rect_w));
+      uint32_t slot = (t * 2654435761u) >> (32 - kTileSlotBits);
+      bool counted = false;
+      for (uint32_t pr = 0; pr < kTileProbes && !counted; ++pr, slot = (slot + 1) & (kTileSlots - 1)) {
+        const uint32_t seen = atomicCAS(&s_tile_key[slot], 0xffffffffu, t);
+        if (seen == 0xffffffffu || seen == t) {
+          atomicAdd(&s_tile_cnt[slot], 1u);
+          counted = true;
+        }
       }
-      const uint32_t peers = __match_any_sync(0xffffffffu, t);
-      if (t != 0xffffffffu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&a.tile_count[t], (uint32_t)__popc(peers));
+      if (!counted) atomicAdd(&a.tile_count[t], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < kTileSlots; i += kBlock) {
+      const uint32_t c = s_tile_cnt[i];
+      if (c) atomicAdd(&a.tile_count[s_tile_key[i]], c);
     }
   }
 
@@ -437,14 +451,7 @@ cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int
   const bool vec16 = !f.colors_precomp && f.M == 16 && al16(f.shs);
   if (vec16) {
     constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(preprocess_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-      if (e != cudaSuccess) return e;
-      if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_fwd_kernel<true>), kSmem)) return e;
     preprocess_fwd_kernel<true><<<blocks, kBlock, kSmem, s>>>(a);
   } else {
     preprocess_fwd_kernel<false><<<blocks, kBlock, 0, s>>>(a);

@@ -16,8 +16,6 @@
 //    with plain peer loads) and all-gather (rank r copies the other reduced slices from their owners).
 // Both need every rank's gradients complete before, and every rank's stores complete after: the caller brackets
 // the kernels with the symmetric-memory barrier (gs_livm_b200/window.py), enqueued on the same stream.
-#include <cstdlib>
-
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -169,16 +167,7 @@ __global__ void __launch_bounds__(256) union_words_kernel(PeerWords peers, int n
   out[w] = u;
 }
 
-int grid_for(int dev) {
-  static int sms[64] = {};
-  if (dev < 0 || dev >= 64) return 148 * 2;
-  if (!sms[dev] && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
-  static const int mult = [] {
-    const char* e = getenv("GSR_AR_GRID");  // tuning knob: CTAs per SM of the exchange kernels
-    return e ? atoi(e) : 2;
-  }();
-  return sms[dev] * (mult > 0 ? mult : 2);
-}
+int grid_for(int /*dev*/) { return device_sm_count() * tuning().ar_grid; }  // CTAs per SM: Tuning::ar_grid
 
 }  // namespace
 }  // namespace gsr

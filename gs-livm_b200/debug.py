@@ -66,4 +66,13 @@ def image_state(imgBuffer: torch.Tensor, width: int, height: int) -> Dict[str, t
         tile_order=_typed(imgBuffer, v.tile_order, torch.int32, 1)[:, 0],
         block_count=_typed(imgBuffer, v.block_count, torch.int32, 1)[:, 0],
         last_group=_typed(imgBuffer, v.last_group, torch.int32, 1)[:, 0],
+        summary=_typed(imgBuffer, v.summary, torch.int32, 1)[:, 0],
     )
+
+
+def frame_counters(imgBuffer: torch.Tensor, width: int, height: int) -> Dict[str, int]:
+    """The per-frame counters the kernels leave in the image state: instance count, list statistics and the blend's
+    executed work (pairs inside the candidates' boxes = alphas evaluated; pairs blended = what the backward visits)."""
+    w = [int(x) & 0xffffffff for x in image_state(imgBuffer, width, height)["summary"].cpu().tolist()]
+    return dict(num_rendered=w[0], longest_list=w[1], long_lists=w[2], overflow=w[3], depth_buckets=w[4],
+                pairs_in_boxes=w[6] | (w[7] << 32), pairs_blended=w[8] | (w[9] << 32))

@@ -141,17 +141,15 @@ class RasterContext:
             return True
         torch.cuda.current_stream(self.device).synchronize()
         words = self._status_np  # numpy view of the pinned ring: no torch CPU ops between two GPU launches
-        ok, worst, too_long = True, 0, False
+        ok, worst = True, 0
         for slot in self._unchecked:
-            code = int(words[slot, 3])
-            if code != 0:
+            if int(words[slot, 3]) != 0:  # the frame had more instances than the arena was carved for
                 ok = False
                 worst = max(worst, int(words[slot, 0]))
-                too_long = too_long or code == 2
         if ok:
             self.last_rendered = int(words[self._unchecked[-1], 0])
         else:
-            self._capacity = 0 if too_long else int(worst * 1.3) + 65536
+            self._capacity = int(worst * 1.3) + 65536
         self._unchecked = []
         return ok
 

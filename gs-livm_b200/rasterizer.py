@@ -135,16 +135,14 @@ class RenderArena:
         # (numpy view of the pinned words: this runs once per step between two GPU launches, and a handful of torch
         # CPU ops here cost more than the camera upload)
         words = self._status_np
-        ok, worst, too_long = True, 0, False
+        ok, worst = True, 0
         for slot in self._unchecked:
-            code = int(words[slot, 3])
-            if code != 0:
+            if int(words[slot, 3]) != 0:  # the frame had more instances than the arena was carved for
                 ok = False
                 worst = max(worst, int(words[slot, 0]))
-                too_long = too_long or code == 2
         self._unchecked = []
         if not ok:
-            self.capacity = 0 if too_long else int(worst * 1.3) + 65536
+            self.capacity = int(worst * 1.3) + 65536
         return ok
 
 

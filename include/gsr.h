@@ -44,7 +44,7 @@ extern "C" {
 #define GSR_API
 #endif
 
-#define GSR_ABI_VERSION 3
+#define GSR_ABI_VERSION 4
 #define GSR_NUM_CHANNELS 3 /* NUM_CHANNELS, include/gs/cuda_rasterizer/config.h:15 */
 #define GSR_BLOCK_X 16     /* BLOCK_X, config.h:16 */
 #define GSR_BLOCK_Y 16     /* BLOCK_Y, config.h:17 */
@@ -168,6 +168,8 @@ typedef struct gsr_image_view {
   gsr_array_view tile_order;  /* uint32 per tile: launch order, longest lists first (ours) */
   gsr_array_view block_count; /* uint32 per 8x4 pixel block (8 per tile): candidates in the block's list (ours) */
   gsr_array_view last_group;  /* uint32 per pixel: 1 + group of 32 candidates of the pixel's last contributor (ours) */
+  gsr_array_view summary;     /* 12 x uint32 per frame: {R, longest list, long lists, overflow, depth buckets, -,
+                                 u64 pairs inside boxes (alphas evaluated), u64 pairs blended, -, -} (ours) */
 } gsr_image_view;
 
 GSR_API int gsr_abi_version(void);
@@ -192,14 +194,14 @@ GSR_API int gsr_forward(const gsr_fwd_args* args,
  * binning of gsr_required_binning(R_capacity) bytes — and nothing waits for the GPU: every kernel reads what it
  * needs from device memory. `status` (pinned host memory, may be NULL) receives the counters through an
  * asynchronous copy on `stream`; it is valid once the caller has synchronised with the stream for its own
- * reasons (e.g. to read the loss). If status->overflow != 0 the frame did not fit (1: R > R_capacity, 2: a tile
- * list longer than the per-tile sort handles) and the outputs are those of an EMPTY scene: redo the frame with
- * gsr_forward. The matching gsr_backward takes R = R_capacity and the same three buffers. */
+ * reasons (e.g. to read the loss). If status->overflow != 0 the frame did not fit (R > R_capacity; there is no
+ * limit on the length of a tile's list) and the outputs are those of an EMPTY scene: redo the frame with
+ * gsr_forward, or with a larger buffer. The matching gsr_backward takes R = R_capacity and the same three buffers. */
 typedef struct gsr_async_status {
   uint32_t num_rendered; /* R */
   uint32_t longest_list;
-  uint32_t long_lists;
-  uint32_t overflow;
+  uint32_t long_lists;   /* tile lists cut into depth buckets before sorting (longer than the split_len knob) */
+  uint32_t overflow;     /* 0, or 1: R > R_capacity */
 } gsr_async_status;
 GSR_API int gsr_forward_presized(const gsr_fwd_args* args, char* geom_buffer, char* binning_buffer, int R_capacity,
                                  char* image_buffer, void* stream, gsr_async_status* status);
@@ -246,12 +248,49 @@ GSR_API int gsr_window_allreduce_multimem_rows(void* multicast_buffer, size_t n_
 GSR_API int gsr_window_allreduce_p2p_rows(void* const* peer_buffers, size_t n_floats, int rank, int world, int phase,
                                           const gsr_window_rows* rows, void* stream);
 
+/* The two GPU steps right behind the rasterizer in GS-LIVM's mapping iteration, fused.
+ *
+ * gsr_image_loss <- gaussian_splatting::l1_loss + ssim and their combination (include/gs/gs/loss_utils.cuh:11-70,
+ *   src/liw/lioOptimization.cpp:1729-1734): loss = (1 - lambda) mean|image - target| + lambda (1 - mean(SSIM map)), with
+ *   the reference's own 11x11 window (loss_utils.cuh:24-30, NOT the textbook one) and zero padding, forward and backward
+ *   in one call: dL_dimage [3,H,W] is what gsr_backward takes as dL_dpix. loss_out (device) receives
+ *   {loss, mean|image - target|, mean(SSIM map)}; scratch = gsr_image_loss_scratch_floats(W, H) floats of device memory.
+ *   lambda_dssim == 0: plain L1 in one pass.
+ * gsr_adam_step <- torch::optim::Adam::step as GaussianModel::Training_setup sets it up (src/gs/gaussian.cu:396-428): no
+ *   weight decay, no amsgrad; `groups` (host array, <= 8) are element ranges of the flat params / grads / exp_avg /
+ *   exp_avg_sq buffers with their learning rates; `step` is the 1-based step count (bias correction). */
+typedef struct gsr_adam_group {
+  size_t first, count; /* element range [first, first + count) */
+  float lr;
+} gsr_adam_group;
+GSR_API size_t gsr_image_loss_scratch_floats(int width, int height);
+GSR_API int gsr_image_loss(const float* image, const float* target, int width, int height, float lambda_dssim,
+                           float* dL_dimage, float* loss_out, float* scratch, void* stream);
+GSR_API int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                          const gsr_adam_group* groups, int n_groups, float beta1, float beta2, float eps, int step,
+                          void* stream);
+
 GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present, void* stream);
 
 GSR_API int gsr_view_geom(char* geom_buffer, int P, gsr_geom_view* out);
 GSR_API int gsr_view_binning(char* binning_buffer, int R, gsr_binning_view* out);
 GSR_API int gsr_view_image(char* image_buffer, int width, int height, gsr_image_view* out);
+
+/* Process-wide tuning / A-B knobs (no counterpart in the reference). Initial values come from the environment, read
+ * ONCE on first use; gsr_configure() overrides them at any time (value < 0: back to the built-in default), takes
+ * effect from the next forward / backward, and is thread-safe. Knobs (environment variable):
+ *   "sort_device"   (GSR_SORT=device)   1: always bin with the reference's own sequence scan -> duplicateWithKeys ->
+ *                                       device-wide radix sort -> ranges (parity tests of the intermediate arrays)
+ *   "heavy_fwd", "heavy_bwd" (GSR_BLEND_HEAVY, both)  list length from which a tile's blend warps use four lanes per
+ *                                       pixel; defaults 3072 / 4096
+ *   "fwd_ilp" (GSR_FWD_ILP) 1|2|4, "bwd_ilp" (GSR_BWD_ILP) 1|2   pairs evaluated per lane per step
+ *   "split_len" (GSR_SORT_SPLIT)        tile lists longer than this (rounded to 2^k - 1, 255..2047) are cut into depth
+ *                                       buckets before sorting; "bucket_target" (GSR_SORT_BUCKET) instances per bucket
+ *   "ar_grid" (GSR_AR_GRID)             CTAs per SM of the window exchange kernels
+ * Returns GSR_ERR_INVALID for an unknown knob. */
+GSR_API int gsr_configure(const char* knob, int value);
+GSR_API int gsr_config_get(const char* knob, int* value);
 
 /* Optional per-stage device timing (CUDA events recorded on the launch stream around each stage of the
  * last forward/backward on the calling thread); used by bench.py for the roofline figures. */

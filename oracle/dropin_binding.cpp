@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "gs/rasterizer.cuh"
+#include "operator_session.h"
 
 namespace {
 
@@ -55,4 +56,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "GS-LIVM's unchanged operator files linked against libgsr_b200.so (test infrastructure)";
   // the LibTorch autograd engine must not be entered with the Python GIL held
   m.def("render_and_backward", &render_and_backward, pybind11::call_guard<pybind11::gil_scoped_release>());
+  gsr_session::bind(m);  // persistent session for bench.py's e2e_dropin (oracle/operator_session.h)
 }

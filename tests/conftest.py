@@ -21,13 +21,13 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def built_library():
-    """Build (if stale) and load libgsr_b200.so. Loading does not need a GPU."""
+    """Build (incrementally: only what is older than its sources) and load libgsr_b200.so, so that a stale prebuilt
+    binary shipped with the snapshot is never what gets tested. Loading does not need a GPU."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("gsr_build", os.path.join(ROOT, "gs-livm_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    if not os.path.exists(mod.LIB):
-        mod.build()
+    mod.build()
     import gs_livm_b200  # noqa: F401
     from gs_livm_b200 import _lib
     return _lib.load()

@@ -82,11 +82,13 @@ def run_oracle_cpu(case: Case, backward: bool = True, nthreads: int = 4) -> Dict
 
 # ------------------------------------------------------------------------------------------------ ours
 SORT_PATHS = ("tile", "device")
-# blend implementations of the library: the pair-sparse kernels with their default warp shapes, the same with the
-# FINE shape (four lanes per pixel) forced on every tile, and the round-1 lock-step kernels
-BLENDS = ("sparse", "sparse-fine", "warp")
-_BLEND_ENV = {"sparse": {}, "sparse-fine": {"GSR_BLEND_HEAVY": "1"},
-              "warp": {"GSR_FWD_IMPL": "warp", "GSR_BWD_IMPL": "warp"}}
+# blend / sort variants of the library (gsr_configure knobs): the pair-sparse kernels with their default warp shapes,
+# the same with the FINE shape (four lanes per pixel) forced on every tile, and the defaults with every list longer
+# than 255 instances cut into small depth buckets (the long-list path of tile_sort.cu on small scenes)
+BLENDS = ("sparse", "sparse-fine", "small-buckets")
+_BLEND_KNOBS = {"sparse": {}, "sparse-fine": {"heavy_fwd": 1, "heavy_bwd": 1},
+                "small-buckets": {"split_len": 255, "bucket_target": 256}}
+_ALL_KNOBS = ("sort_device", "heavy_fwd", "heavy_bwd", "split_len", "bucket_target")
 
 
 def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile", blend: str = "sparse") -> Dict[str, np.ndarray]:
@@ -96,14 +98,9 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile", bl
     "device": the reference's own sequence scan -> duplicateWithKeys -> device-wide radix sort -> ranges, which
     also leaves the reference's intermediate arrays (point_offsets, unsorted keys/values) behind."""
     import gs_livm_b200  # noqa: F401
-    from gs_livm_b200 import debug, rasterizer
-    if sort_path == "device":
-        os.environ["GSR_SORT"] = "device"
-    else:
-        os.environ.pop("GSR_SORT", None)
-    for k in ("GSR_BLEND_HEAVY", "GSR_FWD_IMPL", "GSR_BWD_IMPL"):
-        os.environ.pop(k, None)
-    os.environ.update(_BLEND_ENV[blend])
+    from gs_livm_b200 import _lib, debug, rasterizer
+    _lib.configure(**{k: -1 for k in _ALL_KNOBS})
+    _lib.configure(sort_device=1 if sort_path == "device" else 0, **_BLEND_KNOBS[blend])
     d = lambda t: torch.empty(0, device=dev) if t is None else t.to(dev)  # noqa: E731
     shs = None if case.use_colors else case.shs
     bg, m3, sc, rot, op = d(case.background), d(case.means3D), d(case.scales), d(case.rotations), d(case.opacities)
@@ -113,7 +110,6 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile", bl
         bg, m3, col, op, sc, rot, 1.0, cov, view, proj, case.tanfovx, case.tanfovy,
         case.height, case.width, sh, case.sh_degree, cam, False, False)
     g, b, im = debug.geom_state(gb, case.P), debug.binning_state(bb, R), debug.image_state(ib, case.width, case.height)
-    os.environ.pop("GSR_SORT", None)
     out = dict(sort_path=sort_path, num_rendered=R, out_color=color, out_depth=depth, out_acc=acc, radii=radii, depths=g["depths"],
                means2D=g["means2D"], conic_opacity=g["conic_opacity"], rgb=g["rgb"], clamped_bits=g["clamped"],
                tiles_touched=g["tiles_touched"], point_offsets=g["point_offsets"], extent=g["extent"],
@@ -126,8 +122,7 @@ def run_ours(case: Case, dev, backward: bool = True, sort_path: str = "tile", bl
             d(case.dL_dcolor), d(case.dL_dacc), sh, case.sh_degree, cam, gb, R, bb, ib, False)
         out.update(dict(zip(GRAD_NAMES, grads)))
     torch.cuda.synchronize()
-    for k in _BLEND_ENV[blend]:
-        os.environ.pop(k, None)
+    _lib.configure(**{k: -1 for k in _ALL_KNOBS})
     return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 

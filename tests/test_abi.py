@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built_library):
         assert hasattr(built_library, name), f"{name} declared in include/gsr.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in _lib.SYMBOLS"
     from gs_livm_b200 import _lib
-    assert built_library.gsr_abi_version() == _lib.ABI_VERSION == 3
+    assert built_library.gsr_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_ctypes_struct_layout_matches_the_library(built_library):
@@ -88,3 +88,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(ImportError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_configure_knobs_round_trip_without_a_gpu(built_library):
+    """gsr_configure / gsr_config_get (host-only state): values are clamped, split_len is rounded to 2^k - 1, a
+    negative value restores the default, an unknown knob is an error."""
+    lib = built_library
+    got = C.c_int(0)
+    assert lib.gsr_config_get(b"split_len", C.byref(got)) == 0 and got.value == 2047
+    assert lib.gsr_configure(b"split_len", 1500) == 0
+    assert lib.gsr_config_get(b"split_len", C.byref(got)) == 0 and got.value == 1023
+    assert lib.gsr_configure(b"split_len", 1) == 0
+    assert lib.gsr_config_get(b"split_len", C.byref(got)) == 0 and got.value == 255
+    assert lib.gsr_configure(b"split_len", -1) == 0
+    assert lib.gsr_config_get(b"split_len", C.byref(got)) == 0 and got.value == 2047
+    assert lib.gsr_configure(b"bucket_target", 10) == 0
+    assert lib.gsr_config_get(b"bucket_target", C.byref(got)) == 0 and got.value == 256
+    assert lib.gsr_configure(b"bucket_target", -1) == 0
+    assert lib.gsr_configure(b"no_such_knob", 1) != 0 and b"unknown knob" in lib.gsr_last_error()

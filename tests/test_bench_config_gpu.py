@@ -1,0 +1,175 @@
+"""Parity on the workloads bench.py actually times (BASELINE.json configs[1], [2] and [3]) against Oracle A, the
+reference CUDA rasterizer compiled for sm_100a (oracle/_ref):
+
+  * the bench scene (1 M Gaussians, seed 20241017 + 2, SH degree 3, 752x480) on ALL EIGHT poses of the keyframe
+    window, default knobs, through gsr_forward (the reference's contract: allocator callbacks, R read back) AND
+    through engine.RasterContext (presized sync-free forward, then the captured graph bench.py replays);
+  * config 4 (5 M Gaussians, 1920x1200, heavy overlap, close-up pose) on one pose, both ways.
+
+Bar: sorted keys / point list (incl. tie order) / tile ranges / radii / n_contrib bit-exact, D / S / final_T
+bit-identical, C <= 1e-5 absolute, gradients <= 1e-4 (tests/tolerances.py), exactly as for the small cases.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from tolerances import GRAD_RTOL, assert_cds, assert_grad, grad_error, pure_relative_fraction
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not helpers.ref_available(), reason="oracle/_ref/gsr_ref_ext.so not built")
+
+BENCH_P, BENCH_SEED, BENCH_DEG, WINDOW = 1_000_000, 20241017 + 2, 3, 8
+CFG4_P, CFG4_SEED = 5_000_000, 20241017 + 4
+
+
+def _scene_on(dev, P, seed, deg, heavy):
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import scene
+    sc_cpu = scene.make_scene(P, seed, deg, heavy_overlap=heavy)
+    return sc_cpu, {k: v.to(dev) for k, v in sc_cpu.items()}
+
+
+def _case_for(sc_cpu, cam, deg, seed):
+    return helpers.Case(sc_cpu["means3D"], sc_cpu["scales"], sc_cpu["rotations"], sc_cpu["opacities"], sc_cpu["shs"],
+                        sc_cpu["background"], cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx,
+                        cam.tanfovy, cam.width, cam.height, deg).with_upstream(seed + 1)
+
+
+def _check_against_reference(ours, ref, label, grad_tol=None):
+    """grad_tol: per-gradient tolerance where the reference's OWN run-to-run difference (float atomics in another
+    order) exceeds the 1e-4 contract -- only config 4's heavy overlap needs it; None: tests/tolerances.py."""
+    helpers.assert_integer_stages_equal(ours, ref, check_unsorted=False)
+    np.testing.assert_array_equal(np.asarray(ours["n_contrib"]).astype(np.int64),
+                                  np.asarray(ref["n_contrib"]).astype(np.int64), err_msg=label + " n_contrib")
+    np.testing.assert_array_equal(helpers.bits(ours["out_depth"]), helpers.bits(ref["out_depth"]), err_msg=label + " D")
+    np.testing.assert_array_equal(helpers.bits(ours["out_acc"]), helpers.bits(ref["out_acc"]), err_msg=label + " S")
+    np.testing.assert_array_equal(helpers.bits(ours["accum_alpha"]), helpers.bits(ref["accum_alpha"]),
+                                  err_msg=label + " final_T")
+    assert_cds(label + " C", ours["out_color"], ref["out_color"])
+    worst = {}
+    for n in helpers.GRAD_NAMES:
+        got = np.asarray(ours[n]).reshape(np.asarray(ref[n]).shape)
+        if grad_tol is not None and grad_tol[n] > GRAD_RTOL:
+            e = grad_error(got, ref[n])
+            assert np.isfinite(got).all() and e <= grad_tol[n], "%s %s: %.3e > %.3e" % (label, n, e, grad_tol[n])
+        else:
+            assert_grad(label + " " + n, got, ref[n])
+        worst[n] = pure_relative_fraction(got, ref[n])
+    return worst
+
+
+def _context_outputs(ctx, case, R):
+    """numpy dictionary in helpers.run_ours' format from a RasterContext's arenas after forward + backward."""
+    from gs_livm_b200 import debug
+    g = debug.geom_state(ctx.geom.buf, ctx.P)
+    b = debug.binning_state(ctx.binning.buf, ctx.num_rendered)
+    im = debug.image_state(ctx.image.buf, case.width, case.height)
+    out = dict(sort_path="tile", num_rendered=R, out_color=ctx.out_color, out_depth=ctx.out_depth, out_acc=ctx.out_acc,
+               radii=ctx.radii, depths=g["depths"], means2D=g["means2D"], tiles_touched=g["tiles_touched"],
+               point_list_keys=b["point_list_keys"][:R], point_list=b["point_list"][:R], ranges=im["ranges"],
+               accum_alpha=im["accum_alpha"], n_contrib=im["n_contrib"])
+    out.update(ctx.grads)
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+@pytest.fixture(scope="module")
+def bench_scene(built_library, cuda_device):
+    return _scene_on(cuda_device, BENCH_P, BENCH_SEED, BENCH_DEG, False)
+
+
+@needs_ref
+@pytest.mark.parametrize("pose", range(WINDOW))
+def test_bench_scene_every_pose_matches_reference_cuda(pose, bench_scene, cuda_device, record_property):
+    """gsr_forward + gsr_backward (default knobs) vs the reference CUDA rasterizer on the scene bench.py times."""
+    from gs_livm_b200 import scene
+    sc_cpu, _ = bench_scene
+    cam = scene.scene_camera(sc_cpu, pose, scene.NTU)
+    case = _case_for(sc_cpu, cam, BENCH_DEG, BENCH_SEED)
+    ref = helpers.run_ref_cuda(case, cuda_device)
+    ours = helpers.run_ours(case, cuda_device)
+    lens = np.diff(np.asarray(ref["ranges"]).astype(np.int64), axis=1)
+    assert lens.max() > 4096, "the bench scene must exercise the long-list sort classes and the FINE blend shape"
+    worst = _check_against_reference(ours, ref, "pose %d" % pose)
+    record_property("pure_rtol_fraction", {k: round(v, 6) for k, v in worst.items()})
+
+
+@needs_ref
+def test_bench_scene_sync_free_and_captured_paths_match_reference_cuda(bench_scene, cuda_device):
+    """The path bench.py's `value` goes through: RasterContext (first frame synchronous, then gsr_forward_presized,
+    then the captured CUDA graph), all eight poses, against the reference CUDA rasterizer."""
+    from gs_livm_b200 import engine, scene
+    sc_cpu, sc = bench_scene
+    dev = cuda_device
+    cams_cpu = [scene.scene_camera(sc_cpu, i, scene.NTU) for i in range(WINDOW)]
+    cams = [c.to(dev) for c in cams_cpu]
+    H, W = cams[0].height, cams[0].width
+    ctx = engine.RasterContext(BENCH_P, 16, W, H, dev, BENCH_DEG)
+    cases = [_case_for(sc_cpu, c, BENCH_DEG, BENCH_SEED) for c in cams_cpu]
+    dC, dS = cases[0].dL_dcolor.to(dev), cases[0].dL_dacc.to(dev)
+    refs = [helpers.run_ref_cuda(c, dev) for c in cases]
+    for k in range(WINDOW):  # eager; sizes the arena for the busiest view
+        ctx.forward(sc, cams[k])
+        ctx.backward(dC, dS)
+        if not ctx.check():
+            ctx.forward(sc, cams[k], redo=True)
+            ctx.check()
+    for k in range(WINDOW):  # sync-free (presized) frames
+        ctx.forward(sc, cams[k])
+        ctx.backward(dC, dS)
+        torch.cuda.synchronize()
+        assert ctx.check(), "pose %d must fit the presized arena" % k
+        _check_against_reference(_context_outputs(ctx, cases[k], ctx.last_rendered), refs[k], "presized pose %d" % k)
+    frames = [ctx.capture_step(sc, cams[k], dC, dS) for k in range(WINDOW)]
+    for k in (3, 0, 7, 4):
+        ctx.grad_flat.fill_(float("nan"))
+        frames[k].replay()
+        torch.cuda.synchronize()
+        assert ctx.check()
+        _check_against_reference(_context_outputs(ctx, cases[k], ctx.last_rendered), refs[k], "captured pose %d" % k)
+
+
+@needs_ref
+def test_config4_five_million_gaussians_1920x1200_heavy_overlap(built_library, cuda_device):
+    """BASELINE.json configs[3]: botanic_garden-shaped map, 5 M Gaussians, 1920x1200, heavy tile overlap (scales x4,
+    camera 2 m from a facade): tile lists far beyond one CTA's shared memory. Through gsr_forward and through the
+    sync-free RasterContext (which must NOT report overflow: no list-length ceiling)."""
+    from gs_livm_b200 import engine, scene
+    dev = cuda_device
+    sc_cpu, sc = _scene_on(dev, CFG4_P, CFG4_SEED, 3, True)
+    cam_cpu = scene.scene_camera(sc_cpu, 0, scene.BOTANIC, close_up=True)
+    case = _case_for(sc_cpu, cam_cpu, 3, CFG4_SEED)
+    ref = helpers.run_ref_cuda(case, dev)
+    lens = np.diff(np.asarray(ref["ranges"]).astype(np.int64), axis=1)
+    print("config 4: R = %d, longest tile list = %d, visible = %d" % (ref["num_rendered"], lens.max(),
+                                                                      int((ref["radii"] > 0).sum())))
+    assert lens.max() > 12032, "config 4 must contain tile lists longer than one CTA's shared memory holds"
+    # Heavy overlap sums thousands of float atomics per Gaussian: two runs of the REFERENCE differ from each other by
+    # about as much as the 1e-4 contract allows. The bar here is therefore max(1e-4, 4 x the reference's own
+    # run-to-run difference), measured on the spot and printed.
+    again = helpers.run_ref_cuda(case, dev)
+    noise = {n: grad_error(again[n], ref[n]) for n in helpers.GRAD_NAMES}
+    del again
+    tol = {n: max(GRAD_RTOL, 4.0 * v) for n, v in noise.items()}
+    print("reference run-to-run gradient difference:", {n: "%.2e" % v for n, v in noise.items()})
+    ours = helpers.run_ours(case, dev)
+    _check_against_reference(ours, ref, "config 4", tol)
+    del ours
+    ctx = engine.RasterContext(CFG4_P, 16, cam_cpu.width, cam_cpu.height, dev, 3)
+    cam = cam_cpu.to(dev)
+    dC, dS = case.dL_dcolor.to(dev), case.dL_dacc.to(dev)
+    ctx.forward(sc, cam)  # synchronous: learns the capacity
+    ctx.backward(dC, dS)
+    assert ctx.check()
+    for _ in range(2):  # sync-free: must fit and must be right, frame after frame
+        ctx.forward(sc, cam)
+        ctx.backward(dC, dS)
+        torch.cuda.synchronize()
+        assert ctx.check(), "config 4 must run on the sync-free path (no list-length ceiling)"
+        _check_against_reference(_context_outputs(ctx, case, ctx.last_rendered), ref, "config 4 presized", tol)
+    frame = ctx.capture_step(sc, cam, dC, dS)
+    ctx.grad_flat.fill_(float("nan"))
+    frame.replay()
+    torch.cuda.synchronize()
+    assert ctx.check()
+    _check_against_reference(_context_outputs(ctx, case, ctx.last_rendered), ref, "config 4 captured", tol)

@@ -262,3 +262,49 @@ def test_unchanged_reference_operator_links_and_runs_on_our_library(built_librar
     for got, name in ((g_means, "dL_dmean3D"), (g_sh, "dL_dsh"), (g_op, "dL_dopacity"), (g_sc, "dL_dscale"),
                       (g_rot, "dL_drot")):
         assert_grad(name, got.reshape(raw[name].shape), raw[name])
+
+
+def test_overflowing_frame_from_a_cold_state_is_an_empty_render(built_library, cuda_device):
+    """gsr_forward_presized as the FIRST call on fresh (garbage-filled) buffers, with a capacity the frame does not
+    fit: the launch order must still be a permutation of the tiles and nothing may be read through stale tile ids --
+    the image is exactly the background, every gradient zero, and a different camera afterwards behaves the same."""
+    import ctypes as C
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import _lib, debug, scene
+    case = helpers.scene_case(20_000, 505, 3, intr=SMALL, heavy=True)
+    dev = cuda_device
+    lib = _lib.load()
+    d = lambda t: t.to(dev).contiguous()  # noqa: E731
+    t = dict(bg=d(case.background), m=d(case.means3D), sh=d(case.shs), op=d(case.opacities), sc=d(case.scales),
+             rot=d(case.rotations))
+    cams = [scene.Camera(case.width, case.height, case.tanfovx, case.tanfovy, case.viewmatrix, case.projmatrix,
+                         case.camera_center).to(dev)]
+    sc_cpu = scene.make_scene(20_000, 505, 3, heavy_overlap=True)
+    cams.append(scene.scene_camera(sc_cpu, 5, SMALL).to(dev))
+    W, H, P = case.width, case.height, case.P
+    cap = 1000  # far below R
+    junk = lambda n: torch.randint(0, 255, (int(n),), dtype=torch.uint8, device=dev)  # noqa: E731
+    geom, img, binning = junk(lib.gsr_required_geom(P)), junk(lib.gsr_required_image(W, H)), junk(lib.gsr_required_binning(cap))
+    out = torch.full((5, H, W), float("nan"), device=dev)
+    radii = torch.zeros(P, dtype=torch.int32, device=dev)
+    status = torch.zeros(4, dtype=torch.int32).pin_memory()
+    for cam in cams:
+        a = _lib.FwdArgs()
+        a.P, a.D, a.M, a.width, a.height = P, 3, 16, W, H
+        a.background, a.means3D, a.shs, a.colors_precomp = t["bg"].data_ptr(), t["m"].data_ptr(), t["sh"].data_ptr(), None
+        a.opacities, a.scales, a.scale_modifier = t["op"].data_ptr(), t["sc"].data_ptr(), 1.0
+        a.rotations, a.cov3D_precomp = t["rot"].data_ptr(), None
+        a.viewmatrix, a.projmatrix, a.cam_pos = cam.viewmatrix.data_ptr(), cam.projmatrix.data_ptr(), cam.camera_center.data_ptr()
+        a.tan_fovx, a.tan_fovy, a.prefiltered = cam.tanfovx, cam.tanfovy, 0
+        a.out_color, a.out_depth, a.out_acc = out[:3].data_ptr(), out[3:4].data_ptr(), out[4:5].data_ptr()
+        a.radii, a.debug = radii.data_ptr(), 0
+        st = lib.gsr_forward_presized(C.byref(a), geom.data_ptr(), binning.data_ptr(), cap, img.data_ptr(),
+                                      torch.cuda.current_stream(dev).cuda_stream, status.data_ptr())
+        _lib.check(st, "gsr_forward_presized")
+        torch.cuda.synchronize()
+        assert int(status[3]) == 1 and int(status[0]) > cap
+        assert torch.equal(out[:3], torch.ones_like(out[:3])), "background only"
+        assert float(out[3:].abs().max()) == 0.0
+        order = debug.image_state(img, W, H)["tile_order"].cpu().numpy()
+        np.testing.assert_array_equal(np.sort(order), np.arange(order.size))
+        out.fill_(float("nan"))

@@ -154,9 +154,11 @@ def test_depth_ties_keep_id_order(sort_path, built_library, cuda_device):
     check_forward_exact(ours, ref, case, vs_cuda_reference=False)
 
 
-def test_list_longer_than_one_cta_takes_the_device_path(built_library, cuda_device):
-    """A tile with more instances than tile_sort.cu's shared-memory capacity (kLargeCap = 12032): gsr_forward
-    must switch to the device-wide sort by itself and still match the oracle bit for bit."""
+@pytest.mark.parametrize("blend", ("sparse", "small-buckets"))
+def test_very_long_tile_list_is_cut_into_depth_buckets(blend, built_library, cuda_device):
+    """One tile with 20 000 instances (ten times what a sort CTA holds in shared memory): the list is cut into depth
+    buckets (tile_sort.cu, partition_long_kernel) and still matches the oracle bit for bit. There is no list-length
+    ceiling and no library sort on this path."""
     case = helpers.scene_case(2000, 141, 0, intr=SMALL)
     fwd = helpers.run_oracle_cpu(case, backward=False)
     m2 = np.asarray(fwd["means2D"])
@@ -172,6 +174,27 @@ def test_list_longer_than_one_cta_takes_the_device_path(built_library, cuda_devi
     ref = helpers.run_oracle_cpu(c)
     lengths = np.diff(np.asarray(ref["ranges"]).astype(np.int64), axis=1)
     assert lengths.max() > 12032
+    ours = helpers.run_ours(c, cuda_device, blend=blend)
+    check_forward_exact(ours, ref, c, vs_cuda_reference=False)
+
+
+def test_thousands_of_equal_depths_overflow_a_bucket_and_still_sort(built_library, cuda_device):
+    """6 000 copies of ONE Gaussian: every instance of a tile has the same depth, so no splitter can separate them and
+    the depth bucket exceeds a sort CTA's shared memory -- the global-memory path of segment_sort_kernel; ties must
+    still come out in ascending Gaussian order."""
+    case = helpers.scene_case(2000, 141, 0, intr=SMALL)
+    fwd = helpers.run_oracle_cpu(case, backward=False)
+    m2 = np.asarray(fwd["means2D"])
+    central = (np.asarray(fwd["radii"]) > 0) & (np.abs(m2[:, 0] - 80) < 40) & (np.abs(m2[:, 1] - 48) < 24)
+    k = int(np.argmax(central))
+    n = 6000
+    pick = lambda t: t[k:k + 1].repeat(n, *([1] * (t.dim() - 1)))  # noqa: E731
+    c = helpers.Case(pick(case.means3D), pick(case.scales) * 0.2, pick(case.rotations), torch.full((n, 1), 0.01),
+                     pick(case.shs), case.background, case.viewmatrix, case.projmatrix, case.camera_center,
+                     case.tanfovx, case.tanfovy, case.width, case.height, case.sh_degree).with_upstream(5)
+    ref = helpers.run_oracle_cpu(c)
+    keys = np.asarray(ref["point_list_keys"]).astype(np.uint64)
+    assert ref["num_rendered"] >= n and len(np.unique(keys)) <= 64
     ours = helpers.run_ours(c, cuda_device)
     check_forward_exact(ours, ref, c, vs_cuda_reference=False)
 

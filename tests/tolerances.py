@@ -8,6 +8,8 @@
   of float atomics whose order differs between any two runs: the reference differs from ITSELF by up to
   ~1e-5 of the tensor's scale between two launches (measured, tools/dev_compare.py), so elements that are
   tiny through cancellation cannot be resolved more finely by any implementation.
+  In addition at least ROW_FRACTION_MIN of the elements must be within 1e-4 of the scale of their OWN row (their own
+  Gaussian), and the large parity tests / bench.py report the fraction that passes the pure relative test.
 """
 import numpy as np
 
@@ -33,8 +35,38 @@ def grad_error(ours, ref):
     return float((np.abs(ours - ref) / (np.abs(ref) + scale)).max())
 
 
+def pure_relative_fraction(ours, ref, rtol=GRAD_RTOL):
+    """Fraction of the non-zero reference elements that pass the PURE relative test |ours - ref| <= rtol * |ref|
+    (no absolute floor). Reported by the large parity tests and by bench.py's parity_check: it says how much of the
+    tensor the floor in assert_grad actually matters for."""
+    ours, ref = np.asarray(ours, np.float64).ravel(), np.asarray(ref, np.float64).ravel()
+    nz = ref != 0.0
+    if not nz.any():
+        return 1.0
+    return float((np.abs(ours[nz] - ref[nz]) <= rtol * np.abs(ref[nz])).mean())
+
+
+def row_scale_fraction(ours, ref, rtol=GRAD_RTOL):
+    """Fraction of elements within rtol * (|ref| + max|ref| of the element's OWN row, i.e. its own Gaussian): the
+    floor no longer comes from the largest gradient of the whole tensor. Rows that are tiny through cancellation of
+    large per-pixel terms cannot all pass (two runs of the reference differ there as well), so this is reported and
+    bounded from below (ROW_FRACTION_MIN), not required of every element."""
+    ours, ref = np.asarray(ours, np.float64), np.asarray(ref, np.float64)
+    if ref.size == 0:
+        return 1.0
+    r2 = ref.reshape(ref.shape[0], -1) if ref.ndim > 1 else ref.reshape(-1, 1)
+    o2 = ours.reshape(r2.shape)
+    scale = np.abs(r2).max(axis=1, keepdims=True)
+    return float((np.abs(o2 - r2) <= rtol * (np.abs(r2) + scale)).mean())
+
+
+ROW_FRACTION_MIN = 0.995
+
+
 def assert_grad(name, ours, ref):
     assert np.isfinite(np.asarray(ours)).all(), f"{name}: non-finite gradient"
     assert np.asarray(ours).shape == np.asarray(ref).shape, f"{name}: shape {np.shape(ours)} vs {np.shape(ref)}"
     e = grad_error(ours, ref)
     assert e <= GRAD_RTOL, f"{name}: relative error {e:.3e} > {GRAD_RTOL}"
+    f = row_scale_fraction(ours, ref)
+    assert f >= ROW_FRACTION_MIN, f"{name}: only {f:.5f} of the elements are within 1e-4 of their own row's scale"

@@ -19,9 +19,13 @@ def main():
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     which = sys.argv[3] if len(sys.argv) > 3 else "both"
     intr = scene.BOTANIC if (len(sys.argv) > 4 and sys.argv[4] == "botanic") else scene.NTU
+    pose = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    heavy = len(sys.argv) > 6 and sys.argv[6] == "heavy"
+    close = len(sys.argv) > 7 and sys.argv[7] == "close"
     dev = torch.device("cuda:0")
-    sc = {k: v.to(dev) for k, v in scene.make_scene(P, 20241017 + 2, 3).items()}
-    cam = scene.scene_camera(sc, 0, intr).to(dev)
+    seed = 20241017 + (4 if heavy else 2)
+    sc = {k: v.to(dev) for k, v in scene.make_scene(P, seed, 3, heavy_overlap=heavy).items()}
+    cam = scene.scene_camera(sc, pose, intr, close_up=close).to(dev)
     W, H = cam.width, cam.height
     gen = torch.Generator(device="cpu").manual_seed(7)
     dC = (torch.randn((3, H, W), generator=gen) / (H * W)).to(dev)
@@ -44,7 +48,7 @@ def main():
                     acc[n] += max(v, 0.0)  # -1: the stage did not run on this path
                 tot += e0.elapsed_time(e1)
         ctx.check()
-        print(f"ours P={P} {W}x{H} R={getattr(ctx, 'last_rendered', ctx.num_rendered)} visible={int((ctx.radii > 0).sum())}")
+        print(f"ours P={P} {W}x{H} pose={pose} heavy={heavy} close={close} R={getattr(ctx, 'last_rendered', ctx.num_rendered)} visible={int((ctx.radii > 0).sum())}")
         for n in _lib.STAGES:
             print(f"  {n:12s} {acc[n] / iters * 1000:9.1f} us")
         print(f"  sum stages   {sum(acc.values()) / iters * 1000:9.1f} us ; fwd+bwd wall (events) {tot / iters * 1000:9.1f} us")
