@@ -49,7 +49,11 @@ class BwdArgs(C.Structure):
 
 BWD_OUTPUTS_UNINITIALIZED = 1
 BWD_ACCUMULATORS_ZEROED = 2
-ABI_VERSION = 4  # include/gsr.h GSR_ABI_VERSION this binding was written against
+BWD_SH_FACTORED = 4
+BWD_ONLY_BLEND = 8
+BWD_ONLY_GEOM = 16
+WINDOW_BARRIER_CHANNELS = 8
+ABI_VERSION = 5  # include/gsr.h GSR_ABI_VERSION this binding was written against
 
 
 class WindowRows(C.Structure):
@@ -108,6 +112,12 @@ SYMBOLS = {
     "gsr_window_allreduce_multimem_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsr_window_allreduce_p2p_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p]),
+    "gsr_window_slot_floats": (C.c_size_t, [C.c_int]),
+    "gsr_window_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gsr_window_push_rgb": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
+    "gsr_window_expand_sh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "gsr_image_loss_scratch_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "gsr_image_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),

@@ -12,17 +12,10 @@
 // colour channels pass no gradient (:41-43), Gaussians with radii <= 0 are skipped (outputs stay at the
 // caller's zeros).
 #include "gsr_common.cuh"
+#include "sh_basis.cuh"
 
 namespace gsr {
 namespace {
-
-__device__ constexpr float kC0 = 0.28209479177387814f;
-__device__ constexpr float kC1 = 0.4886025119029199f;
-__device__ constexpr float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                                     -1.0925484305920792f, 0.5462742152960396f};
-__device__ constexpr float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
-                                     0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
-                                     -0.5900435899266435f};
 
 struct GeomBwdArgs {
   int P, D, M;
@@ -56,41 +49,6 @@ __device__ __forceinline__ float xform_row(const float* m, int r, float x, float
   return __fadd_rn(dot3_ref(x, m[r], y, m[4 + r], z, m[8 + r]), m[12 + r]);
 }
 
-// SH basis values and their partial derivatives w.r.t. the (normalised) direction components.
-__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float b[16], float bx[16], float by[16],
-                                         float bz[16]) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) b[i] = bx[i] = by[i] = bz[i] = 0.f;
-  b[0] = kC0;
-  if (deg < 1) return;
-  b[1] = -kC1 * y, b[2] = kC1 * z, b[3] = -kC1 * x;
-  by[1] = -kC1, bz[2] = kC1, bx[3] = -kC1;
-  if (deg < 2) return;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  b[4] = kC2[0] * xy, b[5] = kC2[1] * yz, b[6] = kC2[2] * (2.f * zz - xx - yy), b[7] = kC2[3] * xz,
-  b[8] = kC2[4] * (xx - yy);
-  bx[4] = kC2[0] * y, by[4] = kC2[0] * x;
-  by[5] = kC2[1] * z, bz[5] = kC2[1] * y;
-  bx[6] = kC2[2] * -2.f * x, by[6] = kC2[2] * -2.f * y, bz[6] = kC2[2] * 4.f * z;
-  bx[7] = kC2[3] * z, bz[7] = kC2[3] * x;
-  bx[8] = kC2[4] * 2.f * x, by[8] = kC2[4] * -2.f * y;
-  if (deg < 3) return;
-  b[9] = kC3[0] * y * (3.f * xx - yy);
-  b[10] = kC3[1] * xy * z;
-  b[11] = kC3[2] * y * (4.f * zz - xx - yy);
-  b[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-  b[13] = kC3[4] * x * (4.f * zz - xx - yy);
-  b[14] = kC3[5] * z * (xx - yy);
-  b[15] = kC3[6] * x * (xx - 3.f * yy);
-  bx[9] = kC3[0] * 6.f * xy, by[9] = kC3[0] * 3.f * (xx - yy);
-  bx[10] = kC3[1] * yz, by[10] = kC3[1] * xz, bz[10] = kC3[1] * xy;
-  bx[11] = kC3[2] * -2.f * xy, by[11] = kC3[2] * (4.f * zz - xx - 3.f * yy), bz[11] = kC3[2] * 8.f * yz;
-  bx[12] = kC3[3] * -6.f * xz, by[12] = kC3[3] * -6.f * yz, bz[12] = kC3[3] * 3.f * (2.f * zz - xx - yy);
-  bx[13] = kC3[4] * (4.f * zz - 3.f * xx - yy), by[13] = kC3[4] * -2.f * xy, bz[13] = kC3[4] * 8.f * xz;
-  bx[14] = kC3[5] * 2.f * xz, by[14] = kC3[5] * -2.f * yz, bz[14] = kC3[5] * (xx - yy);
-  bx[15] = kC3[6] * 3.f * (xx - yy), by[15] = kC3[6] * -6.f * xy;
-}
-
 // Gaussians per CTA. The kernel alternates between a memory phase (SH rows in, dL_dsh rows out) and ~1000
 // instructions of covariance / SH math; with 121 registers only 16 warps fit an SM, and eight 64-thread CTAs
 // interleave those phases better than two 256-thread ones (97 -> 91 us).
@@ -100,7 +58,9 @@ constexpr int kShRow = 13;  // float4 per staged SH row: 12 used + 1 pad -> conf
 // kVec16: M == 16 and shs / dL_dsh 16-byte aligned. SH rows of the block's visible Gaussians are staged into
 // shared memory with coalesced 16-byte cp.async transfers (issued first, so they overlap the covariance
 // math), and the dL_dsh rows leave the same way: written row-wise into shared memory, stored coalesced.
-template <bool kVec16>
+// kFactored: GSR_BWD_SH_FACTORED -- dL_dsh is not written at all (window_factored.cu rebuilds the window's sum of it
+// from the views' dRGB); the SH rows are still read for the direction gradient.
+template <bool kVec16, bool kFactored>
 __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   __shared__ float s_view[16], s_proj[16], s_cam[3];
   __shared__ uint8_t s_active[kBlock];
@@ -262,15 +222,15 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     __syncthreads();  // every thread's part of the staged rows has landed
   }
   if (active && a.shs) {
-    const float ox = mx - s_cam[0], oy = my - s_cam[1], oz = mz - s_cam[2];
-    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
-    const float x = ox / len, y = oy / len, z = oz / len;
+    float ox, oy, oz, x, y, z;
+    sh_direction(mx, my, mz, s_cam[0], s_cam[1], s_cam[2], ox, oy, oz, x, y, z);
     const uint32_t cl = cl_early;
     float dRGB[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) dRGB[c] = ((cl >> c) & 1u) ? 0.f : dRGB_early[c];
     float b[16], bx[16], by[16], bz[16];
-    sh_basis(a.D, x, y, z, b, bx, by, bz);
+    sh_basis_values(a.D, x, y, z, b);
+    sh_basis_grads(a.D, x, y, z, bx, by, bz);
     const int ncoef = (a.D + 1) * (a.D + 1);
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;  // dL/d(dir)
     if (kVec16) {
@@ -284,7 +244,7 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const bool on = k < ncoef;
-          o[k * 3 + c] = on ? b[k] * dRGB[c] : 0.f;
+          if (!kFactored) o[k * 3 + c] = on ? __fmul_rn(b[k], dRGB[c]) : 0.f;
           if (on && k > 0) {
             const float w = sh[k * 3 + c] * dRGB[c];
             ddx += bx[k] * w, ddy += by[k] * w, ddz += bz[k] * w;
@@ -292,20 +252,21 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
         }
       }
 #pragma unroll
-      for (int i = 0; i < 12; ++i) s_sh[tid * kShRow + i] = out4[i];  // own row only: no hazard
+      for (int i = 0; i < 12; ++i)
+        if (!kFactored) s_sh[tid * kShRow + i] = out4[i];  // own row only: no hazard
     } else {
       const float* sh = a.shs + (size_t)idx * a.M * 3;
       float* o = a.dL_dsh + (size_t)idx * a.M * 3;
       for (int k = 0; k < ncoef && k < a.M; ++k) {
         for (int c = 0; c < 3; ++c) {
-          o[k * 3 + c] = b[k] * dRGB[c];
+          if (!kFactored) o[k * 3 + c] = __fmul_rn(b[k], dRGB[c]);
           if (k > 0) {
             const float w = __ldg(sh + k * 3 + c) * dRGB[c];
             ddx += bx[k] * w, ddy += by[k] * w, ddz += bz[k] * w;
           }
         }
       }
-      if (a.assign_all)  // coefficients above the active degree
+      if (a.assign_all && !kFactored)  // coefficients above the active degree
         for (int k = ncoef * 3; k < a.M * 3; ++k) o[k] = 0.f;
     }
     // through the normalisation dir = o/|o| (reference dnormvdv, auxiliary.h:93-103)
@@ -315,7 +276,7 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     gmy += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * inv32;
     gmz += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * inv32;
   }
-  if (kVec16) {  // coalesced store of the visible Gaussians' dL_dsh rows (culled rows stay at the caller's zeros)
+  if (kVec16 && !kFactored) {  // coalesced store of the visible Gaussians' dL_dsh rows (culled rows stay at the caller's zeros)
     __syncthreads();
     float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)base * 12;
     for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {
@@ -334,7 +295,7 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
         a.dL_dscale[3 * i] = 0.f, a.dL_dscale[3 * i + 1] = 0.f, a.dL_dscale[3 * i + 2] = 0.f;
         reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (!kVec16 && a.shs)
+      if (!kVec16 && !kFactored && a.shs)
         for (int k = 0; k < a.M * 3; ++k) a.dL_dsh[i * a.M * 3 + k] = 0.f;
     }
     return;
@@ -387,15 +348,23 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   if (!al16(f.dL_dconic) || (!f.cov3D_precomp && (!al16(f.rotations) || !al16(f.dL_drot))))
     return cudaErrorMisalignedAddress;
-  a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && al16(f.dL_dsh);
+  const bool factored = a.shs && (f.flags & GSR_BWD_SH_FACTORED);
+  a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && (factored || al16(f.dL_dsh));
   a.assign_all = (f.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) ? 1 : 0;
   const int blocks = (f.P + kBlock - 1) / kBlock;
   if (a.vec_sh) {
     constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);
-    if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(geom_bwd_kernel<true>), kSmem)) return e;
-    geom_bwd_kernel<true><<<blocks, kBlock, kSmem, s>>>(a);
+    if (factored) {
+      if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(geom_bwd_kernel<true, true>), kSmem)) return e;
+      geom_bwd_kernel<true, true><<<blocks, kBlock, kSmem, s>>>(a);
+    } else {
+      if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(geom_bwd_kernel<true, false>), kSmem)) return e;
+      geom_bwd_kernel<true, false><<<blocks, kBlock, kSmem, s>>>(a);
+    }
+  } else if (factored) {
+    geom_bwd_kernel<false, true><<<blocks, kBlock, 0, s>>>(a);
   } else {
-    geom_bwd_kernel<false><<<blocks, kBlock, 0, s>>>(a);
+    geom_bwd_kernel<false, false><<<blocks, kBlock, 0, s>>>(a);
   }
   return cudaGetLastError();
 }

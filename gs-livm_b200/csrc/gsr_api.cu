@@ -474,7 +474,10 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   if (!a.means3D || !a.viewmatrix || !a.projmatrix || !a.cam_pos || !a.background || !a.dL_dpix || !a.dL_dacc ||
       !a.dL_dmean2D || !a.dL_dconic || !a.dL_dopacity || !a.dL_dcolor || !a.dL_dmean3D || !a.dL_dcov3D)
     return fail(GSR_ERR_INVALID, "gsr_backward: null input/output pointer");
-  if (!a.colors_precomp && (!a.shs || !a.dL_dsh)) return fail(GSR_ERR_INVALID, "gsr_backward: need shs + dL_dsh");
+  if (!a.colors_precomp && (!a.shs || (!a.dL_dsh && !(a.flags & GSR_BWD_SH_FACTORED))))
+    return fail(GSR_ERR_INVALID, "gsr_backward: need shs + dL_dsh");
+  if ((a.flags & GSR_BWD_ONLY_BLEND) && (a.flags & GSR_BWD_ONLY_GEOM))
+    return fail(GSR_ERR_INVALID, "gsr_backward: GSR_BWD_ONLY_BLEND and GSR_BWD_ONLY_GEOM exclude each other");
   if (!a.cov3D_precomp && (!a.scales || !a.rotations || !a.dL_dscale || !a.dL_drot))
     return fail(GSR_ERR_INVALID, "gsr_backward: need scales/rotations and their gradient outputs");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -487,15 +490,17 @@ int gsr_backward(const gsr_bwd_args* args, void* stream_v) {
   const float focal_y = a.height / (2.0f * a.tan_fovy);
   const float focal_x = a.width / (2.0f * a.tan_fovx);
 
-  if ((a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) && !(a.flags & GSR_BWD_ACCUMULATORS_ZEROED))
+  const bool do_blend = !(a.flags & GSR_BWD_ONLY_GEOM), do_geom = !(a.flags & GSR_BWD_ONLY_BLEND);
+  if (do_blend && (a.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) && !(a.flags & GSR_BWD_ACCUMULATORS_ZEROED))
     if (int st = zero_accumulators(a, stream)) return st;
-  if (a.R > 0) {
+  if (do_blend && a.R > 0) {
     GSR_STAGE(GSR_STAGE_BLEND_BWD,
               launch_blend_bwd_sparse(a.width, a.height, img, bin, a.background, a.dL_dpix, a.dL_dacc, a.dL_dmean2D,
                                       a.dL_dconic, a.dL_dopacity, a.dL_dcolor, stream),
               "blend_bwd", debug, stream);
   }
-  GSR_STAGE(GSR_STAGE_GEOM_BWD, launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);
+  if (do_geom)
+    GSR_STAGE(GSR_STAGE_GEOM_BWD, launch_geom_bwd(a, geom, radii, focal_x, focal_y, stream), "geom_bwd", debug, stream);
   return GSR_OK;
 }
 

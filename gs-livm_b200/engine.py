@@ -15,10 +15,25 @@ import torch
 from . import _lib
 from .scene import Camera
 
-GRAD_LAYOUT = (  # name, floats per Gaussian — one flat buffer, so a window's all-reduce is ONE collective
-    ("dL_dmean3D", 3), ("dL_dsh", None), ("dL_dscale", 3), ("dL_drot", 4), ("dL_dopacity", 1),
+GRAD_LAYOUT = (  # name, floats per Gaussian — one flat buffer, so a window's all-reduce is ONE collective.
+    # The SH rows come first and the other 11 parameter-gradient floats behind them: the factored window exchange
+    # (window.FactoredExchange) all-reduces only those 11; dL_dopacity sits next to the other three arrays the blend
+    # backward accumulates into, so one memset clears all four.
+    ("dL_dsh", None), ("dL_dmean3D", 3), ("dL_dscale", 3), ("dL_drot", 4), ("dL_dopacity", 1),
     ("dL_dmean2D", 3), ("dL_dconic", 4), ("dL_dcolor", 3), ("dL_dcov3D", 6),
 )
+
+
+def grad_layout(P: int, M: int):
+    """-> ({name: (first float, floats per Gaussian)}, total floats, floats of the parameter gradients, floats of the SH
+    rows). Every array starts on a 16-byte boundary (float4 accesses in geom_bwd and the exchange kernels), so for P
+    not a multiple of 4 there are up to 3 unused floats behind an array."""
+    at, off = {}, 0
+    for name, w in GRAD_LAYOUT:
+        w = int(M) * 3 if w is None else w
+        at[name] = (off, w)
+        off += (w * int(P) + 3) // 4 * 4
+    return at, off, at["dL_dmean2D"][0], at["dL_dmean3D"][0]
 
 
 class _Arena:
@@ -63,7 +78,7 @@ class RasterContext:
         caller does anyway) tells whether every frame since the last check fitted; a frame that did not is
         redone through the synchronous path by `forward(..., redo=True)`."""
         self.lib = _lib.load()
-        self.grad_numel = (3 + int(M) * 3 + 3 + 4 + 1 + 3 + 4 + 3 + 6) * int(P)
+        self.grad_numel = grad_layout(P, M)[1]
         self.P, self.M, self.W, self.H, self.D = int(P), int(M), int(width), int(height), int(sh_degree)
         self.device = torch.device(device)
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -72,20 +87,17 @@ class RasterContext:
         self.out_acc = torch.zeros((1, self.H, self.W), **f32)
         self.radii = torch.zeros((self.P,), dtype=torch.int32, device=self.device)
         self.geom, self.binning, self.image = _Arena(self.device), _Arena(self.device), _Arena(self.device)
-        # flat gradient buffer; the leading 59 floats per Gaussian (mean3D, sh, scale, rot, opacity) are what a
+        # flat gradient buffer; the leading 59 floats per Gaussian (sh, mean3D, scale, rot, opacity) are what a
         # multi-GPU window all-reduces (236 B per Gaussian at M = 16)
-        sizes = [(n, (self.M * 3 if w is None else w)) for n, w in GRAD_LAYOUT]
-        total = sum(w for _, w in sizes) * self.P
+        at, total, param_floats, sh_floats = grad_layout(self.P, self.M)
         # (a multi-GPU window passes its symmetric gradient buffer here: window.GradExchange.flat)
         self.grad_flat = torch.zeros((total,), **f32) if grad_flat is None else grad_flat
         if self.grad_flat.numel() < total or self.grad_flat.dtype != torch.float32:
             raise ValueError("grad_flat must hold %d float32 values" % total)
-        self.grads: Dict[str, torch.Tensor] = {}
-        off = 0
-        for n, w in sizes:
-            self.grads[n] = self.grad_flat[off:off + w * self.P].view(self.P, w)
-            off += w * self.P
-        self.param_grad_floats = (3 + self.M * 3 + 3 + 4 + 1) * self.P
+        self.grads: Dict[str, torch.Tensor] = {n: self.grad_flat[off:off + w * self.P].view(self.P, w)
+                                               for n, (off, w) in at.items()}
+        self.param_grad_floats = param_floats
+        self.sh_floats = sh_floats  # [0, sh_floats): dL_dsh; [sh_floats, param_grad_floats): the other 11 per Gaussian
         self.num_rendered = 0
         self._fwd_args: Optional[_lib.FwdArgs] = None
         self._keep = None
@@ -166,11 +178,13 @@ class RasterContext:
         _lib.check(self.lib.gsr_backward_prepare(C.byref(a), stream), "gsr_backward_prepare")
 
     def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False,
-                 accumulators_zeroed: bool = False) -> Dict[str, torch.Tensor]:
+                 accumulators_zeroed: bool = False, part: str = "all", sh_factored: bool = False) -> Dict[str, torch.Tensor]:
         """Gradients of the last forward. The reference's caller zero-fills all nine outputs before every
         backward (rasterize_points.cu:173-181); here the library is told they are uninitialised
         (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element itself, inside whatever region the caller is
-        timing."""
+        timing. part: "all", or one half per call — "blend" (accumulator clearing + blend backward; dL_dmean2D,
+        dL_dconic, dL_dopacity, dL_dcolor are complete after it) and "geom" (the per-Gaussian kernel).
+        sh_factored: dL_dsh is not written (GSR_BWD_SH_FACTORED; window.FactoredExchange rebuilds the window's sum)."""
         f = self._fwd_args
         if f is None:
             raise RuntimeError("backward() before forward()")
@@ -189,6 +203,8 @@ class RasterContext:
         a.dL_dsh, a.dL_dscale, a.dL_drot = g["dL_dsh"].data_ptr(), g["dL_dscale"].data_ptr(), g["dL_drot"].data_ptr()
         a.debug = int(debug)
         a.flags = _lib.BWD_OUTPUTS_UNINITIALIZED | (_lib.BWD_ACCUMULATORS_ZEROED if accumulators_zeroed else 0)
+        a.flags |= {"all": 0, "blend": _lib.BWD_ONLY_BLEND, "geom": _lib.BWD_ONLY_GEOM}[part]
+        a.flags |= _lib.BWD_SH_FACTORED if sh_factored else 0
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.gsr_backward(C.byref(a), stream), "gsr_backward")
         return g
@@ -219,6 +235,23 @@ class RasterContext:
         slots = self._unchecked[before:]
         del self._unchecked[before:]
         return CapturedFrame(self, graph, slots, self._fwd_args, (scene, cam, dL_dcolor, dL_dacc))
+
+    def capture(self, step_fn) -> "CapturedFrame":
+        """Any sequence of this context's sync-free forwards / backwards and other stream work (e.g. a window exchange:
+        window.FactoredExchange.render_step) recorded once as a CUDA graph. step_fn() must not wait for the GPU. It is
+        run eagerly once first (one-time kernel attributes, arena growth), then captured."""
+        if not (self.sync_free and self._capacity > 0):
+            raise RuntimeError("capture: render one frame eagerly first (the binning arena must be sized)")
+        step_fn()
+        if not self.check():
+            raise RuntimeError("capture: the frame does not fit the presized binning arena")
+        before = len(self._unchecked)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_fn()
+        slots = self._unchecked[before:]
+        del self._unchecked[before:]
+        return CapturedFrame(self, graph, slots, self._fwd_args, (step_fn, self._keep))
 
     def param_grads(self) -> torch.Tensor:
         """Flat view of the gradients of the optimised parameters (what a window all-reduces)."""

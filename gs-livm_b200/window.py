@@ -157,6 +157,178 @@ class GradExchange:
         return self.flat
 
 
+class FactoredExchange:
+    """The window's gradient exchange with the SH rows factored (csrc/window_factored.cu).
+
+    Per view the 48-float dL_dsh row of a Gaussian is basis(dir_v) (x) dRGB_v, so the ranks exchange the 3 dRGB floats
+    of the Gaussians their view rendered (pushed into every rank's slot of that view as soon as the blend backward is
+    done, i.e. under geom_bwd, which then writes no SH rows at all), all-reduce only the other 11 parameter-gradient
+    floats, and rebuild  dL_dsh = sum_v basis(dir_v) (x) dRGB_v  locally beside that all-reduce — same order on every
+    rank, hence identical bits. Barriers are libgsr_b200's own flag kernels, so `render_step` can be captured in ONE
+    CUDA graph. One view per rank and step; `flat` is the gradient buffer an engine.RasterContext must be built on
+    (`grad_flat=exchange.flat`).
+
+    world == 1 works without any peer memory (the slot is local): that is how the single-GPU tests check the
+    factorisation against the rows geom_bwd writes."""
+
+    def __init__(self, P: int, M: int, device, group=None, reduce_mode: str = "auto", push_mode: str = "auto",
+                 n_views: Optional[int] = None):
+        """n_views: gather slots = views summed per step (default: one per rank; more only make sense where the caller
+        pushes several views itself, as the single-GPU tests do)."""
+        import ctypes as C
+        from . import _lib, engine
+        self._lib, self.lib, self._C = _lib, _lib.load(), C
+        self.group = group
+        self.P, self.M = int(P), int(M)
+        if self.M != 16:
+            raise ValueError("FactoredExchange needs M == 16 SH coefficients (degree-3 storage)")
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.n_views = self.world if n_views is None else int(n_views)
+        if self.world > 16 or not (self.world <= self.n_views <= 16):
+            raise ValueError("at most 16 ranks and 16 views, at least one view per rank")
+        _, self.grad_floats, param_floats, self.sh_floats = engine.grad_layout(self.P, self.M)
+        self.rest_floats = param_floats - self.sh_floats  # mean3D, scale, rotation, opacity: 11 floats per Gaussian
+        self.slot_floats = int(self.lib.gsr_window_slot_floats(self.P))
+        self.vis_words = ((self.P + 31) // 32 + 3) // 4 * 4
+        r4 = lambda n: (n + 31) // 32 * 32  # noqa: E731
+        self._sig_at = r4(self.grad_floats)
+        self._slots_at = self._sig_at + r4(_lib.WINDOW_BARRIER_CHANNELS * 16)
+        self._slot_stride = r4(self.slot_floats + self.vis_words)
+        total = self._slots_at + 2 * self.n_views * self._slot_stride  # two parities x one slot per view
+        self.hdl, mc = None, 0
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.buf = symm_mem.empty(total, dtype=torch.float32, device=self.device)
+            self.hdl = symm_mem.rendezvous(self.buf, grp)
+            off = int(getattr(self.hdl, "offset", 0) or 0)
+            ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
+            if ptrs[self.rank] != self.buf.data_ptr():
+                raise RuntimeError("symmetric buffer pointer mismatch")
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+            mc = mc + off if mc else 0
+        else:
+            self.buf = torch.empty(total, dtype=torch.float32, device=self.device)
+            ptrs = [self.buf.data_ptr()]
+        self.buf.zero_()
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=group)  # every rank's flag words are zero before anybody signals
+        self._ptrs, self._mc = ptrs, mc
+        self.flat = self.buf[:self.grad_floats]
+        self.reduce_mode = reduce_mode if reduce_mode != "auto" else ("multimem" if (mc and self.world > 2) else "p2p")
+        self.push_mode = push_mode if push_mode != "auto" else ("multimem" if (mc and self.world > 2) else "p2p")
+        if not mc and "multimem" in (self.reduce_mode, self.push_mode):
+            raise RuntimeError("no multicast mapping on this system")
+        self._signals = (C.c_void_p * self.world)(*[p + 4 * self._sig_at for p in ptrs])
+        self._reduce_peers = (C.c_void_p * self.world)(*[p + 4 * self.sh_floats for p in ptrs])
+        self._reduce_mc = (mc + 4 * self.sh_floats) if mc else 0
+        self.side = torch.cuda.Stream(device=self.device)
+        self.cam_centres = torch.zeros((self.n_views, 3), dtype=torch.float32, device=self.device)
+
+    # slot of view v, parity q: floats [at, at + slot_floats) then the visibility words
+    def _slot_at(self, v: int, q: int) -> int:
+        return self._slots_at + (q * self.n_views + v) * self._slot_stride
+
+    def _push_targets(self, v: int, q: int):
+        C = self._C
+        at = 4 * self._slot_at(v, q)
+        bases = [self._mc] if self.push_mode == "multimem" else self._ptrs
+        rgb = (C.c_void_p * len(bases))(*[b + at for b in bases])
+        vis = (C.c_void_p * len(bases))(*[b + at + 4 * self.slot_floats for b in bases])
+        return rgb, vis
+
+    def barrier(self, channel: int) -> None:
+        if self.world > 1:
+            st = self.lib.gsr_window_barrier(self._signals, self.rank, self.world, channel,
+                                             torch.cuda.current_stream(self.device).cuda_stream)
+            self._lib.check(st, "gsr_window_barrier")
+
+    def push(self, ctx, parity: int, view: Optional[int] = None) -> None:
+        """This rank's masked dRGB + visibility words into slot `view` (default: this rank's) of every rank (current
+        stream). Needs the blend half of ctx's backward."""
+        rgb, vis = self._push_targets(self.rank if view is None else int(view), parity)
+        st = self.lib.gsr_window_push_rgb(ctx.geom.buf.data_ptr(), self.P, ctx.radii.data_ptr(),
+                                          ctx.grads["dL_dcolor"].data_ptr(), rgb, vis, self.world,
+                                          1 if self.push_mode == "multimem" else 0,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        self._lib.check(st, "gsr_window_push_rgb")
+
+    def expand(self, ctx, means3D: torch.Tensor, parity: int) -> None:
+        """dL_dsh of the whole window from the gathered slots (current stream)."""
+        C = self._C
+        base = self.buf.data_ptr()
+        V = self.n_views
+        rgb = (C.c_void_p * V)(*[base + 4 * self._slot_at(v, parity) for v in range(V)])
+        vis = (C.c_void_p * V)(*[base + 4 * (self._slot_at(v, parity) + self.slot_floats) for v in range(V)])
+        st = self.lib.gsr_window_expand_sh(self.P, ctx.D, self.M, V, means3D.data_ptr(), self.cam_centres.data_ptr(),
+                                           rgb, vis, ctx.grads["dL_dsh"].data_ptr(),
+                                           torch.cuda.current_stream(self.device).cuda_stream)
+        self._lib.check(st, "gsr_window_expand_sh")
+
+    def allreduce_rest_(self) -> None:
+        """Sum over the ranks of the 11 non-SH parameter-gradient floats per Gaussian (current stream), bracketed by
+        barriers: channel 0 = every rank's gradients are complete, channel 2 = every rank holds the sum."""
+        if self.world <= 1:
+            return
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.barrier(0)
+        if self.reduce_mode == "multimem":
+            st = self.lib.gsr_window_allreduce_multimem(self._reduce_mc, self.rest_floats, self.rank, self.world, stream)
+            self._lib.check(st, "gsr_window_allreduce_multimem")
+        elif self.reduce_mode == "p2p":
+            st = self.lib.gsr_window_allreduce_p2p(self._reduce_peers, self.rest_floats, self.rank, self.world, 1, stream)
+            self._lib.check(st, "gsr_window_allreduce_p2p")
+            self.barrier(1)
+            st = self.lib.gsr_window_allreduce_p2p(self._reduce_peers, self.rest_floats, self.rank, self.world, 2, stream)
+            self._lib.check(st, "gsr_window_allreduce_p2p")
+        else:
+            dist.all_reduce(self.flat[self.sh_floats:self.sh_floats + self.rest_floats], op=dist.ReduceOp.SUM, group=self.group)
+        self.barrier(2)
+
+    def exchange(self, ctx, means3D: torch.Tensor, parity: int, blend_done: Optional[torch.cuda.Event] = None) -> None:
+        """Everything after the blend half of the backward, for callers that ran the halves themselves: push + expansion
+        on the side stream (behind `blend_done` if given), all-reduce on the current one, joined at the end."""
+        main = torch.cuda.current_stream(self.device)
+        if blend_done is None:
+            blend_done = torch.cuda.Event()
+            blend_done.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(blend_done)
+            self.push(ctx, parity)
+            self.barrier(3 + parity)  # every view's slot is complete on this rank
+            self.expand(ctx, means3D, parity)
+        self.allreduce_rest_()
+        main.wait_stream(self.side)
+
+    def render_step(self, ctx, scene: Dict[str, torch.Tensor], cam, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor,
+                    parity: int) -> None:
+        """One view per rank: forward + backward of `cam` on ctx, then the factored exchange; afterwards ctx's
+        parameter gradients (ctx.param_grads()) hold the window's sum on every rank. `self.cam_centres` [world,3] must
+        hold the camera centres of the step's views in rank order before the step runs (it is read on the device, so a
+        captured step can be replayed with new cameras). Nothing in here waits for the GPU. Steps alternate `parity`
+        (the gather slots are double-buffered: a rank may be pushing step k+1 while a peer still expands step k)."""
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            ctx.prepare_backward()
+        ctx.forward(scene, cam)
+        main.wait_stream(self.side)
+        ctx.backward(dL_dcolor, dL_dacc, accumulators_zeroed=True, part="blend")
+        blend_done = torch.cuda.Event()
+        blend_done.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(blend_done)
+            self.push(ctx, parity)
+            self.barrier(3 + parity)
+            self.expand(ctx, scene["means3D"], parity)
+        ctx.backward(dL_dcolor, dL_dacc, part="geom", sh_factored=True)
+        self.allreduce_rest_()
+        main.wait_stream(self.side)
+
+
 class WindowStep:
     """One optimisation step over a window of views, sharded over the ranks of `group`.
 

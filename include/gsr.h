@@ -44,7 +44,7 @@ extern "C" {
 #define GSR_API
 #endif
 
-#define GSR_ABI_VERSION 4
+#define GSR_ABI_VERSION 5
 #define GSR_NUM_CHANNELS 3 /* NUM_CHANNELS, include/gs/cuda_rasterizer/config.h:15 */
 #define GSR_BLOCK_X 16     /* BLOCK_X, config.h:16 */
 #define GSR_BLOCK_Y 16     /* BLOCK_Y, config.h:17 */
@@ -131,6 +131,15 @@ typedef struct gsr_bwd_args {
 /* with the flag above: the caller already ran gsr_backward_prepare() on these outputs (e.g. on another stream, beside
  * the forward), so gsr_backward() must not clear the accumulated arrays again */
 #define GSR_BWD_ACCUMULATORS_ZEROED 2
+/* dL_dsh is NOT written (the pointer may be NULL): per view, dL_dsh[k][c] = basis_k(dir) * dRGB[c] has rank one, and a
+ * view-sharded window exchanges the three dRGB floats instead of the 48 of the row and rebuilds the sum of the rows on
+ * every rank (gsr_window_push_rgb / gsr_window_expand_sh below). Everything else is computed as usual. */
+#define GSR_BWD_SH_FACTORED 4
+/* one half of the backward per call, so that a caller can start work that needs only the blend backward's outputs
+ * (dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor are complete after it) beside the per-Gaussian half:
+ * GSR_BWD_ONLY_BLEND = clearing of the accumulators + blend backward; GSR_BWD_ONLY_GEOM = the per-Gaussian kernel. */
+#define GSR_BWD_ONLY_BLEND 8
+#define GSR_BWD_ONLY_GEOM 16
 
 /* Debug / parity view of the opaque buffers. Strides are in BYTES; count = number of elements. */
 typedef struct gsr_array_view {
@@ -247,6 +256,31 @@ GSR_API int gsr_window_allreduce_multimem_rows(void* multicast_buffer, size_t n_
                                                const gsr_window_rows* rows, void* stream);
 GSR_API int gsr_window_allreduce_p2p_rows(void* const* peer_buffers, size_t n_floats, int rank, int world, int phase,
                                           const gsr_window_rows* rows, void* stream);
+
+/* Factored exchange of the SH gradients (csrc/window_factored.cu; no counterpart in the reference). Per view the 48-float
+ * dL_dsh row of a Gaussian is basis(dir_v) (x) dRGB_v (src/cuda_rasterizer/backward.cu:56-135), dir_v follows from the
+ * replicated means and the view's camera centre, so the ranks exchange dRGB_v (3 floats per rendered Gaussian and view,
+ * gathered) and all-reduce only the other 11 parameter-gradient floats; every rank then rebuilds the sum of the rows.
+ *   gsr_window_barrier: barrier across the ranks on `stream`, a kernel over flag words in peer-mapped memory:
+ *     peer_signals[r] = rank r's pad of GSR_WINDOW_BARRIER_CHANNELS x 16 uint32, zero-initialised once. Replay-safe
+ *     (every flag returns to 0): can be captured in a CUDA graph. Different channels may be in flight on different
+ *     streams at once.
+ *   gsr_window_push_rgb: after the blend backward of this rank's view (GSR_BWD_ONLY_BLEND): writes the view's dRGB
+ *     (dL_dcolor with the channels the forward clamped zeroed; culled Gaussians are skipped) and its visibility words
+ *     into the view's slot of EVERY rank: dst_rgb[r] / dst_vis[r], r < world, are the slot as mapped for rank r (plain
+ *     peer stores), or, with multicast != 0, dst_rgb[0] / dst_vis[0] are its multicast mapping (multimem.st). A slot is
+ *     gsr_window_slot_floats(P) floats (16-byte aligned) + ceil(P / 32) words. geom_buffer: of the view's forward.
+ *   gsr_window_expand_sh: dL_dsh[P,16,3] = sum over v < n_views (in that order, identical on every rank) of
+ *     basis(normalize(means3D - cam_pos[v])) (x) rgb_slots[v], skipping views whose visibility bit is clear; rows no
+ *     view rendered are written as zeros. cam_pos: DEVICE array [n_views,3]; rgb_slots / vis_slots: host arrays of
+ *     n_views device pointers. n_views <= 16, M must be 16. */
+#define GSR_WINDOW_BARRIER_CHANNELS 8
+GSR_API size_t gsr_window_slot_floats(int P);
+GSR_API int gsr_window_barrier(void* const* peer_signals, int rank, int world, int channel, void* stream);
+GSR_API int gsr_window_push_rgb(char* geom_buffer, int P, const int* radii, const float* dL_dcolor,
+                                void* const* dst_rgb, void* const* dst_vis, int world, int multicast, void* stream);
+GSR_API int gsr_window_expand_sh(int P, int D, int M, int n_views, const float* means3D, const float* cam_pos,
+                                 const void* const* rgb_slots, const void* const* vis_slots, float* dL_dsh, void* stream);
 
 /* The two GPU steps right behind the rasterizer in GS-LIVM's mapping iteration, fused.
  *

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(built_library):
         assert hasattr(built_library, name), f"{name} declared in include/gsr.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in _lib.SYMBOLS"
     from gs_livm_b200 import _lib
-    assert built_library.gsr_abi_version() == _lib.ABI_VERSION == 4
+    assert built_library.gsr_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_ctypes_struct_layout_matches_the_library(built_library):

@@ -188,7 +188,7 @@ def test_raster_context_matches_operator_and_reuses_memory(built_library, cuda_d
         for n in helpers.GRAD_NAMES:
             assert_grad(n, g[n].cpu().numpy().reshape(raw[n].shape), raw[n])
     flat = ctx.param_grads()
-    assert flat.numel() == 59 * case.P and flat.data_ptr() == ctx.grads["dL_dmean3D"].data_ptr()
+    assert flat.numel() == 59 * case.P and flat.data_ptr() == ctx.grads["dL_dsh"].data_ptr()
     ctx.stage_timing(True)
     ctx.forward(sc, cam)
     ctx.backward(case.dL_dcolor.to(dev), case.dL_dacc.to(dev))

@@ -1,0 +1,79 @@
+"""The factored exchange of the SH gradients (csrc/window_factored.cu, window.FactoredExchange) on ONE GPU: the rows it
+rebuilds from the pushed dRGB must be the rows geom_bwd writes — bit for bit (up to the sign of a zero) with one view (same basis, same product),
+and the exact float sum of the two views' rows with two (what a dense two-rank all-reduce computes). The multi-rank side
+(peer stores / multicast, barriers, the 11-float all-reduce) is covered by tests/test_window_nccl_gpu.py on >= 2 GPUs
+and by bench.py's exchange_max_err."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(P, dev, n_views, seed=20241017 + 5, deg=3):
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import engine, scene, window
+    sc_cpu = scene.make_scene(P, seed, deg)
+    sc = {k: v.to(dev) for k, v in sc_cpu.items()}
+    cams = [scene.scene_camera(sc_cpu, i, scene.NTU).to(dev) for i in (0, 3)]
+    H, W = cams[0].height, cams[0].width
+    ex = window.FactoredExchange(P, 16, dev, n_views=n_views)
+    ctx = engine.RasterContext(P, 16, W, H, dev, deg, grad_flat=ex.flat)
+    g = torch.Generator().manual_seed(seed + 1)
+    dC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
+    dS = (torch.randn((1, H, W), generator=g) / (H * W)).to(dev)
+    return sc, cams, ex, ctx, dC, dS
+
+
+@pytest.mark.parametrize("P", [50_000, 49_999, 130])
+def test_one_view_rows_equal_geom_bwd_bit_for_bit(P, built_library, cuda_device):
+    dev = cuda_device
+    sc, cams, ex, ctx, dC, dS = _setup(P, dev, 1)
+    ex.cam_centres[0].copy_(cams[0].camera_center)
+    ctx.grad_flat.fill_(float("nan"))
+    ex.render_step(ctx, sc, cams[0], dC, dS, parity=0)
+    torch.cuda.synchronize()
+    got = {n: ctx.grads[n].clone() for n in ("dL_dsh", "dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcov3D")}
+    assert int((ctx.radii > 0).sum()) > P // 10 or P < 1000
+    # the dense per-Gaussian half on the SAME accumulated inputs (no second blend backward: float atomics differ per run)
+    ctx.backward(dC, dS, part="geom")
+    torch.cuda.synchronize()
+    for n, t in got.items():
+        np.testing.assert_array_equal(t.cpu().numpy(), ctx.grads[n].cpu().numpy(), err_msg=n)  # (-0 == +0)
+    assert float(ctx.grads["dL_dsh"].abs().max()) > 0
+    # ... and the whole thing replayed from a CUDA graph, on the other parity
+    frame = ctx.capture(lambda: ex.render_step(ctx, sc, cams[0], dC, dS, parity=1))
+    ctx.grad_flat.fill_(float("nan"))
+    frame.replay()
+    torch.cuda.synchronize()
+    assert ctx.check()
+    rows = ctx.grads["dL_dsh"].clone()
+    ctx.backward(dC, dS, part="geom")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(rows.cpu().numpy(), ctx.grads["dL_dsh"].cpu().numpy())
+
+
+def test_two_views_rows_are_the_float_sum_of_the_views_rows(built_library, cuda_device):
+    dev = cuda_device
+    P = 60_000
+    sc, cams, ex, ctx, dC, dS = _setup(P, dev, 2)
+    dense, vis = [], []
+    for v, cam in enumerate(cams):
+        ex.cam_centres[v].copy_(cam.camera_center)
+        ctx.forward(sc, cam)
+        ctx.backward(dC, dS, part="blend")
+        ex.push(ctx, parity=0, view=v)
+        ctx.backward(dC, dS, part="geom")  # dense rows of this view, from the same accumulators
+        torch.cuda.synchronize()
+        dense.append(ctx.grads["dL_dsh"].clone())
+        vis.append((ctx.radii > 0).clone())
+    assert int((vis[0] & vis[1]).sum()) > 1000 and int((vis[0] ^ vis[1]).sum()) > 1000, "views must overlap partly"
+    ctx.grads["dL_dsh"].fill_(float("nan"))
+    ex.expand(ctx, sc["means3D"], parity=0)
+    torch.cuda.synchronize()
+    want = dense[0] + dense[1]
+    np.testing.assert_array_equal(ctx.grads["dL_dsh"].cpu().numpy(), want.cpu().numpy())
+    none = ~(vis[0] | vis[1])
+    assert int(none.sum()) > 0 and float(ctx.grads["dL_dsh"][none].abs().max()) == 0.0
