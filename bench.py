@@ -1,31 +1,44 @@
 """bench.py — forward+backward rendered frames/s of the rasterizer hot path (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-cpu-baseline] [--no-sweep]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 Workload (configs[1] of BASELINE.json): a 1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480,
-one "step" = one forward (C+D+S) + one backward of one keyframe view. With N ranks every rank renders its own
-view of the 8-pose keyframe window per step (weak scaling: the per-GPU work is fixed) and the per-Gaussian
-parameter gradients (59 floats = 236 B per Gaussian) are summed with one NCCL all-reduce inside the step.
+one "step" = one forward (C+D+S) + one backward of one keyframe view. With N ranks every rank renders its own view
+of the 8-pose keyframe window per step (weak scaling: the per-GPU work is fixed) and the per-Gaussian parameter
+gradients are summed inside the step by the factored exchange (gs_livm_b200.window.FactoredExchange: 3 dRGB floats
+per rendered Gaussian pushed to every rank under geom_bwd, an 11-float all-reduce, the SH rows rebuilt locally).
 
-Printed (rank 0, ONE JSON line):
-  value     whole-job frames/s with everything resident in HBM, timed with CUDA events over K steps at the
-            C-ABI level (gs_livm_b200.engine.RasterContext: persistent scratch arenas, gradient zero-fill
-            included), max over ranks;
-  e2e       the same metric through the public tensor-level operator (GaussianRasterizer + autograd) with the
-            step's host inputs (camera + target image, pinned memory) copied host->device and the loss copied
-            device->host inside the timed region;
-  roofline  the dominant kernel's algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json, plus the same
-            for every stage under "stages";
+Printed (rank 0, ONE JSON line), both arms with the IDENTICAL `config` dict:
+  value       whole-job frames/s with everything resident in HBM, CUDA events over K steps at the C-ABI level
+              (engine.RasterContext: persistent scratch, gradient zero-fill included; captured CUDA graphs), max over
+              ranks;
+  e2e         the same metric through the repo's public tensor-level operator (GaussianRasterizer + autograd) with the
+              step's host inputs (camera + target image, pinned) copied host->device and the loss copied device->host
+              inside the timed region (host wall clock);
+  e2e_dropin  the same step through the reference's UNCHANGED operator files (GaussianRasterizer::forward + LibTorch
+              autograd: src/gs/rasterizer.cu, src/gs/rasterize_points.cu) re-linked to libgsr_b200.so
+              (oracle/_ref/gsr_dropin_ext.so) — what a GS-LIVM user gets by swapping the library, host wall clock;
+  parity_check  (outside the timed region) pose 0's outputs against the reference CUDA rasterizer: integer stages
+              bit-exact, C/D/S and gradient errors; exchange_max_err (N > 1): the factored exchange against the NCCL
+              all-reduce of the dense gradients;
+  roofline    the dominant kernel against MEASURED_PEAKS.json + every stage under "stages", each with the bound ncu
+              shows for it, its HBM fraction on algorithmic AND on measured DRAM bytes, and for the blends the
+              executed-work FP32 fraction from the kernels' own pair counters;
+  step_incl_optim  the window step INCLUDING the fused image loss and the fused Adam step (t_a on its own);
+  sweep       the other workloads (config 1: 200 K; the shipped 376x240 SH-0 setting; config 4: 5 M @ 1920x1200), ms per
+              step of this arm — not the headline;
   cpu_baseline  Oracle B (scalar CPU port, all host cores for the blend loops) on one frame of the same workload.
-`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/gsr_ref_ext.so, compiled for
-sm_100a from /root/reference) on the same GPU, scene and step — that is the "reference CUDA rasterizer" the
-north star's >=10x target names; the reference has no CPU implementation of this path.
+`--impl reference` times the UNMODIFIED reference CUDA rasterizer (oracle/_ref/gsr_ref_ext.so, compiled for sm_100a
+from /root/reference) on the same GPU, scene and step — the "reference CUDA rasterizer" the north star's >=10x target
+names (the reference has no CPU implementation of this path); its `e2e` is the reference's own unchanged operator on
+its own kernels (oracle/_ref/gsr_refop_ext.so), host buffers, host wall clock.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -43,9 +56,22 @@ P_GAUSS = 1_000_000
 SH_DEGREE = 3
 SEED = 20241017 + 2
 WINDOW = 8
-MY_KERNELS_PER_STEP = 10  # preprocess, tile_scan, scatter_instances, partition_long, segment_sort x2 (depth buckets, short lists), block_lists, blend_fwd, blend_bwd, geom_bwd
+METRIC = "fwd+bwd rendered frames/s (752x480, C+D+S)"
+WORKLOAD = ("1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480 forward+backward (BASELINE.json "
+            "configs[1]); one keyframe view per GPU per step, 8-pose window")
+# kernels of ours per step: preprocess, tile_scan, scatter_instances, partition_long, segment_sort x2 (depth buckets,
+# short lists), block_lists, blend_fwd, blend_bwd, geom_bwd; with N > 1 also push_rgb, expand_sh, the all-reduce
+# kernel(s) and the barrier kernels of the factored exchange
+MY_KERNELS_PER_STEP = 10
 LIB_KERNELS_PER_STEP = ("none (cub only behind the parity-test knob sort_device); cudaMemsetAsync: tile counters + the "
                         "4 accumulated gradient arrays (44 B/Gaussian)")
+# what bounds each stage, from the committed ncu captures (profiles/r2_step_ncu_summary.txt)
+STAGE_BOUND = {"preprocess": "issue", "scan": "latency", "duplicate": "latency", "sort": "latency", "finalize": "latency",
+               "blend_fwd": "issue", "blend_bwd": "issue", "geom_bwd": "hbm"}
+# not-headline workloads of the sweep: (name, P, seed, sh degree, intrinsics name, scale, heavy overlap, close-up, steps)
+SWEEP = (("config1_200k_752x480_sh3", 200_000, 20241017 + 1, 3, "NTU", 1.0, False, False, 20),
+         ("shipped_ntu_376x240_sh0", 200_000, 20241017 + 1, 0, "NTU", 0.5, False, False, 20),
+         ("config4_5m_1920x1200_heavy", 5_000_000, 20241017 + 4, 3, "BOTANIC", 1.0, True, True, 5))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -102,8 +128,6 @@ def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: keep it to ONE JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     elif n_gpus > 1:
@@ -141,6 +165,53 @@ def build_workload(dev):
     return sc_cpu, sc, cams_cpu, cams, dC, dS
 
 
+def bench_config(W, H, R_per_pose):
+    """The `config` object: byte-identical in both arms (everything arm-specific goes under `details`)."""
+    return {"workload": WORKLOAD, "P": P_GAUSS, "sh_degree": SH_DEGREE, "width": int(W), "height": int(H),
+            "window_poses": WINDOW, "R_per_pose": [int(r) for r in R_per_pose], "seed": SEED,
+            "l2": "inputs (236 MB of Gaussians + 150 MB of per-frame state) exceed the 126 MB L2; no flush needed"}
+
+
+def host_step_inputs(cams_cpu, H, W):
+    """Pinned host buffers of the end-to-end step: 35 camera floats per pose and two target images."""
+    g = torch.Generator().manual_seed(SEED + 7)
+    targets = [torch.rand((3, H, W), generator=g).pin_memory() for _ in range(2)]
+    cams = [torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
+            for c in cams_cpu]
+    return targets, cams
+
+
+def load_oracle_ext(name: str):
+    """oracle/_ref/<name>.so (prebuilt; the reference's operator files on our library or on its own kernels)."""
+    path = os.path.join(ROOT, "oracle", "_ref", name + ".so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def time_operator_session(ext, sc, cams_cpu, H, W, steps, warmup):
+    """Host wall clock per step of the reference's unchanged GaussianRasterizer::forward + autograd backward
+    (oracle/operator_session.h) with host inputs; -> (ms per step, h2d bytes, last loss)."""
+    tanx, tany = cams_cpu[0].tanfovx, cams_cpu[0].tanfovy
+    sess = ext.OperatorSession(sc["means3D"], sc["opacities"], sc["shs"], sc["scales"], sc["rotations"],
+                               sc["background"], tanx, tany, H, W, SH_DEGREE)
+    targets, hcams = host_step_inputs(cams_cpu, H, W)
+    loss = 0.0
+    for i in range(max(warmup, 3)):
+        loss = sess.step(hcams[i % WINDOW], targets[i % 2])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        loss = sess.step(hcams[i % WINDOW], targets[i % 2])
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    del sess
+    return ms, targets[0].numel() * 4 + hcams[0].numel() * 4, float(loss)
+
+
 def algorithmic_bytes(P, P_v, R, px, tiles, S_c, M=16):
     """SURVEY.md section 8d per-unit figures, restated for OUR data layout where it moves fewer bytes
     (DESIGN.md 'algorithmic bytes'): 48-byte records instead of separate arrays, no cov3D round trip.
@@ -148,17 +219,10 @@ def algorithmic_bytes(P, P_v, R, px, tiles, S_c, M=16):
     P_c = P - P_v
     return {
         "preprocess": (12 + 12 + 16 + 4 + 12 * M + 48 + 1 + 4 + 4) * P_v + (12 + 12 + 8) * P_c,
-        # per-tile binning (tile_sort.cu): tile_scan over the tile counters; scatter = radii + record head per
-        # visible Gaussian in, (depth, id) per instance out; tile_sort = (depth, id) in, key + id + gathered
-        # 48-byte record out, 48-byte record gather in. "finalize" is block_lists: the 16-byte head of every sorted
-        # record in, one 8-byte entry per (instance, 8x4 block) candidate out.
         "scan": (4 + 8 + 4 + 4 + 4) * tiles,
         "duplicate": 4 * P + 20 * P_v + 8 * R,
         "sort": (8 + 8 + 4 + 48 + 48) * R,
         "finalize": 16 * R + 8 * S_c,
-        # sparse blend: per candidate its list entry and its record, one 4-byte hit word per pixel and group of 32
-        # candidates; the backward reads the hit words and, per candidate blended somewhere in its block (bounded by
-        # S_c here), entry + record + id, and commits 9 floats
         "blend_fwd": (8 + 48 + 4) * S_c + 32 * px,
         "blend_bwd": 4 * S_c + (8 + 48 + 4 + 36) * S_c + 28 * px,
         "geom_bwd": (12 + 4 + 12 * M + 1 + 12 + 16 + 12 + 16 + 12 + 12 + 24 + 12 * M + 12 + 16) * P_v + 4 * P_c,
@@ -174,7 +238,7 @@ def blend_flops(c_fwd, c_bwd):
 
 def cpu_baseline(sc_cpu, cam_cpu, dC, dS):
     """Oracle B (CPU port of the path) on ONE frame of the same workload: preprocess + binning single-threaded,
-    blend loops on all host cores. Also returns the pair counters the FP32 roofline needs."""
+    blend loops on all host cores. Also returns the pair counters the reference-equivalent FP32 figure needs."""
     from oracle import cpu
     cores = os.cpu_count() or 1
     osc = cpu.OracleScene(sc_cpu["means3D"], sc_cpu["opacities"], sc_cpu["background"], cam_cpu.viewmatrix,
@@ -221,93 +285,527 @@ def cpu_baseline(sc_cpu, cam_cpu, dC, dS):
 
 
 # ----------------------------------------------------------------------------------------------------------
+def sweep_scene(entry, dev):
+    from gs_livm_b200 import scene
+    name, P, seed, deg, intr_name, scale, heavy, close, steps = entry
+    intr = dict(getattr(scene, intr_name))
+    if scale != 1.0:
+        intr = dict(width=int(intr["width"] * scale), height=int(intr["height"] * scale), fx=intr["fx"] * scale,
+                    fy=intr["fy"] * scale)
+    sc_cpu = scene.make_scene(P, seed, deg, heavy_overlap=heavy)
+    sc = {k: v.to(dev) for k, v in sc_cpu.items()}
+    cam = scene.scene_camera(sc_cpu, 0, intr, close_up=close).to(dev)
+    g = torch.Generator().manual_seed(seed + 1)
+    H, W = cam.height, cam.width
+    dC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
+    dS = (torch.randn((1, H, W), generator=g) / (H * W)).to(dev)
+    return sc, cam, dC, dS, P, deg, steps
+
+
+def sweep_ours(dev):
+    """ms per fwd+bwd step of the not-headline workloads, this arm, captured graph like `value`."""
+    from gs_livm_b200 import engine
+    out = {}
+    for entry in SWEEP:
+        sc, cam, dC, dS, P, deg, steps = sweep_scene(entry, dev)
+        ctx = engine.RasterContext(P, sc["shs"].shape[1], cam.width, cam.height, dev, deg)
+        ctx.forward(sc, cam)
+        ctx.backward(dC, dS)
+        ctx.check()
+        frame = ctx.capture_step(sc, cam, dC, dS)
+        for _ in range(3):
+            frame.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            frame.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ok = ctx.check()
+        out[entry[0]] = {"ms_per_step": round(e0.elapsed_time(e1) / steps, 4), "R": int(ctx.last_rendered), "fits": bool(ok),
+                         "width": cam.width, "height": cam.height, "P": P, "sh_degree": deg}
+        del frame, ctx, sc
+        torch.cuda.empty_cache()
+    return out
+
+
+def sweep_reference(dev):
+    from oracle import ref
+    out = {}
+    for entry in SWEEP:
+        sc, cam, dC, dS, P, deg, steps = sweep_scene(entry, dev)
+        H, W = cam.height, cam.width
+
+        def step():
+            fwd = ref.forward(sc["background"], sc["means3D"], sc["opacities"], sc["scales"], sc["rotations"], sc["shs"],
+                              deg, cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, H, W,
+                              with_state=False)
+            ref.backward(fwd, sc["background"], sc["means3D"], sc["scales"], sc["rotations"], sc["shs"], deg,
+                         cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, dC, dS)
+            return fwd["num_rendered"]
+
+        for _ in range(3):
+            R = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[entry[0]] = {"ms_per_step": round(e0.elapsed_time(e1) / steps, 4), "R": int(R), "fits": True,
+                         "width": W, "height": H, "P": P, "sh_degree": deg}
+        del sc
+        torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+def parity_against_reference(ctx, sc, cam, dC, dS, W, H):
+    """Pose 0 of the bench window, ours (the sync-free path the timed steps use) against the reference CUDA rasterizer
+    (the checker; outside every timed region). Integer stages bit-exact, D/S/final_T bit-exact, C <= 1e-5, gradients
+    in the tests' metric (tests/tolerances.py: |d| <= 1e-4 (|ref| + max|ref|))."""
+    from gs_livm_b200 import debug
+    from oracle import ref
+    import numpy as np
+    ctx.forward(sc, cam)
+    ctx.backward(dC, dS)
+    torch.cuda.synchronize()
+    if not ctx.check():
+        return {"status": "frame did not fit the presized arena"}
+    R = int(ctx.last_rendered)
+    r = ref.forward(sc["background"], sc["means3D"], sc["opacities"], sc["scales"], sc["rotations"], sc["shs"], SH_DEGREE,
+                    cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, H, W, with_state=True)
+    g = ref.backward(r, sc["background"], sc["means3D"], sc["scales"], sc["rotations"], sc["shs"], SH_DEGREE,
+                     cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, dC, dS)
+    torch.cuda.synchronize()
+    b = debug.binning_state(ctx.binning.buf, ctx.num_rendered)
+    im = debug.image_state(ctx.image.buf, W, H)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    eq = lambda a, c: bool(torch.equal(a.reshape(-1), c.reshape(-1).to(a.dtype)))  # noqa: E731
+    biteq = lambda a, c: bool(torch.equal(a.reshape(-1).view(torch.int32), c.reshape(-1).view(torch.int32)))  # noqa: E731
+    out = {"pose": 0, "num_rendered_equal": R == int(r["num_rendered"]),
+           "keys_bit_exact": R == int(r["num_rendered"]) and eq(b["point_list_keys"][:R], r["point_list_keys"][:R]),
+           "point_list_bit_exact": R == int(r["num_rendered"]) and eq(b["point_list"][:R], r["point_list"][:R]),
+           "ranges_bit_exact": eq(im["ranges"][:tiles], r["ranges"][:tiles]),
+           "radii_bit_exact": eq(ctx.radii, r["radii"]),
+           "n_contrib_bit_exact": eq(im["n_contrib"], r["n_contrib"]),
+           "D_bit_exact": biteq(ctx.out_depth, r["out_depth"]), "S_bit_exact": biteq(ctx.out_acc, r["out_acc"]),
+           "C_max_abs_err": float((ctx.out_color - r["out_color"]).abs().max())}
+    names = {"dL_dmean3D": "dL_dmean3D", "dL_dsh": "dL_dsh", "dL_dscale": "dL_dscale", "dL_drot": "dL_drot",
+             "dL_dopacity": "dL_dopacity", "dL_dcov3D": "dL_dcov3D", "dL_dmean2D": "dL_dmean2D", "dL_dcolor": "dL_dcolor"}
+    worst, pure = 0.0, 1.0
+    for n in names:
+        ours, want = ctx.grads[n].reshape(-1).double(), g[n].reshape(-1).double()
+        if n == "dL_dmean2D":  # ours [P,3] with z unused, like the reference's
+            ours, want = ctx.grads[n][:, :2].reshape(-1).double(), g[n].reshape(ctx.P, -1)[:, :2].reshape(-1).double()
+        scale = float(want.abs().max())
+        err = float(((ours - want).abs() / (want.abs() + scale + 1e-300)).max()) if scale > 0 else float(ours.abs().max())
+        worst = max(worst, err)
+        nz = want != 0
+        if bool(nz.any()):
+            pure = min(pure, float(((ours[nz] - want[nz]).abs() <= 1e-4 * want[nz].abs()).double().mean()))
+    out["grad_max_err_rel"] = worst
+    out["grad_pure_relative_fraction_min"] = pure  # smallest fraction, over the tensors, of elements within 1e-4 of THEIR OWN value
+    out["grad_metric"] = "max over the 8 gradient tensors of |ours - ref| / (|ref| + max|ref|); bar 1e-4"
+    out["ok"] = bool(all(v for k, v in out.items() if k.endswith("_bit_exact") or k.endswith("_equal")) and
+                     out["C_max_abs_err"] <= 1e-5 and worst <= 1e-4)
+    del r, g
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, dev):
     import gs_livm_b200  # noqa: F401
-    from gs_livm_b200 import _lib, engine, rasterizer, scene
+    from gs_livm_b200 import _lib, debug, engine, rasterizer, train, window
 
     sc_cpu, sc, cams_cpu, cams, dC, dS = build_workload(dev)
     H, W = cams[0].height, cams[0].width
-    from gs_livm_b200 import window
-    grad_floats = (3 + 16 * 3 + 3 + 4 + 1 + 3 + 4 + 3 + 6) * P_GAUSS  # RasterContext.GRAD_LAYOUT
-    param_floats = (3 + 16 * 3 + 3 + 4 + 1) * P_GAUSS                 # what the window all-reduces: 236 B/Gaussian
-    # dL_dsh (48 floats per Gaussian, behind the 3 floats of dL_dmean3D) is exchanged only for Gaussians some view of
-    # the step rendered: rows of the others are zero on every rank (window.GradExchange, sparse_rows)
-    exchange = window.GradExchange(grad_floats, param_floats, dev,
-                                   sparse_rows=(3 * P_GAUSS, P_GAUSS, 48)) if world > 1 else None
+    exchange = window.FactoredExchange(P_GAUSS, 16, dev) if world > 1 else None
     ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE, grad_flat=exchange.flat if exchange else None)
-    assert ctx.param_grads().numel() == param_floats
 
-    captured_frames = [None] * WINDOW  # one captured forward+backward per pose of the window (RasterContext.capture_step)
+    # step i of rank r renders pose (r + i) % 8; the views of step i, in rank order, are what the exchange sums
+    def pose_of(i, r=rank):
+        return (r + i) % WINDOW
+
+    centres = [torch.stack([cams[pose_of(i, r)].camera_center for r in range(world)]) for i in range(WINDOW)]
+
+    def step_eager(i):
+        cam = cams[pose_of(i)]
+        if exchange is None:
+            ctx.forward(sc, cam)
+            ctx.backward(dC, dS)
+        else:
+            exchange.cam_centres.copy_(centres[i % WINDOW], non_blocking=True)
+            exchange.render_step(ctx, sc, cam, dC, dS, parity=i % 2)
+
+    captured = [None] * WINDOW  # by step index modulo the window
 
     def step_resident(i):
-        k = (rank + i) % WINDOW
-        if captured_frames[k] is not None:
-            captured_frames[k].replay()  # the same launches, recorded once: one host call per step
+        f = captured[i % WINDOW]
+        if f is None:
+            step_eager(i)
         else:
-            ctx.forward(sc, cams[k])
-            ctx.backward(dC, dS)
-        if exchange is not None:
-            exchange.allreduce_(radii=ctx.radii)  # own exchange over peer memory where available, else NCCL
+            if exchange is not None:
+                exchange.cam_centres.copy_(centres[i % WINDOW], non_blocking=True)
+            f.replay()  # the same launches, recorded once: one host call per step
 
     # ---- device-resident timing: W warm-up, K timed steps, CUDA events, max over ranks ----
-    # RasterContext is sync-free after its first frame (gsr_forward_presized): the warm-up also walks the whole
-    # window once so that the binning arena is sized for the view with the most instances.
-    for i in range(max(args.warmup, 3) + WINDOW):
-        step_resident(i)
+    # RasterContext is sync-free after its first frame (gsr_forward_presized): the warm-up walks the whole window once
+    # so that the binning arena is sized for the view with the most instances.
+    R_per_pose = [0] * WINDOW
+    for k in range(WINDOW):  # (no collective in here: every rank sizes its arena for all eight poses)
+        ctx.forward(sc, cams[k])
+        ctx.backward(dC, dS)
         if not ctx.check():
-            ctx.forward(sc, cams[(rank + i) % WINDOW], redo=True)
+            ctx.forward(sc, cams[k], redo=True)
             ctx.check()
+            R_per_pose[k] = int(ctx.num_rendered)
+        else:
+            R_per_pose[k] = int(getattr(ctx, "last_rendered", ctx.num_rendered))
+    for i in range(max(args.warmup, 3)):
+        step_eager(i)
+    if not ctx.check():
+        raise SystemExit("bench: a warm-up frame did not fit the presized binning arena")
     resident_mode = "eager launches"
     if os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
         try:
-            captured_frames[:] = [ctx.capture_step(sc, cams[k], dC, dS) for k in range(WINDOW)]
-            resident_mode = "CUDA-graph replay (RasterContext.capture_step), one graph per pose"
+            for i in range(WINDOW):
+                if exchange is None:
+                    captured[i] = ctx.capture_step(sc, cams[pose_of(i)], dC, dS)
+                else:
+                    exchange.cam_centres.copy_(centres[i])
+                    captured[i] = ctx.capture(lambda i=i: exchange.render_step(ctx, sc, cams[pose_of(i)], dC, dS, parity=i % 2))
+            resident_mode = "CUDA-graph replay, one graph per pose" + (
+                " (render + factored exchange incl. its barriers in the graph)" if exchange else " (RasterContext.capture_step)")
         except Exception as exc:  # capture not possible here: the same launches, issued eagerly
-            captured_frames[:] = [None] * WINDOW
+            captured[:] = [None] * WINDOW
             resident_mode = "eager launches (graph capture failed: %s)" % type(exc).__name__
             torch.cuda.synchronize()
         for i in range(WINDOW):
             step_resident(i)
         if not ctx.check():
             raise SystemExit("bench: a captured frame did not fit the presized binning arena")
-    stage_acc = {n: 0.0 for n in _lib.STAGES}
     barrier_sync(world)
     clk = sample_clocks_start(dev.index or 0) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step_resident(i)
-        if i < 16:  # reading the stage events synchronises; keep it to a few steps and outside the rate below
-            pass
     e1.record()
     barrier_sync(world)
     if not ctx.check():
         raise SystemExit("bench: a timed frame did not fit the presized binning arena; the measurement is void")
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
     clocks = sample_clocks_stop(clk) if rank == 0 else None
-    # per-stage times: a second, separately timed pass with eager launches and the library's stage events (event
-    # reads synchronise, so they stay out of `value`)
-    captured_frames[:] = [None] * WINDOW
+
+    # per-pose step times (N = 1: what bounds the scaling, since at N = 8 every step waits for its slowest view)
+    per_pose_ms = None
+    if world == 1 and captured[0] is not None:
+        per_pose_ms = []
+        for k in range(WINDOW):
+            captured[k].replay()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(5):
+                captured[k].replay()
+            a1.record()
+            torch.cuda.synchronize()
+            per_pose_ms.append(round(a0.elapsed_time(a1) / 5, 4))
+        ctx.check()
+
+    # ---- exchange check (N > 1, outside the timed region): factored result vs NCCL all-reduce of the dense gradients,
+    # both from the SAME accumulated inputs (one blend backward), and bit-identity across the ranks
+    exchange_max_err, exchange_identical, exchange_info = None, None, None
+    if exchange is not None:
+        i = 1
+        exchange.cam_centres.copy_(centres[i])
+        ctx.forward(sc, cams[pose_of(i)])
+        ctx.backward(dC, dS, part="blend")
+        ctx.backward(dC, dS, part="geom")
+        want = ctx.param_grads().clone()
+        dist.all_reduce(want)
+        ctx.grads["dL_dsh"].fill_(float("nan"))
+        ev = torch.cuda.Event()
+        ev.record()
+        exchange.exchange(ctx, sc["means3D"], i % 2, ev,
+                          lambda: ctx.backward(dC, dS, part="geom", sh_factored=True))
+        torch.cuda.synchronize()
+        got = ctx.param_grads()
+        exchange_max_err = float((got - want).abs().max()) / float(want.abs().max())
+        chk = torch.tensor([got.double().sum().item(), got.double().abs().sum().item()], device=dev, dtype=torch.float64)
+        lst = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        exchange_identical = bool(all(torch.equal(x, lst[0]) for x in lst))
+        exchange_info = {"reduce": exchange.reduce_mode, "push": exchange.push_mode}
+        del want
+        ctx.check()
+
+    # ---- per-stage times: a second, separately timed pass with eager launches and the library's stage events (event
+    # reads synchronise, so they stay out of `value`) — the plain single-GPU step on every rank
+    stage_acc = {n: 0.0 for n in _lib.STAGES}
     ctx.stage_timing(True)
-    n_stage = min(args.steps, 20)
+    n_stage = min(args.steps, 16)
+    work = {"pairs_in_boxes": 0, "pairs_blended": 0}
     for i in range(n_stage):
-        step_resident(i)
+        ctx.forward(sc, cams[pose_of(i)])
+        ctx.backward(dC, dS)
         torch.cuda.synchronize()
         for n, v in ctx.stage_times().items():
             stage_acc[n] += v
+        fc = debug.frame_counters(ctx.image.buf, W, H)
+        work["pairs_in_boxes"] += fc["pairs_in_boxes"]
+        work["pairs_blended"] += fc["pairs_blended"]
     ctx.stage_timing(False)
+    ctx.check()
     stage_ms = {n: stage_acc[n] / n_stage for n in _lib.STAGES}
-    R = ctx.num_rendered
+    work = {k: v / n_stage for k, v in work.items()}
+    R = int(ctx.last_rendered)
     P_v = int((ctx.radii > 0).sum())
-    from gs_livm_b200 import debug
     S_c = int(debug.image_state(ctx.image.buf, W, H)["block_count"].sum())  # candidate-list entries of the last frame
 
+    # ---- parity of the benchmarked workload against the reference CUDA rasterizer (rank 0, outside timed regions)
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import ref
+            parity = parity_against_reference(ctx, sc, cams[0], dC, dS, W, H) if ref.available() else {
+                "status": "oracle/_ref/gsr_ref_ext.so missing"}
+        except Exception as exc:  # the checker must never take the measurement down
+            parity = {"status": "checker failed: %s" % (repr(exc)[:200],)}
+
+    # ---- the window step including the optimiser (SURVEY.md 8e/8f-f3): fused image loss -> dL_dC, backward, exchange,
+    # fused Adam over the flat parameter buffer. Learning rates are ZERO so that the timed scene stays the bench scene
+    # (the kernel does all of Adam's reads, arithmetic and writes regardless).
+    optim = None
+    try:
+        optim = time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, centres, pose_of, W, H, train)
+    except Exception as exc:
+        optim = {"status": "failed: %s" % (repr(exc)[:200],)}
+
     # ---- end to end through the public operator: H2D camera + target, autograd, D2H loss ----
+    e2e_ms, e2e_mode, h2d_bytes = time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer)
+
+    if rank != 0:
+        return None
+    # ---- the reference's unchanged operator files on our library (N = 1 only: the reference has no multi-GPU path)
+    dropin = None
+    if world == 1:
+        ext = load_oracle_ext("gsr_dropin_ext")
+        if ext is None or not hasattr(ext, "OperatorSession"):
+            dropin = {"status": "oracle/_ref/gsr_dropin_ext.so missing (make -C oracle dropin)"}
+        else:
+            torch.cuda.empty_cache()
+            ms, hb, loss = time_operator_session(ext, sc, cams_cpu, H, W, args.steps, args.warmup)
+            dropin = {"value": 1e3 / ms, "unit": "frames/s", "ms_per_step": ms, "h2d_bytes_per_step": hb,
+                      "d2h_bytes_per_step": 8, "clock": "host wall clock",
+                      "path": "the reference's UNCHANGED src/gs/rasterizer.cu + src/gs/rasterize_points.cu "
+                              "(GaussianRasterizer::forward, _RasterizeGaussians autograd node: resize_ allocations, 9 "
+                              "zero-filled gradient tensors, torch::cuda::synchronize, loss.item) linked to "
+                              "libgsr_b200.so: oracle/operator_session.h via oracle/_ref/gsr_dropin_ext.so"}
+
+    # ---- roofline + CPU baseline (rank 0 only) ----
+    hbm_peak, peak_src, sm_max_mhz = measured_peaks()
+    px, tiles = H * W, ((W + 15) // 16) * ((H + 15) // 16)
+    alg = algorithmic_bytes(P_GAUSS, P_v, R, px, tiles, S_c)
+    cpu_base, c_fwd, c_bwd = None, None, None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base, c_fwd, c_bwd, _ = cpu_baseline(sc_cpu, cams_cpu[0], dC, dS)
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_peak_tf = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+    stages = {}
+    for n in _lib.STAGES:
+        t = stage_ms[n] * 1e-3
+        if t <= 0:
+            continue  # the stage did not run
+        ach = alg[n] / t / 1e9
+        st = {"us": round(stage_ms[n] * 1e3, 1), "bound": STAGE_BOUND[n], "alg_bytes": int(alg[n]),
+              "achieved_gbs": round(ach, 1), "frac_hbm": round(ach / hbm_peak, 4)}
+        if isinstance(traffic.get(n), (int, float)):
+            st["dram_bytes_ncu"] = int(traffic[n])
+            st["frac_hbm_dram"] = round(traffic[n] / t / 1e9 / hbm_peak, 4)
+        stages[n] = st
+    # executed work of the sparse blends, from the kernels' own counters: every pair inside a candidate's box costs the
+    # forward the power + exp + min (23 flop, 1 MUFU), every blended pair the 16 flop of the recurrence and updates; the
+    # backward re-evaluates alpha for every blended pair (23) and does the reference's 81 flop of gradient arithmetic
+    ex_fwd = 23.0 * work["pairs_in_boxes"] + 16.0 * work["pairs_blended"]
+    ex_bwd = (23.0 + 81.0) * work["pairs_blended"]
+    for n, fl in (("blend_fwd", ex_fwd), ("blend_bwd", ex_bwd)):
+        tf = fl / (stage_ms[n] * 1e-3) / 1e12
+        stages[n].update({"executed_flops": fl, "executed_tflops": round(tf, 3), "frac_fp32_executed": round(tf / fp32_peak_tf, 4),
+                          "pairs_in_boxes": work["pairs_in_boxes"], "pairs_blended": work["pairs_blended"]})
+    if c_fwd is not None:
+        f_fwd, f_bwd = blend_flops(c_fwd, c_bwd)
+        for n, fl in (("blend_fwd", f_fwd), ("blend_bwd", f_bwd)):
+            tf = fl / (stage_ms[n] * 1e-3) / 1e12
+            stages[n].update({"ref_equiv_flops": fl, "ref_equiv_tflops": round(tf, 3),
+                              "ref_equiv_note": "the REFERENCE's pair counts (every pixel x tile-list pair) over our time: "
+                                                "a speed-up restated, not pipe utilisation"})
+    dominant = max(_lib.STAGES, key=lambda n: stage_ms[n])
+    d = stages[dominant]
+    roofline = {"kernel": dominant, "bound": d["bound"], "achieved": d["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": d["frac_hbm"], "traffic": d.get("dram_bytes_ncu"), "peak_source": peak_src,
+                "fp32_peak_tflops": round(fp32_peak_tf, 1),
+                "note": "bound per stage from ncu (profiles/): 'issue' = instruction-issue bound (FP32/ALU pipes and "
+                        "LSU), 'latency' = dependent chains / few resident CTAs, 'hbm' = DRAM bandwidth. achieved/peak/"
+                        "frac are HBM figures on algorithmic bytes for every stage; the blends also carry "
+                        "frac_fp32_executed (peak = SMs x 128 lanes x 2 x max SM clock)",
+                "stages": stages}
+    frames = args.steps * world
+    launches = MY_KERNELS_PER_STEP  # + per chunk: push, PUSHED wait, expansion, geom_bwd, all-reduce kernel(s); + DONE wait
+    if exchange:
+        launches += 3 * len(exchange.chunks) + (1 if exchange.reduce_mode == "multimem" else 2) + 1
+    out = {
+        "metric": METRIC, "value": frames / (ms_total * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(W, H, R_per_pose),
+        "details": {"P_visible_last": P_v, "R_last": R, "block_candidates_last": S_c, "launch": resident_mode,
+                    "parallelism": "view-sharded window, replicated Gaussians" + (
+                        "; factored exchange per step: 12 B x rendered Gaussians pushed to every rank in %d chunks (%s) "
+                        "under geom_bwd, all-reduce of 44 B x Gaussians rendered by some view (%s), SH rows rebuilt "
+                        "locally chunk by chunk" % (
+                            len(exchange.chunks), exchange.push_mode, exchange.reduce_mode) if exchange else ""),
+                    "library_kernels": LIB_KERNELS_PER_STEP, "per_pose_ms": per_pose_ms},
+        "clocks": clocks,
+        "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "clock": "host wall clock",
+                "path": "GaussianRasterizer(settings, arena=RenderArena) (tensor-level mirror of the reference operator, "
+                        "persistent scratch, sync-free forward) + torch autograd + L1 loss; "
+                        "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream; "
+                        "launched as: " + e2e_mode},
+        "e2e_dropin": dropin,
+        "parity_check": parity,
+        "exchange_max_err": exchange_max_err, "exchange_ranks_identical": exchange_identical, "exchange": exchange_info,
+        "step_incl_optim": optim,
+        "gpu_launches": launches * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu_base,
+    }
+    if world == 1 and not args.no_sweep:
+        try:
+            del ctx
+            torch.cuda.empty_cache()
+            out["sweep"] = sweep_ours(dev)
+        except Exception as exc:
+            out["sweep"] = {"status": "failed: %s" % (repr(exc)[:200],)}
+    return out
+
+
+def time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, centres, pose_of, W, H, train):
+    """forward -> fused image loss (gsr_image_loss: L1 + 0.2 DSSIM, dL_dC) -> backward -> exchange -> fused Adam
+    (gsr_adam_step) over one flat parameter buffer laid out like the gradient buffer; captured per pose. -> dict."""
+    from gs_livm_b200 import engine
+    P = P_GAUSS
+    at, _, param_floats, sh_floats = engine.grad_layout(P, 16)
+    flat_p = torch.zeros(param_floats, dtype=torch.float32, device=dev)
+    views = {"shs": ("dL_dsh", (P, 16, 3)), "means3D": ("dL_dmean3D", (P, 3)), "scales": ("dL_dscale", (P, 3)),
+             "rotations": ("dL_drot", (P, 4)), "opacities": ("dL_dopacity", (P, 1))}
+    scp = dict(sc)
+    for name, (gname, shape) in views.items():
+        off, w = at[gname]
+        v = flat_p[off:off + w * P].view(shape)
+        v.copy_(sc[name].reshape(shape))
+        scp[name] = v if name != "opacities" else v.view(sc["opacities"].shape)
+    groups = [(at[g][0], at[g][1] * P, 0.0) for g in ("dL_dsh", "dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity")]
+    adam = train.FusedAdam(flat_p, groups)
+    loss_fn = train.ImageLoss(W, H, dev, lambda_dssim=0.2)
+    g = torch.Generator().manual_seed(SEED + 9)
+    target = torch.rand((3, H, W), generator=g).to(dev)
+    dS0 = torch.zeros((1, H, W), device=dev)
+    step_no = [0]
+
+    def body(i):
+        cam = cams[pose_of(i)]
+        main = torch.cuda.current_stream(dev)
+        if exchange is None:
+            ctx.forward(scp, cam)
+            _, dimg = loss_fn(ctx.out_color, target)
+            ctx.backward(dimg, dS0)
+        else:
+            side = exchange.side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ctx.prepare_backward()
+            ctx.forward(scp, cam)
+            _, dimg = loss_fn(ctx.out_color, target)
+            main.wait_stream(side)
+            ctx.backward(dimg, dS0, accumulators_zeroed=True, part="blend")
+            ev = torch.cuda.Event()
+            ev.record(main)
+            exchange.exchange(ctx, scp["means3D"], i % 2, ev,
+                              lambda: ctx.backward(dimg, dS0, part="geom", sh_factored=True))
+
+    # Adam's step count is a kernel argument: the optimiser step is launched eagerly behind the captured render
+    def run(i, frames):
+        if exchange is not None:
+            exchange.cam_centres.copy_(centres[i % WINDOW], non_blocking=True)
+        if frames[i % WINDOW] is not None:
+            frames[i % WINDOW].replay()
+        else:
+            body(i)
+        step_no[0] += 1
+        adam.step(ctx.param_grads())
+
+    frames = [None] * WINDOW
+    for i in range(WINDOW):
+        run(i, frames)
+    if not ctx.check():
+        return {"status": "a frame did not fit the presized arena"}
+    mode = "eager"
+    if os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
+        try:
+            for i in range(WINDOW):
+                if exchange is not None:
+                    exchange.cam_centres.copy_(centres[i])
+                frames[i] = ctx.capture(lambda i=i: body(i))
+            mode = "graph per pose + eager Adam launch"
+        except Exception:
+            frames = [None] * WINDOW
+            torch.cuda.synchronize()
+    for i in range(WINDOW):
+        run(i, frames)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run(i, frames)
+    e1.record()
+    barrier_sync(world)
+    ok = ctx.check()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
+    # the two added pieces on their own
+    torch.cuda.synchronize()
+    a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a0.record()
+    for _ in range(10):
+        adam.step(ctx.param_grads())
+    a1.record()
+    for _ in range(10):
+        loss_fn(ctx.out_color, target)
+    a2.record()
+    torch.cuda.synchronize()
+    return {"value": world / (ms * 1e-3), "unit": "frames/s", "ms_per_step": round(ms, 4), "fits": bool(ok),
+            "t_adam_ms": round(a0.elapsed_time(a1) / 10, 4), "t_loss_ms": round(a1.elapsed_time(a2) / 10, 4),
+            "launch": mode,
+            "note": "forward + gsr_image_loss (L1 + 0.2 DSSIM -> dL_dC) + backward%s + gsr_adam_step over 59 floats per "
+                    "Gaussian (flat buffer, 6 groups' layout, eps 1e-15); learning rates 0 so the timed scene stays the "
+                    "bench scene; parameters are the activated values (activation fusion, SURVEY 8f-f1, is not built)"
+                    % (" + factored exchange" if exchange else "")}
+
+
+def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer):
+    """The step through gs_livm_b200.rasterizer (tensor-level mirror of the reference operator) with host inputs."""
     leaves = {k: sc[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
     means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-    host_targets = [torch.rand((3, H, W)).pin_memory() for _ in range(2)]
-    host_cams = [torch.cat([c.viewmatrix.reshape(-1), c.projmatrix.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
-                 for c in cams_cpu]
+    host_targets, host_cams = host_step_inputs(cams_cpu, H, W)
     h2d_bytes = host_targets[0].numel() * 4 + host_cams[0].numel() * 4
     loss_host = torch.zeros(1).pin_memory()
 
@@ -354,7 +852,6 @@ def run_ours(args, rank, world, dev):
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
     captured = [None, None]
-
     cam_stage_np, loss_np = cam_stage.numpy(), loss_host.numpy()  # same (pinned) memory, without torch's per-op overhead
     host_cams_np = [c.numpy() for c in host_cams]
 
@@ -384,7 +881,7 @@ def run_ours(args, rank, world, dev):
         arena.capacity = max(caps)
     e2e_mode = "eager launches"
     # the step is captured once and replayed; with several GPUs the graph contains the NCCL all-reduce of the
-    # parameter-gradient span (validated on this pool at N = 2 and N = 8). GSR_BENCH_GRAPH=0: eager launches.
+    # parameter-gradient span. GSR_BENCH_GRAPH=0: eager launches.
     if os.environ.get("GSR_BENCH_GRAPH", "1") != "0":
         try:
             for j in range(2):
@@ -401,72 +898,7 @@ def run_ours(args, rank, world, dev):
         step_e2e(i)
     barrier_sync(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
-
-    if rank != 0:
-        return None
-    # ---- roofline + CPU baseline (rank 0 only) ----
-    hbm_peak, peak_src, sm_max_mhz = measured_peaks()
-    px, tiles = H * W, ((W + 15) // 16) * ((H + 15) // 16)
-    alg = algorithmic_bytes(P_GAUSS, P_v, R, px, tiles, S_c)
-    cpu_base, c_fwd, c_bwd = None, None, None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu_base, c_fwd, c_bwd, _ = cpu_baseline(sc_cpu, cams_cpu[0], dC, dS)
-    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    fp32_peak_tf = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-    stages = {}
-    for n in _lib.STAGES:
-        t = stage_ms[n] * 1e-3
-        ach = alg[n] / t / 1e9 if t > 0 else 0.0
-        if t <= 0:
-            continue  # the stage did not run
-        stages[n] = {"us": round(stage_ms[n] * 1e3, 1), "alg_bytes": int(alg[n]), "achieved_gbs": round(ach, 1),
-                     "frac_hbm": round(ach / hbm_peak, 4)}
-    if c_fwd is not None:
-        f_fwd, f_bwd = blend_flops(c_fwd, c_bwd)
-        for n, fl in (("blend_fwd", f_fwd), ("blend_bwd", f_bwd)):
-            tf = fl / (stage_ms[n] * 1e-3) / 1e12
-            stages[n].update({"ref_flops": fl, "achieved_tflops": round(tf, 3), "frac_fp32": round(tf / fp32_peak_tf, 4)})
-    dominant = max(_lib.STAGES, key=lambda n: stage_ms[n])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(dominant)
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": stages[dominant]["achieved_gbs"], "peak": hbm_peak,
-                "unit": "GB/s", "frac": stages[dominant]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
-                "note": "blend kernels are FP32/latency-bound, not HBM-bound: see stages[*].frac_fp32 (peak %.1f "
-                        "TFLOP/s = SMs x 128 lanes x 2 x max SM clock); preprocess/geom_bwd are the HBM-bound stages"
-                        % fp32_peak_tf,
-                "stages": stages}
-    frames = args.steps * world
-    out = {
-        "metric": "fwd+bwd rendered frames/s (752x480, C+D+S)", "value": frames / (ms_total * 1e-3), "unit": "frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480 forward+backward "
-                               "(BASELINE.json configs[1]); one keyframe view per GPU per step, 8-pose window",
-                   "P": P_GAUSS, "P_visible": P_v, "R": R, "block_candidates": S_c, "sh_degree": SH_DEGREE, "width": W, "height": H,
-                   "parallelism": "view-sharded window, replicated Gaussians" + (
-                       ", all-reduce of 236 B/Gaussian per step: %s%s" % (
-                           {"multimem": "own NVSwitch-multicast kernel (multimem.ld_reduce/st)",
-                            "p2p": "own two-shot peer-to-peer kernels", "nccl": "NCCL"}[exchange.mode],
-                           "; calibration ms " + json.dumps(getattr(exchange, "calibration_ms", {}))
-                           if hasattr(exchange, "calibration_ms") else "") if world > 1 else ""),
-                   "launch": resident_mode,
-                   "l2": "inputs (236 MB of Gaussians + 150 MB of per-frame state) exceed the 126 MB L2; no flush needed",
-                   "library_kernels": LIB_KERNELS_PER_STEP},
-        "clocks": clocks,
-        "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
-                "path": "GaussianRasterizer(settings, arena=RenderArena) (tensor-level mirror of the reference operator, "
-                        "persistent scratch, sync-free forward) + torch autograd + L1 loss; "
-                        "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream; "
-                        "launched as: " + e2e_mode},
-        "gpu_launches": MY_KERNELS_PER_STEP * args.steps,
-        "roofline": roofline,
-        "cpu_baseline": cpu_base,
-    }
-    return out
+    return e2e_ms, e2e_mode, h2d_bytes
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -489,8 +921,9 @@ def run_reference(args, rank, world, dev):
                      cam.viewmatrix, cam.projmatrix, cam.camera_center, cam.tanfovx, cam.tanfovy, dC, dS)
         return fwd["num_rendered"]
 
+    R_per_pose = [int(step(k)) for k in range(WINDOW)]
     for i in range(max(args.warmup, 3)):
-        R = step(i)
+        step(i)
     torch.cuda.synchronize()
     clk = sample_clocks_start(dev.index or 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -502,22 +935,42 @@ def run_reference(args, rank, world, dev):
     ms = e0.elapsed_time(e1)
     clocks = sample_clocks_stop(clk)
     fps = args.steps / (ms * 1e-3)
-    return {
-        "impl": "reference", "metric": "fwd+bwd rendered frames/s (752x480, C+D+S)", "value": fps, "unit": "frames/s",
+    # end to end: the reference's own unchanged operator on its own kernels, host inputs, host wall clock
+    e2e = {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+           "path": "gsr_refop_ext.so missing: repeats `value`"}
+    ext = load_oracle_ext("gsr_refop_ext")
+    if ext is not None and hasattr(ext, "OperatorSession"):
+        torch.cuda.empty_cache()
+        oms, hb, _ = time_operator_session(ext, sc, cams_cpu, H, W, args.steps, args.warmup)
+        e2e = {"value": 1e3 / oms, "unit": "frames/s", "h2d_bytes_per_step": hb, "d2h_bytes_per_step": 8,
+               "ms_per_step": oms, "clock": "host wall clock",
+               "path": "the reference's own operator, unchanged, on its own kernels (GaussianRasterizer::forward + LibTorch "
+                       "autograd backward, oracle/operator_session.h via oracle/_ref/gsr_refop_ext.so): camera + target "
+                       "H2D, loss.item() D2H per step"}
+    out = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1M-Gaussian synthetic NTU-VIRAL-shaped scene, SH degree 3, 752x480 forward+backward "
-                               "(BASELINE.json configs[1])", "P": P_GAUSS, "R": int(R), "sh_degree": SH_DEGREE,
-                   "width": W, "height": H},
+        "config": bench_config(W, H, R_per_pose),
+        "details": {"what": "UNMODIFIED reference CUDA rasterizer (src/cuda_rasterizer + rasterize_points.cu) compiled for "
+                            "sm_100a into oracle/_ref, RasterizeGaussiansCUDA + RasterizeGaussiansBackwardCUDA per step "
+                            "(its own resize_ allocations, zero-fills and blocking D2H of num_rendered included)"},
         "clocks": clocks,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
-                         "sample": "UNMODIFIED reference CUDA rasterizer (src/cuda_rasterizer + rasterize_points.cu) "
-                                   "compiled for sm_100a into oracle/_ref, RasterizeGaussiansCUDA + "
-                                   "RasterizeGaussiansBackwardCUDA per step on this B200, driven by 1 host thread; "
-                                   "the reference has no CPU implementation of this path"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "sample": "the reference's implementation of this path is CUDA: this is the UNMODIFIED reference "
+                                   "CUDA rasterizer on this B200 (kind would be 'gpu' if the contract had the word), "
+                                   "driven by 1 host thread; all %d steps of this run" % args.steps},
+        "e2e": e2e,
         "gpu_launches": 0,
     }
+    if not args.no_sweep:
+        try:
+            del sc
+            torch.cuda.empty_cache()
+            out["sweep"] = sweep_reference(dev)
+        except Exception as exc:
+            out["sweep"] = {"status": "failed: %s" % (repr(exc)[:200],)}
+    return out
 
 
 def main():
@@ -527,16 +980,25 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gs_livm_b200 has no CPU path")
+    # ONE JSON line on stdout: whatever libraries print there during the run (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         # rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work (no process group)
         if int(os.environ.get("RANK", "0")) != 0:
             return
         dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
         torch.cuda.set_device(dev)
-        print(json.dumps(run_reference(args, 0, 1, dev)))
+        emit(run_reference(args, 0, 1, dev))
         return
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
@@ -546,7 +1008,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0 and out is not None:
-        print(json.dumps(out))
+        emit(out)
 
 
 if __name__ == "__main__":

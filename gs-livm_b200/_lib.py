@@ -43,7 +43,7 @@ class BwdArgs(C.Structure):
         ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p),
         ("dL_dcolor", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p),
         ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p), ("dL_drot", C.c_void_p), ("debug", C.c_int),
-        ("flags", C.c_int),
+        ("flags", C.c_int), ("range_first", C.c_int), ("range_count", C.c_int),
     ]
 
 
@@ -52,13 +52,17 @@ BWD_ACCUMULATORS_ZEROED = 2
 BWD_SH_FACTORED = 4
 BWD_ONLY_BLEND = 8
 BWD_ONLY_GEOM = 16
-WINDOW_BARRIER_CHANNELS = 8
+WINDOW_CH_DONE, WINDOW_CH_PUSHED = 2, 3
 ABI_VERSION = 5  # include/gsr.h GSR_ABI_VERSION this binding was written against
 
 
 class WindowRows(C.Structure):
     _fields_ = [("union_words", C.c_void_p), ("first_float", C.c_size_t), ("n_rows", C.c_uint32),
                 ("floats_per_row", C.c_uint32)]
+
+
+class WindowComm(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("pads", C.c_void_p * 16)]
 
 
 class AdamGroup(C.Structure):
@@ -113,11 +117,16 @@ SYMBOLS = {
     "gsr_window_allreduce_p2p_rows": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p]),
     "gsr_window_slot_floats": (C.c_size_t, [C.c_int]),
-    "gsr_window_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "gsr_window_push_rgb": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
-                                      C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
-    "gsr_window_expand_sh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p),
-                                       C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "gsr_window_pad_words": (C.c_size_t, []),
+    "gsr_window_wait": (C.c_int, [C.POINTER(WindowComm), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gsr_window_push_rgb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                      C.POINTER(WindowComm), C.c_void_p]),
+    "gsr_window_expand_sh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "gsr_window_allreduce_rest": (C.c_int, [C.POINTER(WindowComm), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.c_int,
+                                            C.POINTER(C.c_void_p), C.c_void_p]),
     "gsr_image_loss_scratch_floats": (C.c_size_t, [C.c_int, C.c_int]),
     "gsr_image_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),

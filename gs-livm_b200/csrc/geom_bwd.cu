@@ -38,6 +38,7 @@ struct GeomBwdArgs {
   float* dL_dsh;
   float* dL_dscale;
   float* dL_drot;
+  int first;   // the kernel covers Gaussians [first, P): P is the END of the range here
   int vec_sh;  // M == 16 and shs / dL_dsh 16-byte aligned
   int assign_all;  // GSR_BWD_OUTPUTS_UNINITIALIZED: also write the zeros of Gaussians with radii <= 0
 };
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     else if (i < 32) s_proj[i - 16] = __ldg(a.projmatrix + i - 16);
     else s_cam[i - 32] = __ldg(a.cam_pos + i - 32);
   }
-  const int base = blockIdx.x * kBlock;
+  const int base = a.first + blockIdx.x * kBlock;
   const int n = min(kBlock, a.P - base);
   const int idx = base + tid;
   const bool active = tid < n && a.radii[idx] > 0;
@@ -336,7 +337,11 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
 cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int* radii, float focal_x, float focal_y,
                             cudaStream_t s) {
   GeomBwdArgs a;
-  a.P = f.P, a.D = f.D, a.M = f.M;
+  a.P = f.P, a.D = f.D, a.M = f.M, a.first = 0;
+  if ((f.flags & GSR_BWD_ONLY_GEOM) && f.range_count > 0) {
+    if (f.range_first < 0 || f.range_first + (long long)f.range_count > f.P) return cudaErrorInvalidValue;
+    a.first = f.range_first, a.P = f.range_first + f.range_count;
+  }
   a.scale_modifier = f.scale_modifier, a.tan_fovx = f.tan_fovx, a.tan_fovy = f.tan_fovy;
   a.focal_x = focal_x, a.focal_y = focal_y;
   a.means3D = f.means3D, a.radii = radii, a.shs = f.colors_precomp ? nullptr : f.shs, a.clamped = g.clamped;
@@ -351,7 +356,7 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
   const bool factored = a.shs && (f.flags & GSR_BWD_SH_FACTORED);
   a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && (factored || al16(f.dL_dsh));
   a.assign_all = (f.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) ? 1 : 0;
-  const int blocks = (f.P + kBlock - 1) / kBlock;
+  const int blocks = (a.P - a.first + kBlock - 1) / kBlock;
   if (a.vec_sh) {
     constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);
     if (factored) {

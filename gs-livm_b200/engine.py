@@ -178,13 +178,16 @@ class RasterContext:
         _lib.check(self.lib.gsr_backward_prepare(C.byref(a), stream), "gsr_backward_prepare")
 
     def backward(self, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor, debug: bool = False,
-                 accumulators_zeroed: bool = False, part: str = "all", sh_factored: bool = False) -> Dict[str, torch.Tensor]:
+                 accumulators_zeroed: bool = False, part: str = "all", sh_factored: bool = False,
+                 gaussian_range: Optional[tuple] = None) -> Dict[str, torch.Tensor]:
         """Gradients of the last forward. The reference's caller zero-fills all nine outputs before every
         backward (rasterize_points.cu:173-181); here the library is told they are uninitialised
         (GSR_BWD_OUTPUTS_UNINITIALIZED) and writes every element itself, inside whatever region the caller is
         timing. part: "all", or one half per call — "blend" (accumulator clearing + blend backward; dL_dmean2D,
         dL_dconic, dL_dopacity, dL_dcolor are complete after it) and "geom" (the per-Gaussian kernel).
-        sh_factored: dL_dsh is not written (GSR_BWD_SH_FACTORED; window.FactoredExchange rebuilds the window's sum)."""
+        sh_factored: dL_dsh is not written (GSR_BWD_SH_FACTORED; window.FactoredExchange rebuilds the window's sum).
+        gaussian_range = (first, count): with part == "geom", only those Gaussians (a window exchange pipelines the
+        per-Gaussian kernel in chunks)."""
         f = self._fwd_args
         if f is None:
             raise RuntimeError("backward() before forward()")
@@ -205,6 +208,10 @@ class RasterContext:
         a.flags = _lib.BWD_OUTPUTS_UNINITIALIZED | (_lib.BWD_ACCUMULATORS_ZEROED if accumulators_zeroed else 0)
         a.flags |= {"all": 0, "blend": _lib.BWD_ONLY_BLEND, "geom": _lib.BWD_ONLY_GEOM}[part]
         a.flags |= _lib.BWD_SH_FACTORED if sh_factored else 0
+        if gaussian_range is not None:
+            if part != "geom":
+                raise ValueError("gaussian_range needs part == 'geom'")
+            a.range_first, a.range_count = int(gaussian_range[0]), int(gaussian_range[1])
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.gsr_backward(C.byref(a), stream), "gsr_backward")
         return g

@@ -162,19 +162,26 @@ class FactoredExchange:
 
     Per view the 48-float dL_dsh row of a Gaussian is basis(dir_v) (x) dRGB_v, so the ranks exchange the 3 dRGB floats
     of the Gaussians their view rendered (pushed into every rank's slot of that view as soon as the blend backward is
-    done, i.e. under geom_bwd, which then writes no SH rows at all), all-reduce only the other 11 parameter-gradient
-    floats, and rebuild  dL_dsh = sum_v basis(dir_v) (x) dRGB_v  locally beside that all-reduce — same order on every
-    rank, hence identical bits. Barriers are libgsr_b200's own flag kernels, so `render_step` can be captured in ONE
-    CUDA graph. One view per rank and step; `flat` is the gradient buffer an engine.RasterContext must be built on
+    done), all-reduce only the other 11 parameter-gradient floats — and only for the Gaussians some view of the step
+    rendered — and rebuild  dL_dsh = sum_v basis(dir_v) (x) dRGB_v  locally: same order on every rank, hence identical
+    bits. The push and the expansion are pipelined over `n_chunks` ranges of Gaussians (the expansion of a range starts
+    as soon as its dRGB has arrived from every rank); the per-Gaussian backward, which writes no SH rows at all, and
+    the all-reduce behind it run once over all Gaussians. The cross-rank signalling lives inside
+    libgsr_b200's kernels (flag words in the symmetric allocation), so `render_step` can be captured in ONE CUDA graph.
+    One view per rank and step; `flat` is the gradient buffer an engine.RasterContext must be built on
     (`grad_flat=exchange.flat`).
 
-    world == 1 works without any peer memory (the slot is local): that is how the single-GPU tests check the
+    world == 1 works without any peer memory (the slots are local): that is how the single-GPU tests check the
     factorisation against the rows geom_bwd writes."""
 
     def __init__(self, P: int, M: int, device, group=None, reduce_mode: str = "auto", push_mode: str = "auto",
-                 n_views: Optional[int] = None):
+                 n_views: Optional[int] = None, sparse_reduce: bool = True, n_chunks: int = 1):
         """n_views: gather slots = views summed per step (default: one per rank; more only make sense where the caller
-        pushes several views itself, as the single-GPU tests do)."""
+        pushes several views itself, as the single-GPU tests do). sparse_reduce: the 11-float all-reduce skips the
+        Gaussians no view rendered. n_chunks: ranges of Gaussians the push -> expansion pipeline works on. (Cutting the
+        per-Gaussian backward and the all-reduce into the same chunks as well was measured SLOWER at N = 2: 623 us per
+        step with 1 chunk, 697 with 4, 804 with 8 -- every chunk boundary drains geom_bwd's CTAs, and a chunk's reducing
+        kernel holds SM slots while it waits for the slowest rank.)"""
         import ctypes as C
         from . import _lib, engine
         self._lib, self.lib, self._C = _lib, _lib.load(), C
@@ -188,14 +195,19 @@ class FactoredExchange:
         self.n_views = self.world if n_views is None else int(n_views)
         if self.world > 16 or not (self.world <= self.n_views <= 16):
             raise ValueError("at most 16 ranks and 16 views, at least one view per rank")
-        _, self.grad_floats, param_floats, self.sh_floats = engine.grad_layout(self.P, self.M)
+        # chunk boundaries at multiples of 128 Gaussians (whole visibility words per warp of the push kernel)
+        n_chunks = max(1, min(int(n_chunks), 32, (self.P + 127) // 128))
+        per = ((self.P + n_chunks - 1) // n_chunks + 127) // 128 * 128
+        self.chunks = [(f, min(per, self.P - f)) for f in range(0, self.P, per)]
+        at, self.grad_floats, param_floats, self.sh_floats = engine.grad_layout(self.P, self.M)
+        self._rest_first = (C.c_size_t * 4)(*[at[n][0] for n in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity")])
         self.rest_floats = param_floats - self.sh_floats  # mean3D, scale, rotation, opacity: 11 floats per Gaussian
         self.slot_floats = int(self.lib.gsr_window_slot_floats(self.P))
         self.vis_words = ((self.P + 31) // 32 + 3) // 4 * 4
-        r4 = lambda n: (n + 31) // 32 * 32  # noqa: E731
-        self._sig_at = r4(self.grad_floats)
-        self._slots_at = self._sig_at + r4(_lib.WINDOW_BARRIER_CHANNELS * 16)
-        self._slot_stride = r4(self.slot_floats + self.vis_words)
+        r32 = lambda n: (n + 31) // 32 * 32  # noqa: E731
+        self._pad_at = r32(self.grad_floats)
+        self._slots_at = self._pad_at + r32(int(self.lib.gsr_window_pad_words()))
+        self._slot_stride = r32(self.slot_floats + self.vis_words)
         total = self._slots_at + 2 * self.n_views * self._slot_stride  # two parities x one slot per view
         self.hdl, mc = None, 0
         if self.world > 1:
@@ -215,93 +227,136 @@ class FactoredExchange:
         self.buf.zero_()
         torch.cuda.synchronize(self.device)
         if self.world > 1:
-            dist.barrier(group=group)  # every rank's flag words are zero before anybody signals
+            dist.barrier(group=group)  # every rank's flag words and epoch are zero before anybody signals
         self._ptrs, self._mc = ptrs, mc
         self.flat = self.buf[:self.grad_floats]
         self.reduce_mode = reduce_mode if reduce_mode != "auto" else ("multimem" if (mc and self.world > 2) else "p2p")
         self.push_mode = push_mode if push_mode != "auto" else ("multimem" if (mc and self.world > 2) else "p2p")
         if not mc and "multimem" in (self.reduce_mode, self.push_mode):
             raise RuntimeError("no multicast mapping on this system")
-        self._signals = (C.c_void_p * self.world)(*[p + 4 * self._sig_at for p in ptrs])
-        self._reduce_peers = (C.c_void_p * self.world)(*[p + 4 * self.sh_floats for p in ptrs])
-        self._reduce_mc = (mc + 4 * self.sh_floats) if mc else 0
+        self.sparse_reduce = bool(sparse_reduce)
+        self._comm = None
+        if self.world > 1:
+            self._comm = _lib.WindowComm()
+            self._comm.rank, self._comm.world = self.rank, self.world
+            for r in range(self.world):
+                self._comm.pads[r] = ptrs[r] + 4 * self._pad_at
+        self._reduce_bufs = (C.c_void_p * self.world)(*([mc] if self.reduce_mode == "multimem" else ptrs))
+        # Streams. The pushes and the all-reduces are short on SM work but sit on the step's critical path and run beside
+        # kernels that fill every SM (geom_bwd, the expansion): on high-priority streams their CTAs are placed as soon as
+        # a slot frees up instead of queueing behind thousands of pending CTAs.
         self.side = torch.cuda.Stream(device=self.device)
+        self.hi_push = torch.cuda.Stream(device=self.device, priority=-1)
+        self.hi_reduce = torch.cuda.Stream(device=self.device, priority=-1)
+        self.segment_events = None
         self.cam_centres = torch.zeros((self.n_views, 3), dtype=torch.float32, device=self.device)
 
     # slot of view v, parity q: floats [at, at + slot_floats) then the visibility words
     def _slot_at(self, v: int, q: int) -> int:
         return self._slots_at + (q * self.n_views + v) * self._slot_stride
 
-    def _push_targets(self, v: int, q: int):
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _comm_ref(self):
+        return self._C.byref(self._comm) if self._comm is not None else None
+
+    def _local_slots(self, parity: int):
+        C, base, V = self._C, self.buf.data_ptr(), self.n_views
+        rgb = (C.c_void_p * V)(*[base + 4 * self._slot_at(v, parity) for v in range(V)])
+        vis = (C.c_void_p * V)(*[base + 4 * (self._slot_at(v, parity) + self.slot_floats) for v in range(V)])
+        return rgb, vis
+
+    def push(self, ctx, parity: int, view: Optional[int] = None, chunk: Optional[int] = None) -> None:
+        """This rank's masked dRGB + visibility words (of one chunk, or all of them one after the other) into slot `view`
+        (default: this rank's) of every rank, each followed by its PUSHED signal (current stream). Needs the blend half of
+        ctx's backward."""
         C = self._C
-        at = 4 * self._slot_at(v, q)
+        at = 4 * self._slot_at(self.rank if view is None else int(view), parity)
         bases = [self._mc] if self.push_mode == "multimem" else self._ptrs
         rgb = (C.c_void_p * len(bases))(*[b + at for b in bases])
         vis = (C.c_void_p * len(bases))(*[b + at + 4 * self.slot_floats for b in bases])
-        return rgb, vis
+        for c in (range(len(self.chunks)) if chunk is None else [chunk]):
+            first, count = self.chunks[c]
+            st = self.lib.gsr_window_push_rgb(ctx.geom.buf.data_ptr(), self.P, first, count, c, ctx.radii.data_ptr(),
+                                              ctx.grads["dL_dcolor"].data_ptr(), rgb, vis, len(bases),
+                                              1 if self.push_mode == "multimem" else 0, self._comm_ref(), self._stream())
+            self._lib.check(st, "gsr_window_push_rgb")
 
-    def barrier(self, channel: int) -> None:
-        if self.world > 1:
-            st = self.lib.gsr_window_barrier(self._signals, self.rank, self.world, channel,
-                                             torch.cuda.current_stream(self.device).cuda_stream)
-            self._lib.check(st, "gsr_window_barrier")
+    def wait_pushed(self, chunk: int) -> None:
+        """Every peer's push of the chunk has landed here (current stream)."""
+        if self._comm is not None:
+            self._lib.check(self.lib.gsr_window_wait(self._comm_ref(), self._lib.WINDOW_CH_PUSHED, chunk, 0, self._stream()),
+                            "gsr_window_wait")
 
-    def push(self, ctx, parity: int, view: Optional[int] = None) -> None:
-        """This rank's masked dRGB + visibility words into slot `view` (default: this rank's) of every rank (current
-        stream). Needs the blend half of ctx's backward."""
-        rgb, vis = self._push_targets(self.rank if view is None else int(view), parity)
-        st = self.lib.gsr_window_push_rgb(ctx.geom.buf.data_ptr(), self.P, ctx.radii.data_ptr(),
-                                          ctx.grads["dL_dcolor"].data_ptr(), rgb, vis, self.world,
-                                          1 if self.push_mode == "multimem" else 0,
-                                          torch.cuda.current_stream(self.device).cuda_stream)
-        self._lib.check(st, "gsr_window_push_rgb")
+    def expand(self, ctx, means3D: torch.Tensor, parity: int, chunk: Optional[int] = None) -> None:
+        """dL_dsh of the whole window from the gathered slots (current stream); one chunk, or all."""
+        rgb, vis = self._local_slots(parity)
+        for c in (range(len(self.chunks)) if chunk is None else [chunk]):
+            first, count = self.chunks[c]
+            st = self.lib.gsr_window_expand_sh(self.P, first, count, ctx.D, self.M, self.n_views, means3D.data_ptr(),
+                                               self.cam_centres.data_ptr(), rgb, vis, ctx.grads["dL_dsh"].data_ptr(),
+                                               self._stream())
+            self._lib.check(st, "gsr_window_expand_sh")
 
-    def expand(self, ctx, means3D: torch.Tensor, parity: int) -> None:
-        """dL_dsh of the whole window from the gathered slots (current stream)."""
-        C = self._C
-        base = self.buf.data_ptr()
-        V = self.n_views
-        rgb = (C.c_void_p * V)(*[base + 4 * self._slot_at(v, parity) for v in range(V)])
-        vis = (C.c_void_p * V)(*[base + 4 * (self._slot_at(v, parity) + self.slot_floats) for v in range(V)])
-        st = self.lib.gsr_window_expand_sh(self.P, ctx.D, self.M, V, means3D.data_ptr(), self.cam_centres.data_ptr(),
-                                           rgb, vis, ctx.grads["dL_dsh"].data_ptr(),
-                                           torch.cuda.current_stream(self.device).cuda_stream)
-        self._lib.check(st, "gsr_window_expand_sh")
-
-    def allreduce_rest_(self) -> None:
-        """Sum over the ranks of the 11 non-SH parameter-gradient floats per Gaussian (current stream), bracketed by
-        barriers: channel 0 = every rank's gradients are complete, channel 2 = every rank holds the sum."""
-        if self.world <= 1:
+    def allreduce_rest_(self, parity: int) -> None:
+        """Sum over the ranks of the 11 non-SH parameter-gradient floats per Gaussian (current stream). The kernels wait
+        for every rank's READY (and, sparse, the last chunk's PUSHED) themselves and signal DONE; THIS rank's own pushes
+        must be ordered before by the caller."""
+        if self._comm is None:
             return
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.barrier(0)
-        if self.reduce_mode == "multimem":
-            st = self.lib.gsr_window_allreduce_multimem(self._reduce_mc, self.rest_floats, self.rank, self.world, stream)
-            self._lib.check(st, "gsr_window_allreduce_multimem")
-        elif self.reduce_mode == "p2p":
-            st = self.lib.gsr_window_allreduce_p2p(self._reduce_peers, self.rest_floats, self.rank, self.world, 1, stream)
-            self._lib.check(st, "gsr_window_allreduce_p2p")
-            self.barrier(1)
-            st = self.lib.gsr_window_allreduce_p2p(self._reduce_peers, self.rest_floats, self.rank, self.world, 2, stream)
-            self._lib.check(st, "gsr_window_allreduce_p2p")
-        else:
-            dist.all_reduce(self.flat[self.sh_floats:self.sh_floats + self.rest_floats], op=dist.ReduceOp.SUM, group=self.group)
-        self.barrier(2)
+        vis = self._local_slots(parity)[1] if self.sparse_reduce else None
+        st = self.lib.gsr_window_allreduce_rest(self._comm_ref(), self._reduce_bufs, 1 if self.reduce_mode == "multimem" else 0,
+                                                self.P, 0, self.P, 0, len(self.chunks) - 1, self._rest_first,
+                                                self.n_views if vis is not None else 0, vis, self._stream())
+        self._lib.check(st, "gsr_window_allreduce_rest")
 
-    def exchange(self, ctx, means3D: torch.Tensor, parity: int, blend_done: Optional[torch.cuda.Event] = None) -> None:
-        """Everything after the blend half of the backward, for callers that ran the halves themselves: push + expansion
-        on the side stream (behind `blend_done` if given), all-reduce on the current one, joined at the end."""
+    def step_end(self) -> None:
+        """LAST call of a step (current stream, after the other streams have been joined): every rank's part of the
+        all-reduce has landed here; advances the step epoch."""
+        if self._comm is not None:
+            self._lib.check(self.lib.gsr_window_wait(self._comm_ref(), self._lib.WINDOW_CH_DONE, 0, 1, self._stream()),
+                            "gsr_window_wait")
+
+    def exchange(self, ctx, means3D: torch.Tensor, parity: int, blend_done: torch.cuda.Event, geom) -> None:
+        """Everything after the blend half of the backward. `blend_done`: recorded on the current stream right after the
+        blend half; `geom()`: issues the per-Gaussian half (GSR_BWD_SH_FACTORED) on the current stream. Per chunk c:
+        push(c) on hi_push, PUSHED wait + expansion(c) on side; geom on the current stream, the all-reduce on hi_reduce
+        behind geom and the last push. Joined at the end, then the DONE wait."""
         main = torch.cuda.current_stream(self.device)
-        if blend_done is None:
-            blend_done = torch.cuda.Event()
-            blend_done.record(main)
+        ev = self.segment_events  # None, or a dict that receives timing events of this step's segments (diagnostics)
+        mark = (lambda n, s: ev.setdefault(n, torch.cuda.Event(enable_timing=True)).record(s)) if ev is not None else (lambda n, s: None)
+        n = len(self.chunks)
+        pushed = [torch.cuda.Event() for _ in range(n)]
+        geom_done = torch.cuda.Event()
+        with torch.cuda.stream(self.hi_push):
+            self.hi_push.wait_event(blend_done)
+            mark("push_begin", self.hi_push)
+            for c in range(n):
+                self.push(ctx, parity, chunk=c)
+                pushed[c].record(self.hi_push)
+            mark("push_end", self.hi_push)
         with torch.cuda.stream(self.side):
-            self.side.wait_event(blend_done)
-            self.push(ctx, parity)
-            self.barrier(3 + parity)  # every view's slot is complete on this rank
-            self.expand(ctx, means3D, parity)
-        self.allreduce_rest_()
+            for c in range(n):
+                self.side.wait_event(pushed[c])
+                self.wait_pushed(c)
+                self.expand(ctx, means3D, parity, chunk=c)
+            mark("expand_end", self.side)
+        mark("geom_begin", main)
+        geom()
+        geom_done.record(main)
+        mark("geom_end", main)
+        if self._comm is not None:
+            with torch.cuda.stream(self.hi_reduce):
+                self.hi_reduce.wait_event(geom_done)
+                self.hi_reduce.wait_event(pushed[n - 1])
+                self.allreduce_rest_(parity)
+                mark("reduce_end", self.hi_reduce)
+            main.wait_stream(self.hi_reduce)
+        main.wait_stream(self.hi_push)
         main.wait_stream(self.side)
+        self.step_end()
+        mark("step_end", main)
 
     def render_step(self, ctx, scene: Dict[str, torch.Tensor], cam, dL_dcolor: torch.Tensor, dL_dacc: torch.Tensor,
                     parity: int) -> None:
@@ -319,14 +374,8 @@ class FactoredExchange:
         ctx.backward(dL_dcolor, dL_dacc, accumulators_zeroed=True, part="blend")
         blend_done = torch.cuda.Event()
         blend_done.record(main)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(blend_done)
-            self.push(ctx, parity)
-            self.barrier(3 + parity)
-            self.expand(ctx, scene["means3D"], parity)
-        ctx.backward(dL_dcolor, dL_dacc, part="geom", sh_factored=True)
-        self.allreduce_rest_()
-        main.wait_stream(self.side)
+        self.exchange(ctx, scene["means3D"], parity, blend_done,
+                      lambda: ctx.backward(dL_dcolor, dL_dacc, part="geom", sh_factored=True))
 
 
 class WindowStep:

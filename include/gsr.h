@@ -120,6 +120,8 @@ typedef struct gsr_bwd_args {
   float* dL_drot;        /* [P,4] */
   int debug;
   int flags;             /* 0 = the reference's contract (all 9 outputs pre-zeroed by the caller); GSR_BWD_* bits */
+  int range_first;       /* with GSR_BWD_ONLY_GEOM: the per-Gaussian kernel covers Gaussians [range_first, range_first + */
+  int range_count;       /* range_count) only (range_count == 0: all P) -- a window exchange pipelines it in chunks */
 } gsr_bwd_args;
 
 /* gsr_bwd_args.flags. With GSR_BWD_OUTPUTS_UNINITIALIZED the caller does NOT zero the gradient outputs (the
@@ -261,26 +263,54 @@ GSR_API int gsr_window_allreduce_p2p_rows(void* const* peer_buffers, size_t n_fl
  * dL_dsh row of a Gaussian is basis(dir_v) (x) dRGB_v (src/cuda_rasterizer/backward.cu:56-135), dir_v follows from the
  * replicated means and the view's camera centre, so the ranks exchange dRGB_v (3 floats per rendered Gaussian and view,
  * gathered) and all-reduce only the other 11 parameter-gradient floats; every rank then rebuilds the sum of the rows.
- *   gsr_window_barrier: barrier across the ranks on `stream`, a kernel over flag words in peer-mapped memory:
- *     peer_signals[r] = rank r's pad of GSR_WINDOW_BARRIER_CHANNELS x 16 uint32, zero-initialised once. Replay-safe
- *     (every flag returns to 0): can be captured in a CUDA graph. Different channels may be in flight on different
- *     streams at once.
- *   gsr_window_push_rgb: after the blend backward of this rank's view (GSR_BWD_ONLY_BLEND): writes the view's dRGB
- *     (dL_dcolor with the channels the forward clamped zeroed; culled Gaussians are skipped) and its visibility words
- *     into the view's slot of EVERY rank: dst_rgb[r] / dst_vis[r], r < world, are the slot as mapped for rank r (plain
- *     peer stores), or, with multicast != 0, dst_rgb[0] / dst_vis[0] are its multicast mapping (multimem.st). A slot is
- *     gsr_window_slot_floats(P) floats (16-byte aligned) + ceil(P / 32) words. geom_buffer: of the view's forward.
- *   gsr_window_expand_sh: dL_dsh[P,16,3] = sum over v < n_views (in that order, identical on every rank) of
- *     basis(normalize(means3D - cam_pos[v])) (x) rgb_slots[v], skipping views whose visibility bit is clear; rows no
- *     view rendered are written as zeros. cam_pos: DEVICE array [n_views,3]; rgb_slots / vis_slots: host arrays of
- *     n_views device pointers. n_views <= 16, M must be 16. */
-#define GSR_WINDOW_BARRIER_CHANNELS 8
+ *
+ * Cross-rank ordering is inside the kernels. gsr_window_comm describes the ranks' flag pads: pads[r] = rank r's pad as
+ * mapped into this process, gsr_window_pad_words() uint32 each, in peer-mapped (symmetric) memory, zero-initialised
+ * once before the first step. Signals are release stores of the step's epoch, waits spin on the own pad; the epoch lives
+ * in the own pad and is advanced by the step's last call, so a step can be captured in a CUDA graph and replayed.
+ * The Gaussians may be cut into chunks that are pushed / reduced / expanded one after the other (`first`, `count`: the
+ * chunk's Gaussians, first a multiple of 128; `sub` < 32: the chunk's number, ascending within a step), so that the
+ * exchange of one chunk runs beside the per-Gaussian backward of the next. Every rank must issue the same sequence:
+ *   gsr_window_push_rgb      (any stream; after the blend backward of this rank's view, GSR_BWD_ONLY_BLEND): writes the
+ *       view's dRGB (dL_dcolor with the channels the forward clamped zeroed; culled Gaussians are skipped) and its
+ *       visibility words into the view's slot of EVERY rank -- dst_rgb[r] / dst_vis[r], r < n_dst, are the slot as
+ *       mapped for rank r (plain peer stores), or, with multicast != 0, dst_rgb[0] / dst_vis[0] its multicast mapping
+ *       (multimem.st) -- then signals PUSHED(sub). A slot is gsr_window_slot_floats(P) floats (16-byte aligned) +
+ *       ceil(P / 32) words. geom_buffer: of the view's forward.
+ *   gsr_window_wait(GSR_WINDOW_CH_PUSHED, sub)   every peer's push of the chunk has landed here.
+ *   gsr_window_expand_sh     dL_dsh[g] for the chunk's Gaussians = sum over v < n_views (in that order, identical on
+ *       every rank) of basis(normalize(means3D - cam_pos[v])) (x) rgb_slots[v], skipping views whose visibility bit is
+ *       clear; rows no view rendered are written as zeros. cam_pos: DEVICE array [n_views,3]; rgb_slots / vis_slots:
+ *       host arrays of n_views device pointers; n_views <= 16, M == 16.
+ *   gsr_window_allreduce_rest  (after the per-Gaussian backward of the chunk, GSR_BWD_ONLY_GEOM | GSR_BWD_SH_FACTORED):
+ *       sum over the ranks of dL_dmean3D [P,3], dL_dscale [P,3], dL_drot [P,4], dL_dopacity [P] (the chunk's part), which
+ *       start at floats first_float[0..3] (multiples of 4) of ONE symmetric buffer: buffers[r] = rank r's buffer
+ *       (two-shot over peer loads), or with multicast != 0 buffers[0] = its multicast mapping (multimem.ld_reduce /
+ *       multimem.st). With vis_slots (the gathered visibility words of the step's n_views views) groups of four
+ *       Gaussians no view rendered are skipped; the kernel then waits for PUSHED(pushed_sub) itself (the pushes of a
+ *       step are ordered, so the last chunk's signal covers them all). Waits for every rank's READY(sub) and signals
+ *       DONE(sub).
+ *   gsr_window_wait(GSR_WINDOW_CH_DONE, last sub, advance_epoch = 1)   LAST call of the step, after everything above:
+ *       every rank's part of the all-reduce has landed here. */
+#define GSR_WINDOW_FLAG_CHANNELS 4
+#define GSR_WINDOW_CH_DONE 2
+#define GSR_WINDOW_CH_PUSHED 3
+typedef struct gsr_window_comm {
+  int rank, world; /* world <= 16; world == 1: the calls do their local part only */
+  void* pads[16];
+} gsr_window_comm;
 GSR_API size_t gsr_window_slot_floats(int P);
-GSR_API int gsr_window_barrier(void* const* peer_signals, int rank, int world, int channel, void* stream);
-GSR_API int gsr_window_push_rgb(char* geom_buffer, int P, const int* radii, const float* dL_dcolor,
-                                void* const* dst_rgb, void* const* dst_vis, int world, int multicast, void* stream);
-GSR_API int gsr_window_expand_sh(int P, int D, int M, int n_views, const float* means3D, const float* cam_pos,
-                                 const void* const* rgb_slots, const void* const* vis_slots, float* dL_dsh, void* stream);
+GSR_API size_t gsr_window_pad_words(void);
+GSR_API int gsr_window_wait(const gsr_window_comm* comm, int channel, int sub, int advance_epoch, void* stream);
+GSR_API int gsr_window_push_rgb(char* geom_buffer, int P, int first, int count, int sub, const int* radii,
+                                const float* dL_dcolor, void* const* dst_rgb, void* const* dst_vis, int n_dst,
+                                int multicast, const gsr_window_comm* comm, void* stream);
+GSR_API int gsr_window_expand_sh(int P, int first, int count, int D, int M, int n_views, const float* means3D,
+                                 const float* cam_pos, const void* const* rgb_slots, const void* const* vis_slots,
+                                 float* dL_dsh, void* stream);
+GSR_API int gsr_window_allreduce_rest(const gsr_window_comm* comm, void* const* buffers, int multicast, int P, int first,
+                                      int count, int sub, int pushed_sub, const size_t* first_float, int n_views,
+                                      const void* const* vis_slots, void* stream);
 
 /* The two GPU steps right behind the rasterizer in GS-LIVM's mapping iteration, fused.
  *

@@ -24,10 +24,14 @@ g = torch.Generator().manual_seed(SEED + 1)
 dC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
 dS = (torch.randn((1, H, W), generator=g) / (H * W)).to(dev)
 
-combos = [("p2p", "p2p"), ("multimem", "multimem"), ("multimem", "p2p"), ("p2p", "multimem"), ("auto", "auto")]
-for reduce_mode, push_mode in combos:
+combos = [("p2p", "p2p", True, 1), ("multimem", "multimem", True, 1), ("multimem", "multimem", True, 2),
+          ("multimem", "multimem", True, 4), ("multimem", "multimem", False, 1), ("auto", "auto", True, 4)]
+if len(sys.argv) > 2:
+    combos = [c for i, c in enumerate(combos) if str(i) in sys.argv[2]]
+for reduce_mode, push_mode, sparse, track in combos:
     try:
-        ex = window.FactoredExchange(P, 16, dev, reduce_mode=reduce_mode, push_mode=push_mode)
+        ex = window.FactoredExchange(P, 16, dev, reduce_mode=reduce_mode, push_mode=push_mode, sparse_reduce=sparse,
+                                     n_chunks=track)
     except RuntimeError as e:
         if rank == 0:
             print(f"factored reduce={reduce_mode} push={push_mode}: skipped ({e})", flush=True)
@@ -59,8 +63,8 @@ for reduce_mode, push_mode in combos:
         # factored: push + geom half without the SH rows + exchange, from the same accumulators
         ctx.grads["dL_dsh"].fill_(float("nan"))
         ev = torch.cuda.Event(); ev.record()
-        ctx.backward(dC, dS, part="geom", sh_factored=True)
-        ex.exchange(ctx, sc["means3D"], parity=i % 2, blend_done=ev)
+        ex.exchange(ctx, sc["means3D"], i % 2, ev,
+                    lambda: ctx.backward(dC, dS, part="geom", sh_factored=True))
         torch.cuda.synchronize()
         got = ctx.param_grads()
         scale = float(want.abs().max())
@@ -69,6 +73,21 @@ for reduce_mode, push_mode in combos:
         chk = torch.tensor([got.double().sum().item(), got.double().abs().sum().item()], device=dev, dtype=torch.float64)
         lst = [torch.empty_like(chk) for _ in range(world)]; dist.all_gather(lst, chk)
         same_all &= all(torch.equal(x, lst[0]) for x in lst)
+    # the segments of real (eager) steps, from events inside FactoredExchange.exchange: us after the blend backward
+    ex.segment_events = {}
+    seg = {}
+    for i in range(4, 12):
+        set_centres(i); ex.render_step(ctx, sc, cams_of(i)[rank], dC, dS, parity=i % 2)
+        torch.cuda.synchronize()
+        E = ex.segment_events
+        for name, (a, b) in {"push": ("push_begin", "push_end"), "geom": ("geom_begin", "geom_end"),
+                             "geom_end->reduce_end": ("geom_end", "reduce_end"), "blend_end->expand_end": ("geom_begin", "expand_end"),
+                             "blend_end->step_end": ("geom_begin", "step_end")}.items():
+            seg[name] = seg.get(name, 0.0) + E[a].elapsed_time(E[b]) * 1e3 / 8
+    ex.segment_events = None
+    t = torch.tensor(list(seg.values()), device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("   segments, max over ranks (us): " + ", ".join(f"{k} {float(v):.1f}" for k, v in zip(seg, t)), flush=True)
     # timing: the full step, eager and captured
     def step(i):
         ex.render_step(ctx, sc, cams_of(i)[rank], dC, dS, parity=i % 2)
@@ -103,11 +122,13 @@ for reduce_mode, push_mode in combos:
             print("graph capture failed:", repr(e)[:300], flush=True)
     t = torch.tensor([eager_us, graph_us], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"factored reduce={ex.reduce_mode} push={ex.push_mode} (asked {reduce_mode}/{push_mode}): max|err|/max|ref| vs dense NCCL "
+        print(f"factored reduce={ex.reduce_mode} push={ex.push_mode} sparse={sparse} chunks={track} (asked {reduce_mode}/{push_mode}): max|err|/max|ref| vs dense NCCL "
               f"{worst:.3e}, ranks identical {same_all}, step eager {float(t[0]):.1f} us, graph {float(t[1]):.1f} us", flush=True)
     del ctx, ex
     torch.cuda.synchronize(); dist.barrier()
 
+if len(sys.argv) > 2:
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
 # the dense exchange for comparison (window.GradExchange, as bench.py used it in round 1)
 grad_floats = 75 * P
 exd = window.GradExchange(grad_floats, 59 * P, dev, sparse_rows=(0, P, 48))
