@@ -423,7 +423,9 @@ def run_ours(args, rank, world, dev):
     sc_cpu, sc, cams_cpu, cams, dC, dS = build_workload(dev)
     H, W = cams[0].height, cams[0].width
     exchange = window.FactoredExchange(P_GAUSS, 16, dev) if world > 1 else None
-    ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE, grad_flat=exchange.flat if exchange else None)
+    # (the window exchange sums into the gradient buffer in place: no zero-row tracking there)
+    ctx = engine.RasterContext(P_GAUSS, 16, W, H, dev, SH_DEGREE, grad_flat=exchange.flat if exchange else None,
+                               track_rows=exchange is None)
 
     # step i of rank r renders pose (r + i) % 8; the views of step i, in rank order, are what the exchange sums
     def pose_of(i, r=rank):
@@ -516,6 +518,12 @@ def run_ours(args, rank, world, dev):
             per_pose_ms.append(round(a0.elapsed_time(a1) / 5, 4))
         ctx.check()
 
+    captured[:] = [None] * WINDOW  # (the graphs and their memory pools are released before anything else is measured)
+    torch.cuda.synchronize()
+
+    # ---- end to end through the public operator: H2D camera + target, autograd, D2H loss ----
+    e2e_ms, e2e_mode, h2d_bytes = time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer)
+
     # ---- exchange check (N > 1, outside the timed region): factored result vs NCCL all-reduce of the dense gradients,
     # both from the SAME accumulated inputs (one blend backward), and bit-identity across the ranks
     exchange_max_err, exchange_identical, exchange_info = None, None, None
@@ -584,9 +592,6 @@ def run_ours(args, rank, world, dev):
         optim = time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, centres, pose_of, W, H, train)
     except Exception as exc:
         optim = {"status": "failed: %s" % (repr(exc)[:200],)}
-
-    # ---- end to end through the public operator: H2D camera + target, autograd, D2H loss ----
-    e2e_ms, e2e_mode, h2d_bytes = time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer)
 
     if rank != 0:
         return None
@@ -680,6 +685,7 @@ def run_ours(args, rank, world, dev):
                 "path": "GaussianRasterizer(settings, arena=RenderArena) (tensor-level mirror of the reference operator, "
                         "persistent scratch, sync-free forward) + torch autograd + L1 loss; "
                         "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream; "
+                        "the host launches step i+1 before it reads step i's loss (every loss is read, one step late); "
                         "launched as: " + e2e_mode},
         "e2e_dropin": dropin,
         "parity_check": parity,
@@ -807,20 +813,20 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
     means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
     host_targets, host_cams = host_step_inputs(cams_cpu, H, W)
     h2d_bytes = host_targets[0].numel() * 4 + host_cams[0].numel() * 4
-    loss_host = torch.zeros(1).pin_memory()
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
 
     arena = rasterizer.RenderArena(dev)  # persistent scratch + sync-free forward (one render in flight at a time)
     copy_stream = torch.cuda.Stream(device=dev)
     target_dev = [torch.empty((3, H, W), device=dev) for _ in range(2)]
 
-    cam_stage = torch.zeros(35).pin_memory()  # the step's camera, written by the host before the step is launched
+    cam_stage = [torch.zeros(35).pin_memory() for _ in range(2)]  # the step's camera, written by the host before launch
     cam_dev = torch.zeros(35, device=dev)
 
     def step_body(j):
         """One step as the operator's user writes it; nothing in here waits for the GPU, so it can be launched
         eagerly or captured once and replayed (rasterizer.CapturedStep). j: which target staging buffer."""
         main = torch.cuda.current_stream(dev)
-        cam_dev.copy_(cam_stage, non_blocking=True)
+        cam_dev.copy_(cam_stage[j], non_blocking=True)
         # the step's target image goes up on a copy stream while the forward renders; the loss waits for it
         copy_stream.wait_stream(main)  # the buffer's previous use (two steps ago) is over
         with torch.cuda.stream(copy_stream):
@@ -849,22 +855,38 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
             else:
                 for t in leaves.values():
                     dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_host[j].copy_(loss.detach().reshape(1), non_blocking=True)
 
     captured = [None, None]
-    cam_stage_np, loss_np = cam_stage.numpy(), loss_host.numpy()  # same (pinned) memory, without torch's per-op overhead
+    # same (pinned) memory, without torch's per-op overhead
+    cam_stage_np, loss_np = [c.numpy() for c in cam_stage], [t.numpy() for t in loss_host]
     host_cams_np = [c.numpy() for c in host_cams]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    losses = []
+    lag = 0 if os.environ.get("GSR_BENCH_E2E_LAG", "1") == "0" else 1
+
+    def finish(k):
+        """Step k's result on the host: its loss (D2H inside the step) and whether its render fitted the arena."""
+        done[k % 2].synchronize()
+        if not arena.check(sync=False, keep_last=len(arena._unchecked) - 1):
+            raise SystemExit("bench: a view did not fit the presized binning buffer; the measurement is void")
+        losses.append(float(loss_np[k % 2][0]))
 
     def step_e2e(i):
-        cam_stage_np[:] = host_cams_np[(rank + i) % WINDOW]  # 140 bytes, host to pinned host
-        if captured[i % 2] is not None:
-            captured[i % 2].replay()  # the whole step, copies included, is one graph launch
+        """Launch step i, then take step i-1's result: nothing in the operator waits for the GPU (sync-free forward,
+        persistent arena), so the host prepares and launches the next step while the device still renders this one —
+        every step's loss is read on the host, one step late. Staging buffers alternate (j)."""
+        j = i % 2
+        cam_stage_np[j][:] = host_cams_np[(rank + i) % WINDOW]  # 140 bytes, host to pinned host
+        if captured[j] is not None:
+            captured[j].replay()  # the whole step, copies included, is one graph launch
         else:
-            step_body(i % 2)
-        torch.cuda.current_stream().synchronize()  # the step's result is on the host
-        if not arena.check():
-            raise SystemExit("bench: a view did not fit the presized binning buffer; the measurement is void")
-        return float(loss_np[0])
+            step_body(j)
+        done[j].record()
+        if lag == 0:
+            finish(i)
+        elif i > 0:
+            finish(i - 1)
 
     # size the arena for the window's busiest view before any timed (or collective) step: one synchronous render
     # per camera tells its instance count
@@ -890,14 +912,19 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
         except Exception as exc:  # e.g. a collective that cannot be captured on this system
             captured[0] = captured[1] = None
             e2e_mode = "eager launches (graph capture failed: %s)" % type(exc).__name__
-    for i in range(3):
+    for i in range(4):
         step_e2e(i)
+    if lag:
+        finish(3)
     barrier_sync(world)
     t0 = time.perf_counter()
     for i in range(args.steps):
         step_e2e(i)
+    if lag:
+        finish(args.steps - 1)  # the last step's result
     barrier_sync(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    assert len(losses) == 4 + args.steps
     return e2e_ms, e2e_mode, h2d_bytes
 
 

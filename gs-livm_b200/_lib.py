@@ -43,7 +43,7 @@ class BwdArgs(C.Structure):
         ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p),
         ("dL_dcolor", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p),
         ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p), ("dL_drot", C.c_void_p), ("debug", C.c_int),
-        ("flags", C.c_int), ("range_first", C.c_int), ("range_count", C.c_int),
+        ("flags", C.c_int), ("row_state", C.c_void_p), ("range_first", C.c_int), ("range_count", C.c_int),
     ]
 
 

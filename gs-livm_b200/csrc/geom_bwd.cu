@@ -41,6 +41,8 @@ struct GeomBwdArgs {
   int first;   // the kernel covers Gaussians [first, P): P is the END of the range here
   int vec_sh;  // M == 16 and shs / dL_dsh 16-byte aligned
   int assign_all;  // GSR_BWD_OUTPUTS_UNINITIALIZED: also write the zeros of Gaussians with radii <= 0
+  uint8_t* row_state;  // gsr_bwd_args.row_state (with assign_all): != 0 <=> the Gaussian's outputs may be non-zero; a culled
+                       // Gaussian whose outputs are known to be zero already is skipped, not rewritten
 };
 
 __device__ __forceinline__ float dot3_ref(float a, float b, float c, float d, float e, float f) {
@@ -76,6 +78,9 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   const int n = min(kBlock, a.P - base);
   const int idx = base + tid;
   const bool active = tid < n && a.radii[idx] > 0;
+  // requested here, looked at only when the outputs are written: the kernel is latency-bound, and a dependent load in
+  // front of the SH-row prefetch costs more than the zero rows it saves (measured: 95 vs 88 us)
+  const uint8_t may_be_nonzero = (a.row_state && tid < n) ? a.row_state[idx] : (uint8_t)1;
   s_active[tid] = active;
   __syncthreads();
   if (kVec16) {
@@ -215,6 +220,32 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     gmz += (PM[8] * m_w - PM[11] * mul1) * d2x + (PM[9] * m_w - PM[11] * mul2) * d2y;
   }
 
+    // ---- scale / rotation backward (reference computeCov3D backward) ------------------------------
+    if (a.scales && !a.cov3D_precomp) {
+      // dL/dSigma as a symmetric matrix; dL/dM = 2 M dL/dSigma, M rows = (A,B,C)
+      const float S00 = dcov[0], S01 = 0.5f * dcov[1], S02 = 0.5f * dcov[2], S11 = dcov[3], S12 = 0.5f * dcov[4],
+                  S22 = dcov[5];
+      const float dA0 = 2.f * (A0 * S00 + A1 * S01 + A2 * S02), dA1 = 2.f * (A0 * S01 + A1 * S11 + A2 * S12),
+                  dA2 = 2.f * (A0 * S02 + A1 * S12 + A2 * S22);
+      const float dB0 = 2.f * (B0 * S00 + B1 * S01 + B2 * S02), dB1 = 2.f * (B0 * S01 + B1 * S11 + B2 * S12),
+                  dB2 = 2.f * (B0 * S02 + B1 * S12 + B2 * S22);
+      const float dC0 = 2.f * (C0 * S00 + C1 * S01 + C2 * S02), dC1 = 2.f * (C0 * S01 + C1 * S11 + C2 * S12),
+                  dC2 = 2.f * (C0 * S02 + C1 * S12 + C2 * S22);
+      a.dL_dscale[3 * (size_t)idx] = R00 * dA0 + R01 * dA1 + R02 * dA2;
+      a.dL_dscale[3 * (size_t)idx + 1] = R10 * dB0 + R11 * dB1 + R12 * dB2;
+      a.dL_dscale[3 * (size_t)idx + 2] = R20 * dC0 + R21 * dC1 + R22 * dC2;
+      // E[i][j] = s_i * dM[i][j]
+      const float E00 = sx * dA0, E01 = sx * dA1, E02 = sx * dA2;
+      const float E10 = sy * dB0, E11 = sy * dB1, E12 = sy * dB2;
+      const float E20 = sz * dC0, E21 = sz * dC1, E22 = sz * dC2;
+      float4 dq;
+      dq.x = 2.f * qz * (E01 - E10) + 2.f * qy * (E20 - E02) + 2.f * qx * (E12 - E21);
+      dq.y = 2.f * qy * (E10 + E01) + 2.f * qz * (E20 + E02) + 2.f * qr * (E12 - E21) - 4.f * qx * (E22 + E11);
+      dq.z = 2.f * qx * (E10 + E01) + 2.f * qr * (E20 - E02) + 2.f * qz * (E12 + E21) - 4.f * qy * (E22 + E00);
+      dq.w = 2.f * qr * (E01 - E10) + 2.f * qx * (E20 + E02) + 2.f * qy * (E12 + E21) - 4.f * qz * (E11 + E00);
+      reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+    }
+
   }  // if (active): covariance + projection part
 
   // ---- SH backward (reference computeColorFromSH backward) -------------------------------------
@@ -235,26 +266,32 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     const int ncoef = (a.D + 1) * (a.D + 1);
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;  // dL/d(dir)
     if (kVec16) {
-      float4 in4[12], out4[12];
+      // four coefficients (three 16-byte words of the staged row) at a time: 12 values in, 12 out -- not the whole
+      // 48-float row in registers twice
 #pragma unroll
-      for (int i = 0; i < 12; ++i) in4[i] = s_sh[tid * kShRow + i];
-      const float* sh = reinterpret_cast<const float*>(in4);
-      float* o = reinterpret_cast<float*>(out4);
+      for (int g = 0; g < 4; ++g) {
+        float4 in4[3], out4[3];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
+        for (int i = 0; i < 3; ++i) in4[i] = s_sh[tid * kShRow + 3 * g + i];
+        const float* sh = reinterpret_cast<const float*>(in4);
+        float* o = reinterpret_cast<float*>(out4);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const bool on = k < ncoef;
-          if (!kFactored) o[k * 3 + c] = on ? __fmul_rn(b[k], dRGB[c]) : 0.f;
-          if (on && k > 0) {
-            const float w = sh[k * 3 + c] * dRGB[c];
-            ddx += bx[k] * w, ddy += by[k] * w, ddz += bz[k] * w;
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = 4 * g + kk;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const bool on = k < ncoef;
+            if (!kFactored) o[kk * 3 + c] = on ? __fmul_rn(b[k], dRGB[c]) : 0.f;
+            if (on && k > 0) {
+              const float w = sh[kk * 3 + c] * dRGB[c];
+              ddx += bx[k] * w, ddy += by[k] * w, ddz += bz[k] * w;
+            }
           }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 12; ++i)
-        if (!kFactored) s_sh[tid * kShRow + i] = out4[i];  // own row only: no hazard
+        for (int i = 0; i < 3; ++i)
+          if (!kFactored) s_sh[tid * kShRow + 3 * g + i] = out4[i];  // own row only: no hazard
+      }
     } else {
       const float* sh = a.shs + (size_t)idx * a.M * 3;
       float* o = a.dL_dsh + (size_t)idx * a.M * 3;
@@ -277,17 +314,21 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     gmy += (-ox * oy * ddx + (sum2 - oy * oy) * ddy - oz * oy * ddz) * inv32;
     gmz += (-ox * oz * ddx - oy * oz * ddy + (sum2 - oz * oz) * ddz) * inv32;
   }
+  // 1: the Gaussian's row goes out; 2: culled and the outputs are not known to be zero already: zeros go out; 0: nothing
+  const uint8_t todo = active ? 1 : ((a.assign_all && tid < n && may_be_nonzero) ? 2 : 0);
+  if (a.row_state && tid < n && may_be_nonzero != (uint8_t)active) a.row_state[idx] = active;
+  if (kVec16 && !kFactored) s_active[tid] = todo;  // (its readers below come after the barrier)
   if (kVec16 && !kFactored) {  // coalesced store of the visible Gaussians' dL_dsh rows (culled rows stay at the caller's zeros)
     __syncthreads();
     float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)base * 12;
     for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {
-      if (s_active[row]) d4[q] = s_sh[row * kShRow + rem];
-      else if (a.assign_all) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s_active[row] == 1) d4[q] = s_sh[row * kShRow + rem];
+      else if (s_active[row] == 2) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }
     }
   }
   if (!active) {
-    if (a.assign_all && tid < n) {  // the caller did not zero the outputs: culled Gaussians get their zeros here
+    if (todo == 2) {  // the caller did not zero the outputs: culled Gaussians get their zeros here
       const size_t i = (size_t)idx;
       a.dL_dmean3D[3 * i] = 0.f, a.dL_dmean3D[3 * i + 1] = 0.f, a.dL_dmean3D[3 * i + 2] = 0.f;
 #pragma unroll
@@ -305,31 +346,6 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   a.dL_dmean3D[3 * (size_t)idx + 1] = gmy;
   a.dL_dmean3D[3 * (size_t)idx + 2] = gmz;
 
-  // ---- scale / rotation backward (reference computeCov3D backward) ------------------------------
-  if (a.scales && !a.cov3D_precomp) {
-    // dL/dSigma as a symmetric matrix; dL/dM = 2 M dL/dSigma, M rows = (A,B,C)
-    const float S00 = dcov[0], S01 = 0.5f * dcov[1], S02 = 0.5f * dcov[2], S11 = dcov[3], S12 = 0.5f * dcov[4],
-                S22 = dcov[5];
-    const float dA0 = 2.f * (A0 * S00 + A1 * S01 + A2 * S02), dA1 = 2.f * (A0 * S01 + A1 * S11 + A2 * S12),
-                dA2 = 2.f * (A0 * S02 + A1 * S12 + A2 * S22);
-    const float dB0 = 2.f * (B0 * S00 + B1 * S01 + B2 * S02), dB1 = 2.f * (B0 * S01 + B1 * S11 + B2 * S12),
-                dB2 = 2.f * (B0 * S02 + B1 * S12 + B2 * S22);
-    const float dC0 = 2.f * (C0 * S00 + C1 * S01 + C2 * S02), dC1 = 2.f * (C0 * S01 + C1 * S11 + C2 * S12),
-                dC2 = 2.f * (C0 * S02 + C1 * S12 + C2 * S22);
-    a.dL_dscale[3 * (size_t)idx] = R00 * dA0 + R01 * dA1 + R02 * dA2;
-    a.dL_dscale[3 * (size_t)idx + 1] = R10 * dB0 + R11 * dB1 + R12 * dB2;
-    a.dL_dscale[3 * (size_t)idx + 2] = R20 * dC0 + R21 * dC1 + R22 * dC2;
-    // E[i][j] = s_i * dM[i][j]
-    const float E00 = sx * dA0, E01 = sx * dA1, E02 = sx * dA2;
-    const float E10 = sy * dB0, E11 = sy * dB1, E12 = sy * dB2;
-    const float E20 = sz * dC0, E21 = sz * dC1, E22 = sz * dC2;
-    float4 dq;
-    dq.x = 2.f * qz * (E01 - E10) + 2.f * qy * (E20 - E02) + 2.f * qx * (E12 - E21);
-    dq.y = 2.f * qy * (E10 + E01) + 2.f * qz * (E20 + E02) + 2.f * qr * (E12 - E21) - 4.f * qx * (E22 + E11);
-    dq.z = 2.f * qx * (E10 + E01) + 2.f * qr * (E20 - E02) + 2.f * qz * (E12 + E21) - 4.f * qy * (E22 + E00);
-    dq.w = 2.f * qr * (E01 - E10) + 2.f * qx * (E20 + E02) + 2.f * qy * (E12 + E21) - 4.f * qz * (E11 + E00);
-    reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
-  }
 }
 
 }  // namespace
@@ -356,6 +372,7 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
   const bool factored = a.shs && (f.flags & GSR_BWD_SH_FACTORED);
   a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && (factored || al16(f.dL_dsh));
   a.assign_all = (f.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) ? 1 : 0;
+  a.row_state = a.assign_all ? f.row_state : nullptr;
   const int blocks = (a.P - a.first + kBlock - 1) / kBlock;
   if (a.vec_sh) {
     constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);

@@ -71,7 +71,7 @@ class RasterContext:
     """One (Gaussian set, image size) rasterization context on one device."""
 
     def __init__(self, P: int, M: int, width: int, height: int, device, sh_degree: int = 3, sync_free: bool = True,
-                 grad_flat: Optional[torch.Tensor] = None):
+                 grad_flat: Optional[torch.Tensor] = None, track_rows: bool = True):
         """sync_free: after a first frame has told how many (Gaussian, tile) instances the scene produces, later
         forwards go through gsr_forward_presized — the binning arena is kept 30 % larger than the largest R seen
         and the host never waits for the GPU inside a forward. `check()` (any time after a synchronisation the
@@ -98,6 +98,10 @@ class RasterContext:
                                                for n, (off, w) in at.items()}
         self.param_grad_floats = param_floats
         self.sh_floats = sh_floats  # [0, sh_floats): dL_dsh; [sh_floats, param_grad_floats): the other 11 per Gaussian
+        # which Gaussians' assigned gradient outputs may be non-zero (gsr_bwd_args.row_state): culled Gaussians whose
+        # outputs are still zero from an earlier frame are not zero-filled again. 1 = unknown (a caller's own buffer).
+        self.track_rows = bool(track_rows)
+        self.row_state = torch.ones((self.P,), dtype=torch.uint8, device=self.device)
         self.num_rendered = 0
         self._fwd_args: Optional[_lib.FwdArgs] = None
         self._keep = None
@@ -208,6 +212,13 @@ class RasterContext:
         a.flags = _lib.BWD_OUTPUTS_UNINITIALIZED | (_lib.BWD_ACCUMULATORS_ZEROED if accumulators_zeroed else 0)
         a.flags |= {"all": 0, "blend": _lib.BWD_ONLY_BLEND, "geom": _lib.BWD_ONLY_GEOM}[part]
         a.flags |= _lib.BWD_SH_FACTORED if sh_factored else 0
+        # (the state describes mean3D / cov3D / scale / rot and, unless factored, the SH rows: a context that mixes
+        # factored and dense backwards must not skip SH rows on the strength of a factored frame)
+        if self.track_rows and part in ("all", "geom"):
+            if sh_factored != getattr(self, "_rows_factored", sh_factored):
+                self.row_state.fill_(1)
+            self._rows_factored = sh_factored
+            a.row_state = self.row_state.data_ptr()
         if gaussian_range is not None:
             if part != "geom":
                 raise ValueError("gaussian_range needs part == 'geom'")
@@ -259,6 +270,11 @@ class RasterContext:
         slots = self._unchecked[before:]
         del self._unchecked[before:]
         return CapturedFrame(self, graph, slots, self._fwd_args, (step_fn, self._keep))
+
+    def invalidate_grads(self) -> None:
+        """Call after anything but this context's backward wrote into the gradient buffer (a fill, an in-place
+        collective over it): the next backward rewrites every Gaussian's outputs, culled ones included."""
+        self.row_state.fill_(1)
 
     def param_grads(self) -> torch.Tensor:
         """Flat view of the gradients of the optimised parameters (what a window all-reduces)."""

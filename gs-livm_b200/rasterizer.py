@@ -128,19 +128,23 @@ class RenderArena:
         self._unchecked.append(slot)
         return self._status[slot].data_ptr()
 
-    def check(self) -> bool:
-        if not self._unchecked:
+    def check(self, sync: bool = True, keep_last: int = 0) -> bool:
+        """sync=False: the caller has already waited for the renders in question (e.g. on an event behind a step whose
+        successor is already in flight); keep_last: the newest `keep_last` renders are still running and stay pending."""
+        n = len(self._unchecked) - max(0, int(keep_last))
+        if n <= 0:
             return True
-        torch.cuda.current_stream(self.device).synchronize()
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
         # (numpy view of the pinned words: this runs once per step between two GPU launches, and a handful of torch
         # CPU ops here cost more than the camera upload)
         words = self._status_np
         ok, worst = True, 0
-        for slot in self._unchecked:
+        for slot in self._unchecked[:n]:
             if int(words[slot, 3]) != 0:  # the frame had more instances than the arena was carved for
                 ok = False
                 worst = max(worst, int(words[slot, 0]))
-        self._unchecked = []
+        del self._unchecked[:n]
         if not ok:
             self.capacity = int(worst * 1.3) + 65536
         return ok

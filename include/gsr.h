@@ -120,6 +120,13 @@ typedef struct gsr_bwd_args {
   float* dL_drot;        /* [P,4] */
   int debug;
   int flags;             /* 0 = the reference's contract (all 9 outputs pre-zeroed by the caller); GSR_BWD_* bits */
+  unsigned char* row_state; /* optional, with GSR_BWD_OUTPUTS_UNINITIALIZED: P bytes owned by the caller, all 1 when the
+                            * five assigned outputs hold arbitrary data (e.g. freshly allocated), kept by the library
+                            * from then on: != 0 <=> the outputs of that Gaussian may be non-zero. A culled Gaussian
+                            * whose outputs are still zero from an earlier backward is then skipped instead of being
+                            * zero-filled again (256 B per Gaussian per frame). NULL: every culled Gaussian is written.
+                            * The same five arrays must be passed every time; with GSR_BWD_SH_FACTORED the state covers
+                            * the other four. */
   int range_first;       /* with GSR_BWD_ONLY_GEOM: the per-Gaussian kernel covers Gaussians [range_first, range_first + */
   int range_count;       /* range_count) only (range_count == 0: all P) -- a window exchange pipelines it in chunks */
 } gsr_bwd_args;

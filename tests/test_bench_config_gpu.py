@@ -123,6 +123,7 @@ def test_bench_scene_sync_free_and_captured_paths_match_reference_cuda(bench_sce
     frames = [ctx.capture_step(sc, cams[k], dC, dS) for k in range(WINDOW)]
     for k in (3, 0, 7, 4):
         ctx.grad_flat.fill_(float("nan"))
+        ctx.invalidate_grads()
         frames[k].replay()
         torch.cuda.synchronize()
         assert ctx.check()
@@ -169,6 +170,7 @@ def test_config4_five_million_gaussians_1920x1200_heavy_overlap(built_library, c
         _check_against_reference(_context_outputs(ctx, case, ctx.last_rendered), ref, "config 4 presized", tol)
     frame = ctx.capture_step(sc, cam, dC, dS)
     ctx.grad_flat.fill_(float("nan"))
+    ctx.invalidate_grads()
     frame.replay()
     torch.cuda.synchronize()
     assert ctx.check()

@@ -203,6 +203,7 @@ def test_raster_context_matches_operator_and_reuses_memory(built_library, cuda_d
         dC.copy_(case.dL_dcolor.to(dev) * scale)
         dS.copy_(case.dL_dacc.to(dev) * scale)
         ctx.grad_flat.fill_(float("nan"))  # every element must be rewritten by the replay
+        ctx.invalidate_grads()
         frame.replay()
         torch.cuda.synchronize()
         assert ctx.check()

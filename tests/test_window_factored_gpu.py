@@ -34,6 +34,7 @@ def test_one_view_rows_equal_geom_bwd_bit_for_bit(P, chunks, built_library, cuda
     sc, cams, ex, ctx, dC, dS = _setup(P, dev, 1, chunks=chunks)
     ex.cam_centres[0].copy_(cams[0].camera_center)
     ctx.grad_flat.fill_(float("nan"))
+    ctx.invalidate_grads()
     ex.render_step(ctx, sc, cams[0], dC, dS, parity=0)
     torch.cuda.synchronize()
     got = {n: ctx.grads[n].clone() for n in ("dL_dsh", "dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcov3D")}
@@ -47,6 +48,7 @@ def test_one_view_rows_equal_geom_bwd_bit_for_bit(P, chunks, built_library, cuda
     # ... and the whole thing replayed from a CUDA graph, on the other parity
     frame = ctx.capture(lambda: ex.render_step(ctx, sc, cams[0], dC, dS, parity=1))
     ctx.grad_flat.fill_(float("nan"))
+    ctx.invalidate_grads()
     frame.replay()
     torch.cuda.synchronize()
     assert ctx.check()

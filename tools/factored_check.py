@@ -36,7 +36,7 @@ for reduce_mode, push_mode, sparse, track in combos:
         if rank == 0:
             print(f"factored reduce={reduce_mode} push={push_mode}: skipped ({e})", flush=True)
         continue
-    ctx = engine.RasterContext(P, 16, W, H, dev, 3, grad_flat=ex.flat)
+    ctx = engine.RasterContext(P, 16, W, H, dev, 3, grad_flat=ex.flat, track_rows=False)
     n_param = ctx.param_grad_floats
 
     def cams_of(i):
@@ -132,7 +132,7 @@ if len(sys.argv) > 2:
 # the dense exchange for comparison (window.GradExchange, as bench.py used it in round 1)
 grad_floats = 75 * P
 exd = window.GradExchange(grad_floats, 59 * P, dev, sparse_rows=(0, P, 48))
-ctx = engine.RasterContext(P, 16, W, H, dev, 3, grad_flat=exd.flat)
+ctx = engine.RasterContext(P, 16, W, H, dev, 3, grad_flat=exd.flat, track_rows=False)
 for k in range(8):
     ctx.forward(sc, cams[k]); ctx.backward(dC, dS)
     if not ctx.check():
