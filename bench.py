@@ -714,13 +714,21 @@ def time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, ce
     flat_p = torch.zeros(param_floats, dtype=torch.float32, device=dev)
     views = {"shs": ("dL_dsh", (P, 16, 3)), "means3D": ("dL_dmean3D", (P, 3)), "scales": ("dL_dscale", (P, 3)),
              "rotations": ("dL_drot", (P, 4)), "opacities": ("dL_dopacity", (P, 1))}
+    # GaussianModel's RAW parameters (gaussian.cuh:40-54): log-scales, logit-opacities, unnormalised quaternions, and the
+    # SH coefficients as ONE [P,16,3] array (no torch::cat per render); the kernels apply the activations themselves
+    from gs_livm_b200 import _lib as lib_
+    op = sc["opacities"].clamp(1e-4, 1 - 1e-4)
+    raw = {"shs": sc["shs"], "means3D": sc["means3D"], "scales": torch.log(sc["scales"]), "rotations": 1.7 * sc["rotations"],
+           "opacities": torch.log(op / (1 - op))}
     scp = dict(sc)
     for name, (gname, shape) in views.items():
         off, w = at[gname]
         v = flat_p[off:off + w * P].view(shape)
-        v.copy_(sc[name].reshape(shape))
+        v.copy_(raw[name].reshape(shape))
         scp[name] = v if name != "opacities" else v.view(sc["opacities"].shape)
-    groups = [(at[g][0], at[g][1] * P, 0.0) for g in ("dL_dsh", "dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity")]
+    # learning rates of GaussianModel::Training_setup (gaussian.cu:396-428), scaled to ZERO here (see the note below)
+    groups = [(at["dL_dsh"][0], 48 * P, 0.0, 48, 0, 3, 0.0)] + [
+        (at[g][0], at[g][1] * P, 0.0) for g in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity")]
     adam = train.FusedAdam(flat_p, groups)
     loss_fn = train.ImageLoss(W, H, dev, lambda_dssim=0.2)
     g = torch.Generator().manual_seed(SEED + 9)
@@ -732,7 +740,7 @@ def time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, ce
         cam = cams[pose_of(i)]
         main = torch.cuda.current_stream(dev)
         if exchange is None:
-            ctx.forward(scp, cam)
+            ctx.forward(scp, cam, activations=lib_.ACT_ALL)
             _, dimg = loss_fn(ctx.out_color, target)
             ctx.backward(dimg, dS0)
         else:
@@ -740,7 +748,7 @@ def time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, ce
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 ctx.prepare_backward()
-            ctx.forward(scp, cam)
+            ctx.forward(scp, cam, activations=lib_.ACT_ALL)
             _, dimg = loss_fn(ctx.out_color, target)
             main.wait_stream(side)
             ctx.backward(dimg, dS0, accumulators_zeroed=True, part="blend")
@@ -801,9 +809,11 @@ def time_step_with_optimizer(args, rank, world, dev, ctx, exchange, sc, cams, ce
     return {"value": world / (ms * 1e-3), "unit": "frames/s", "ms_per_step": round(ms, 4), "fits": bool(ok),
             "t_adam_ms": round(a0.elapsed_time(a1) / 10, 4), "t_loss_ms": round(a1.elapsed_time(a2) / 10, 4),
             "launch": mode,
-            "note": "forward + gsr_image_loss (L1 + 0.2 DSSIM -> dL_dC) + backward%s + gsr_adam_step over 59 floats per "
-                    "Gaussian (flat buffer, 6 groups' layout, eps 1e-15); learning rates 0 so the timed scene stays the "
-                    "bench scene; parameters are the activated values (activation fusion, SURVEY 8f-f1, is not built)"
+            "note": "forward on GaussianModel's RAW parameters (sigmoid / exp / normalize fused into preprocess and "
+                    "geom_bwd, SH as one [P,16,3] array: no LibTorch activation kernels, no torch::cat) + gsr_image_loss "
+                    "(L1 + 0.2 DSSIM -> dL_dC) + backward%s + gsr_adam_step over 59 floats per Gaussian (flat buffer, the "
+                    "reference's six learning-rate groups incl. the dc/rest pattern over the SH rows, eps 1e-15); "
+                    "learning rates 0 so the timed scene stays the bench scene"
                     % (" + factored exchange" if exchange else "")}
 
 

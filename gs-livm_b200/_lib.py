@@ -27,7 +27,7 @@ class FwdArgs(C.Structure):
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("cam_pos", C.c_void_p),
         ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("prefiltered", C.c_int),
         ("out_color", C.c_void_p), ("out_depth", C.c_void_p), ("out_acc", C.c_void_p),
-        ("radii", C.c_void_p), ("debug", C.c_int),
+        ("radii", C.c_void_p), ("debug", C.c_int), ("activations", C.c_int),
     ]
 
 
@@ -43,7 +43,8 @@ class BwdArgs(C.Structure):
         ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p),
         ("dL_dcolor", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p),
         ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p), ("dL_drot", C.c_void_p), ("debug", C.c_int),
-        ("flags", C.c_int), ("row_state", C.c_void_p), ("range_first", C.c_int), ("range_count", C.c_int),
+        ("flags", C.c_int), ("row_state", C.c_void_p), ("activations", C.c_int), ("opacities", C.c_void_p), ("range_first", C.c_int),
+        ("range_count", C.c_int),
     ]
 
 
@@ -52,6 +53,8 @@ BWD_ACCUMULATORS_ZEROED = 2
 BWD_SH_FACTORED = 4
 BWD_ONLY_BLEND = 8
 BWD_ONLY_GEOM = 16
+ACT_OPACITY_SIGMOID, ACT_SCALE_EXP, ACT_ROTATION_NORMALIZE = 1, 2, 4
+ACT_ALL = 7
 WINDOW_CH_DONE, WINDOW_CH_PUSHED = 2, 3
 ABI_VERSION = 5  # include/gsr.h GSR_ABI_VERSION this binding was written against
 
@@ -66,7 +69,8 @@ class WindowComm(C.Structure):
 
 
 class AdamGroup(C.Structure):
-    _fields_ = [("first", C.c_size_t), ("count", C.c_size_t), ("lr", C.c_float)]
+    _fields_ = [("first", C.c_size_t), ("count", C.c_size_t), ("lr", C.c_float), ("period", C.c_uint), ("phase_lo", C.c_uint),
+                ("phase_hi", C.c_uint), ("lr_other", C.c_float)]
 
 
 class ArrayView(C.Structure):

@@ -41,6 +41,9 @@ struct GeomBwdArgs {
   int first;   // the kernel covers Gaussians [first, P): P is the END of the range here
   int vec_sh;  // M == 16 and shs / dL_dsh 16-byte aligned
   int assign_all;  // GSR_BWD_OUTPUTS_UNINITIALIZED: also write the zeros of Gaussians with radii <= 0
+  int act;                 // GSR_ACT_* bits: scales / rotations / opacities are raw parameters (see gsr.h)
+  const float* opacities;  // raw, with GSR_ACT_OPACITY_SIGMOID
+  float* dL_dopacity;      // accumulated by the blend backward w.r.t. the activated opacity; rescaled in place
   uint8_t* row_state;  // gsr_bwd_args.row_state (with assign_all): != 0 <=> the Gaussian's outputs may be non-zero; a culled
                        // Gaussian whose outputs are known to be zero already is skipped, not rewritten
 };
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   float mx = 0.f, my = 0.f, mz = 0.f;
   uint32_t cl_early = 0;
   float dRGB_early[3] = {0.f, 0.f, 0.f};
+  float act_s0 = 1.f, act_s1 = 1.f, act_s2 = 1.f, q_norm = 1.f;  // activated scales, |raw quaternion| (GSR_ACT_*)
   if (active) {
 
   const float* V = s_view;
@@ -123,10 +127,13 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
     const float* cp = a.cov3D_precomp + (size_t)idx * 6;
     c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2), c3 = __ldg(cp + 3), c4 = __ldg(cp + 4), c5 = __ldg(cp + 5);
   } else {
-    sx = __fmul_rn(__ldg(a.scales + 3 * (size_t)idx), a.scale_modifier);
-    sy = __fmul_rn(__ldg(a.scales + 3 * (size_t)idx + 1), a.scale_modifier);
-    sz = __fmul_rn(__ldg(a.scales + 3 * (size_t)idx + 2), a.scale_modifier);
-    const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+    float s0 = __ldg(a.scales + 3 * (size_t)idx), s1 = __ldg(a.scales + 3 * (size_t)idx + 1),
+          s2 = __ldg(a.scales + 3 * (size_t)idx + 2);
+    if (a.act & GSR_ACT_SCALE_EXP) s0 = expf(s0), s1 = expf(s1), s2 = expf(s2);
+    act_s0 = s0, act_s1 = s1, act_s2 = s2;
+    sx = __fmul_rn(s0, a.scale_modifier), sy = __fmul_rn(s1, a.scale_modifier), sz = __fmul_rn(s2, a.scale_modifier);
+    float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+    if (a.act & GSR_ACT_ROTATION_NORMALIZE) q = normalize_quat(q, &q_norm);
     qr = q.x, qx = q.y, qy = q.z, qz = q.w;
     const float xz = __fmul_rn(qx, qz), rx = __fmul_rn(qr, qx), rz = __fmul_rn(qr, qz);
     const float yy = __fmul_rn(qy, qy), zz = __fmul_rn(qz, qz);
@@ -231,9 +238,11 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
                   dB2 = 2.f * (B0 * S02 + B1 * S12 + B2 * S22);
       const float dC0 = 2.f * (C0 * S00 + C1 * S01 + C2 * S02), dC1 = 2.f * (C0 * S01 + C1 * S11 + C2 * S12),
                   dC2 = 2.f * (C0 * S02 + C1 * S12 + C2 * S22);
-      a.dL_dscale[3 * (size_t)idx] = R00 * dA0 + R01 * dA1 + R02 * dA2;
-      a.dL_dscale[3 * (size_t)idx + 1] = R10 * dB0 + R11 * dB1 + R12 * dB2;
-      a.dL_dscale[3 * (size_t)idx + 2] = R20 * dC0 + R21 * dC1 + R22 * dC2;
+      // (GSR_ACT_SCALE_EXP: d exp(x)/dx = exp(x), torch's exp backward: grad * result)
+      const bool raw_s = a.act & GSR_ACT_SCALE_EXP;
+      a.dL_dscale[3 * (size_t)idx] = (R00 * dA0 + R01 * dA1 + R02 * dA2) * (raw_s ? act_s0 : 1.f);
+      a.dL_dscale[3 * (size_t)idx + 1] = (R10 * dB0 + R11 * dB1 + R12 * dB2) * (raw_s ? act_s1 : 1.f);
+      a.dL_dscale[3 * (size_t)idx + 2] = (R20 * dC0 + R21 * dC1 + R22 * dC2) * (raw_s ? act_s2 : 1.f);
       // E[i][j] = s_i * dM[i][j]
       const float E00 = sx * dA0, E01 = sx * dA1, E02 = sx * dA2;
       const float E10 = sy * dB0, E11 = sy * dB1, E12 = sy * dB2;
@@ -243,7 +252,16 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
       dq.y = 2.f * qy * (E10 + E01) + 2.f * qz * (E20 + E02) + 2.f * qr * (E12 - E21) - 4.f * qx * (E22 + E11);
       dq.z = 2.f * qx * (E10 + E01) + 2.f * qr * (E20 - E02) + 2.f * qz * (E12 + E21) - 4.f * qy * (E22 + E00);
       dq.w = 2.f * qr * (E01 - E10) + 2.f * qx * (E20 + E02) + 2.f * qy * (E12 + E21) - 4.f * qz * (E11 + E00);
+      if (a.act & GSR_ACT_ROTATION_NORMALIZE) {  // through q / max(|q|, eps): (g - qn (qn . g)) / |q|
+        const float d = dq.x * qr + dq.y * qx + dq.z * qy + dq.w * qz;
+        const float inv = 1.0f / q_norm;
+        dq = make_float4((dq.x - qr * d) * inv, (dq.y - qx * d) * inv, (dq.z - qy * d) * inv, (dq.w - qz * d) * inv);
+      }
       reinterpret_cast<float4*>(a.dL_drot)[idx] = dq;
+    }
+    if (a.act & GSR_ACT_OPACITY_SIGMOID) {  // torch's sigmoid backward: grad * (1 - y) * y
+      const float y = sigmoid_ref(__ldg(a.opacities + idx));
+      a.dL_dopacity[idx] = a.dL_dopacity[idx] * ((1.0f - y) * y);
     }
 
   }  // if (active): covariance + projection part
@@ -373,6 +391,8 @@ cudaError_t launch_geom_bwd(const gsr_bwd_args& f, const GeomState& g, const int
   a.vec_sh = a.shs && f.M == 16 && al16(f.shs) && (factored || al16(f.dL_dsh));
   a.assign_all = (f.flags & GSR_BWD_OUTPUTS_UNINITIALIZED) ? 1 : 0;
   a.row_state = a.assign_all ? f.row_state : nullptr;
+  a.act = f.activations, a.opacities = f.opacities, a.dL_dopacity = f.dL_dopacity;
+  if ((a.act & GSR_ACT_OPACITY_SIGMOID) && !f.opacities) return cudaErrorInvalidValue;
   const int blocks = (a.P - a.first + kBlock - 1) / kBlock;
   if (a.vec_sh) {
     constexpr int kSmem = kBlock * kShRow * (int)sizeof(float4);

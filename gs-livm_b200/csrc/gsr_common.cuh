@@ -168,6 +168,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// torch::nn::functional::normalize(q, dim = 1): q / max(|q|_2, 1e-12) (GaussianModel::Get_rotation, gaussian.cuh:47-49);
+// n_out = the denominator (the backward needs it)
+__device__ __forceinline__ float4 normalize_quat(const float4 q, float* n_out = nullptr) {
+  const float n = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)),
+                                             __fadd_rn(__fmul_rn(q.z, q.z), __fmul_rn(q.w, q.w)))), 1e-12f);
+  if (n_out) *n_out = n;
+  return make_float4(__fdiv_rn(q.x, n), __fdiv_rn(q.y, n), __fdiv_rn(q.z, n), __fdiv_rn(q.w, n));
+}
+// GaussianModel::Get_opacity = torch::sigmoid (gaussian.cuh:44-46), as LibTorch's kernel computes it
+__device__ __forceinline__ float sigmoid_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

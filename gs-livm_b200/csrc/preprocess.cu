@@ -44,6 +44,7 @@ struct PreArgs {
   uint8_t* clamped;
   uint32_t* tile_count;  // [tiles] instances per tile, accumulated here (tile_sort.cu)
   int vec_ok;  // means3D/scales/shs 16-byte aligned -> float4 staging
+  int act;     // GSR_ACT_* bits: opacities / scales / rotations are raw parameters, activated on load
 };
 
 // a*b + c*d + e*f as nvcc contracts the reference's left-to-right sums:
@@ -135,6 +136,15 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
     op_in = __ldg(a.opacities + idx);
   }
   __syncthreads();
+  // GaussianModel's activations (gaussian.cuh:40-54) on load, written like LibTorch's kernels compute them
+  if (a.act) {
+    if ((a.act & GSR_ACT_SCALE_EXP) && a.scales && tid < n) {  // own three values only: no hazard
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s_scales[3 * tid + c] = expf(s_scales[3 * tid + c]);
+    }
+    if (a.act & GSR_ACT_OPACITY_SIGMOID) op_in = sigmoid_ref(op_in);
+    if (a.act & GSR_ACT_ROTATION_NORMALIZE) rot_in = normalize_quat(rot_in);
+  }
 
   int out_radius = 0;
   int rect_x0 = 0, rect_y0 = 0, rect_w = 1;
@@ -443,6 +453,7 @@ cudaError_t launch_preprocess_fwd(const gsr_fwd_args& f, const GeomState& g, int
   a.viewmatrix = f.viewmatrix, a.projmatrix = f.projmatrix, a.cam_pos = f.cam_pos;
   a.radii = radii, a.rec = g.rec, a.tiles_touched = g.tiles_touched, a.clamped = g.clamped;
   a.tile_count = tile_count;
+  a.act = f.activations;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   a.vec_ok = al16(f.means3D) && (!f.scales || al16(f.scales));
   const bool rot_ok = f.cov3D_precomp || al16(f.rotations);

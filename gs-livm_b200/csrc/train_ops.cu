@@ -200,26 +200,54 @@ __global__ void loss_finish_kernel(const float* __restrict__ sums, float* __rest
 // ---- Adam -------------------------------------------------------------------------------------------------------
 struct AdamGroups {
   unsigned long long begin[8], end[8];  // element ranges of the flat buffers
-  float lr[8];
+  float lr[8], lr_other[8];
+  unsigned period[8], lo[8], hi[8];     // period 0: lr everywhere; else lr on [lo, hi) of every row, lr_other elsewhere
   int n;
 };
 
+__device__ __forceinline__ void adam_element(float& p, float grad, float& m, float& v, float step_size, float beta1,
+                                             float beta2, float eps, float sqrt_bc2) {
+  m = m * beta1 + grad * (1.f - beta1);           // exp_avg.mul_(beta1).add_(grad, 1 - beta1)
+  v = v * beta2 + (grad * grad) * (1.f - beta2);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(v) / sqrt_bc2 + eps;  // (exp_avg_sq.sqrt() / sqrt(bc2)).add_(eps)
+  p = p - step_size * (m / denom);                // param.addcdiv_(exp_avg, denom, -step_size)
+}
+
+// 16-byte accesses where the group's range allows it (7 streams of 4 bytes per element: the step is HBM-bound), scalar
+// head / tail otherwise.
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v,
                                                         const AdamGroups groups, float beta1, float beta2, float eps,
                                                         float bc1, float sqrt_bc2) {
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (int k = 0; k < groups.n; ++k) {
-    const float step_size = groups.lr[k] / bc1;  // torch/csrc/api/src/optim/adam.cpp: lr / bias_correction1
-    const size_t end = groups.end[k];
-    for (size_t i = groups.begin[k] + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < end;
-         i += (size_t)gridDim.x * blockDim.x) {
-      const float grad = g[i];
-      const float mi = m[i] * beta1 + grad * (1.f - beta1);           // exp_avg.mul_(beta1).add_(grad, 1 - beta1)
-      const float vi = v[i] * beta2 + (grad * grad) * (1.f - beta2);  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-      const float denom = sqrtf(vi) / sqrt_bc2 + eps;                 // (exp_avg_sq.sqrt() / sqrt(bc2)).add_(eps)
-      m[i] = mi, v[i] = vi;
-      p[i] = p[i] - step_size * (mi / denom);                         // param.addcdiv_(exp_avg, denom, -step_size)
+    // torch/csrc/api/src/optim/adam.cpp: step_size = lr / bias_correction1
+    const float step_a = groups.lr[k] / bc1, step_b = groups.lr_other[k] / bc1;
+    const unsigned period = groups.period[k], lo = groups.lo[k], hi = groups.hi[k];
+    const size_t begin = groups.begin[k], end = groups.end[k];
+    auto step_of = [&](size_t i) {
+      if (period == 0) return step_a;
+      const unsigned ph = (unsigned)((i - begin) % period);
+      return (ph >= lo && ph < hi) ? step_a : step_b;
+    };
+    const size_t vb = (begin + 3) & ~(size_t)3, ve = end & ~(size_t)3;  // the 16-byte aligned middle
+    if (vb < ve) {
+      for (size_t i = vb + 4 * t0; i < ve; i += 4 * stride) {
+        float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
+               vv = *reinterpret_cast<float4*>(v + i);
+        const float4 gg = *reinterpret_cast<const float4*>(g + i);
+        adam_element(pp.x, gg.x, mm.x, vv.x, step_of(i), beta1, beta2, eps, sqrt_bc2);
+        adam_element(pp.y, gg.y, mm.y, vv.y, step_of(i + 1), beta1, beta2, eps, sqrt_bc2);
+        adam_element(pp.z, gg.z, mm.z, vv.z, step_of(i + 2), beta1, beta2, eps, sqrt_bc2);
+        adam_element(pp.w, gg.w, mm.w, vv.w, step_of(i + 3), beta1, beta2, eps, sqrt_bc2);
+        *reinterpret_cast<float4*>(m + i) = mm, *reinterpret_cast<float4*>(v + i) = vv;
+        *reinterpret_cast<float4*>(p + i) = pp;
+      }
     }
+    // head [begin, vb) and tail [ve, end): at most three elements each (or the whole of a tiny range)
+    const size_t head_end = vb < end ? vb : end, tail_begin = ve > head_end ? ve : head_end;
+    for (size_t i = begin + t0; i < head_end; i += stride) adam_element(p[i], g[i], m[i], v[i], step_of(i), beta1, beta2, eps, sqrt_bc2);
+    for (size_t i = tail_begin + t0; i < end; i += stride) adam_element(p[i], g[i], m[i], v[i], step_of(i), beta1, beta2, eps, sqrt_bc2);
   }
 }
 
@@ -270,12 +298,15 @@ int gsr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   size_t total = 0;
   for (int k = 0; k < n_groups; ++k) {
     g.begin[k] = groups[k].first, g.end[k] = groups[k].first + groups[k].count, g.lr[k] = groups[k].lr;
+    g.period[k] = groups[k].period, g.lo[k] = groups[k].phase_lo, g.hi[k] = groups[k].phase_hi;
+    g.lr_other[k] = groups[k].lr_other;
+    if (g.period[k] && (g.lo[k] > g.hi[k] || g.hi[k] > g.period[k])) return GSR_ERR_INVALID;
     total += groups[k].count;
   }
   if (total == 0) return GSR_OK;
   // bias corrections in double on the host like LibTorch (std::pow on doubles), applied in float on the device
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  size_t blocks = (total / n_groups + 255) / 256;
+  size_t blocks = (total / n_groups / 4 + 255) / 256;
   const size_t cap = (size_t)device_sm_count() * 8;
   blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
   adam_step_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(

@@ -114,8 +114,13 @@ class RasterContext:
 
     # ------------------------------------------------------------------------------------------------
     def forward(self, scene: Dict[str, torch.Tensor], cam: Camera, scale_modifier: float = 1.0, debug: bool = False,
-                redo: bool = False):
+                redo: bool = False, activations: int = 0):
+        """activations (_lib.ACT_* bits): scene["opacities"] / ["scales"] / ["rotations"] are GaussianModel's RAW
+        parameters and the kernels apply sigmoid / exp / normalize themselves; the matching
+        backward then returns gradients w.r.t. the raw parameters."""
         a = _lib.FwdArgs()
+        a.activations = int(activations)
+        self._activations = int(activations)
         a.P, a.D, a.M, a.width, a.height = self.P, self.D, self.M, self.W, self.H
         a.background, a.means3D, a.shs = scene["background"].data_ptr(), scene["means3D"].data_ptr(), scene["shs"].data_ptr()
         a.colors_precomp, a.opacities, a.scales = None, scene["opacities"].data_ptr(), scene["scales"].data_ptr()
@@ -212,6 +217,7 @@ class RasterContext:
         a.flags = _lib.BWD_OUTPUTS_UNINITIALIZED | (_lib.BWD_ACCUMULATORS_ZEROED if accumulators_zeroed else 0)
         a.flags |= {"all": 0, "blend": _lib.BWD_ONLY_BLEND, "geom": _lib.BWD_ONLY_GEOM}[part]
         a.flags |= _lib.BWD_SH_FACTORED if sh_factored else 0
+        a.activations, a.opacities = getattr(self, "_activations", 0), f.opacities
         # (the state describes mean3D / cov3D / scale / rot and, unless factored, the SH rows: a context that mixes
         # factored and dense backwards must not skip SH rows on the strength of a factored frame)
         if self.track_rows and part in ("all", "geom"):

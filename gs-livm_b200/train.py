@@ -45,7 +45,10 @@ class ImageLoss:
 
 class FusedAdam:
     """Adam over ONE flat float32 parameter buffer with per-group learning rates, eps 1e-15 and the default betas like
-    the reference (gaussian.cu:396-428). groups: sequence of (first_element, count, lr)."""
+    the reference (gaussian.cu:396-428). groups: sequence of (first_element, count, lr) or
+    (first_element, count, lr, period, phase_lo, phase_hi, lr_other): rows of `period` elements whose elements
+    [phase_lo, phase_hi) take lr and the others lr_other — e.g. ONE [P,16,3] SH array instead of the reference's
+    _features_dc / _features_rest pair: (first, 48 P, lr_dc, 48, 0, 3, lr_dc / 20)."""
 
     def __init__(self, params: torch.Tensor, groups: Sequence[Tuple[int, int, float]], betas=(0.9, 0.999),
                  eps: float = 1e-15):
@@ -53,7 +56,8 @@ class FusedAdam:
             raise TypeError("FusedAdam needs a flat contiguous float32 CUDA buffer")
         if not 1 <= len(groups) <= 8:
             raise ValueError("1..8 parameter groups")
-        for first, count, _ in groups:
+        groups = [tuple(g) + (0, 0, 0, 0.0) * (len(g) == 3) for g in groups]
+        for first, count, *_ in groups:
             if first < 0 or count < 0 or first + count > params.numel():
                 raise ValueError("group outside the parameter buffer")
         self.lib = _lib.load()
@@ -61,7 +65,9 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(params)
         self.exp_avg_sq = torch.zeros_like(params)
         self.betas, self.eps, self.steps = (float(betas[0]), float(betas[1])), float(eps), 0
-        self._groups = (_lib.AdamGroup * len(groups))(*[_lib.AdamGroup(int(f), int(c), float(lr)) for f, c, lr in groups])
+        self._groups = (_lib.AdamGroup * len(groups))(*[
+            _lib.AdamGroup(int(f), int(c), float(lr), int(per), int(lo), int(hi), float(lro))
+            for f, c, lr, per, lo, hi, lro in groups])
 
     def step(self, grads: torch.Tensor) -> None:
         if grads.dtype != torch.float32 or grads.numel() < self.params.numel() or not grads.is_contiguous():

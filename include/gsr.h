@@ -84,7 +84,22 @@ typedef struct gsr_fwd_args {
   float* out_acc;              /* [1,H,W]  silhouette sum alpha*T      (forward.cu:387) */
   int* radii;                  /* [P] or NULL -> internal */
   int debug;                   /* !=0: synchronise + check after every stage (CHECK_CUDA, auxiliary.h:146-154) */
+  int activations;             /* 0: opacities / scales / rotations are activated values, as the reference passes them.
+                                * GSR_ACT_* bits: they are the RAW optimised parameters and the kernels apply the
+                                * reference's activations themselves */
 } gsr_fwd_args;
+
+/* gsr_fwd_args.activations / gsr_bwd_args.activations: GaussianModel's activations (include/gs/gs/gaussian.cuh:40-54)
+ * fused into the kernels instead of running as LibTorch elementwise ops (and their autograd backwards) around every
+ * render. With a bit set the corresponding input is the raw parameter, the forward applies
+ *   opacity = sigmoid(_opacity) = 1 / (1 + exp(-x)),  scale = exp(_scaling),  rotation = _rotation / max(|_rotation|, 1e-12)
+ * on load, and the backward returns the gradient w.r.t. the RAW parameter in the same output array
+ * (dL_dopacity, dL_dscale, dL_drot). The SH coefficients need no entry point of their own: pass ONE [P,M,3] array
+ * (what torch::cat({_features_dc, _features_rest}, 1) would build, render_utils.cuh:38-44) that the optimiser updates
+ * in place -- gsr_adam_step takes the two learning rates as a pattern over the row (gsr_adam_group.period). */
+#define GSR_ACT_OPACITY_SIGMOID 1
+#define GSR_ACT_SCALE_EXP 2
+#define GSR_ACT_ROTATION_NORMALIZE 4
 
 /* Arguments of one backward; == reference Rasterizer::backward parameters. Gradient outputs must be
  * pre-zeroed by the caller (rasterize_points.cu:173-181); there is no dL_ddepth input (rasterizer.cu:77-80). */
@@ -127,6 +142,9 @@ typedef struct gsr_bwd_args {
                             * zero-filled again (256 B per Gaussian per frame). NULL: every culled Gaussian is written.
                             * The same five arrays must be passed every time; with GSR_BWD_SH_FACTORED the state covers
                             * the other four. */
+  int activations;       /* GSR_ACT_* bits as given to the forward; scales / rotations / opacities are then the raw
+                          * parameters and dL_dscale / dL_drot / dL_dopacity are gradients w.r.t. them */
+  const float* opacities; /* [P]; only read with GSR_ACT_OPACITY_SIGMOID */
   int range_first;       /* with GSR_BWD_ONLY_GEOM: the per-Gaussian kernel covers Gaussians [range_first, range_first + */
   int range_count;       /* range_count) only (range_count == 0: all P) -- a window exchange pipelines it in chunks */
 } gsr_bwd_args;
@@ -333,6 +351,11 @@ GSR_API int gsr_window_allreduce_rest(const gsr_window_comm* comm, void* const* 
 typedef struct gsr_adam_group {
   size_t first, count; /* element range [first, first + count) */
   float lr;
+  /* period == 0: lr applies to the whole range. Otherwise the range is rows of `period` elements: the elements
+   * [phase_lo, phase_hi) of every row take lr, the others lr_other. E.g. ONE [P,16,3] SH array instead of the
+   * reference's _features_dc / _features_rest pair: {period 48, [0,3), lr_dc, lr_other = lr_dc / 20} (gaussian.cu:406-412). */
+  unsigned period, phase_lo, phase_hi;
+  float lr_other;
 } gsr_adam_group;
 GSR_API size_t gsr_image_loss_scratch_floats(int width, int height);
 GSR_API int gsr_image_loss(const float* image, const float* target, int width, int height, float lambda_dssim,
