@@ -77,7 +77,16 @@ class GradExchange:
                     self.why = "no multicast support: using p2p"
             except Exception as e:  # no peer access / symmetric memory unavailable
                 self.why = "symmetric memory unavailable (%s)" % (repr(e)[:200],)
+                self.flat, self.hdl = None, None
+        if self.world > 1 and self.device.type == "cuda" and prefer in ("auto", "multimem", "p2p"):
+            # the ranks must agree: a rank that fell back on its own would meet its peers in different collectives
+            ok = torch.tensor([1 if self.flat is not None else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0 and self.flat is not None:
+                self.flat, self.hdl, self.mode = None, None, "nccl"
+                self.why = "symmetric memory unavailable on another rank"
         if self.flat is None:
+            self.mode = "nccl"
             self.flat = torch.zeros(int(numel_total), dtype=torch.float32, device=self.device)
         if self.mode != "nccl":
             from . import _lib
@@ -211,16 +220,25 @@ class FactoredExchange:
         total = self._slots_at + 2 * self.n_views * self._slot_stride  # two parities x one slot per view
         self.hdl, mc = None, 0
         if self.world > 1:
-            import torch.distributed._symmetric_memory as symm_mem
-            grp = group if group is not None else dist.group.WORLD
-            self.buf = symm_mem.empty(total, dtype=torch.float32, device=self.device)
-            self.hdl = symm_mem.rendezvous(self.buf, grp)
-            off = int(getattr(self.hdl, "offset", 0) or 0)
-            ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
-            if ptrs[self.rank] != self.buf.data_ptr():
-                raise RuntimeError("symmetric buffer pointer mismatch")
-            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-            mc = mc + off if mc else 0
+            err, ptrs = "", []
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                self.buf = symm_mem.empty(total, dtype=torch.float32, device=self.device)
+                self.hdl = symm_mem.rendezvous(self.buf, grp)
+                off = int(getattr(self.hdl, "offset", 0) or 0)
+                ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
+                if ptrs[self.rank] != self.buf.data_ptr():
+                    err = "symmetric buffer pointer mismatch"
+                mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+                mc = mc + off if mc else 0
+            except Exception as e:  # no peer access / symmetric memory unavailable
+                err = "symmetric memory unavailable (%s)" % (repr(e)[:200],)
+            # every rank raises or none does (a rank that gave up alone would leave its peers inside a collective)
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                raise RuntimeError("FactoredExchange: " + (err or "symmetric memory unavailable on another rank"))
         else:
             self.buf = torch.empty(total, dtype=torch.float32, device=self.device)
             ptrs = [self.buf.data_ptr()]

@@ -185,3 +185,31 @@ def assert_integer_stages_equal(ours: Dict, ref: Dict, check_unsorted: bool = Fa
                                       np.asarray(ref["point_list_keys_unsorted"]).astype(np.uint64))
         np.testing.assert_array_equal(np.asarray(ours["point_list_unsorted"]).astype(np.int64),
                                       np.asarray(ref["point_list_unsorted"]).astype(np.int64))
+
+
+# ------------------------------------------------------------------------------------------------ fragile pixels
+FRAGILE_STATS = {"cases": 0, "cases_with_fragile_pixels": 0, "fragile_pixels": 0, "gaussians_masked": 0, "gaussians": 0}
+
+
+def fragile_gaussian_rows(ref: Dict, case: "Case") -> np.ndarray:
+    """Bool [P]: Gaussians whose gradients the CPU oracle cannot vouch for — those in the list of a tile that contains
+    a pixel the oracle flagged fragile (a discrete decision within rounding distance of its threshold, where two
+    correct expf implementations may differ). Everything else is compared; the counts are accumulated in
+    FRAGILE_STATS and printed by the tests instead of the whole gradient check being skipped."""
+    P = case.P
+    mask = np.zeros(P, dtype=bool)
+    frag = (np.asarray(ref["fragile"]) != 0).reshape(case.height, case.width)
+    FRAGILE_STATS["cases"] += 1
+    FRAGILE_STATS["gaussians"] += P
+    if not frag.any():
+        return mask
+    FRAGILE_STATS["cases_with_fragile_pixels"] += 1
+    FRAGILE_STATS["fragile_pixels"] += int(frag.sum())
+    grid_x = (case.width + 15) // 16
+    ys, xs = np.nonzero(frag)
+    tiles = np.unique((ys // 16) * grid_x + xs // 16)
+    ranges, plist = np.asarray(ref["ranges"]).astype(np.int64), np.asarray(ref["point_list"]).astype(np.int64)
+    for t in tiles:
+        mask[plist[ranges[t, 0]:ranges[t, 1]]] = True
+    FRAGILE_STATS["gaussians_masked"] += int(mask.sum())
+    return mask

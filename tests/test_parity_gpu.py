@@ -44,11 +44,28 @@ def check_forward_exact(ours, ref, case, vs_cuda_reference: bool):
         assert np.abs(np.asarray(ours["accum_alpha"])[sel] - np.asarray(ref_T)[sel]).max() <= 1e-6
 
 
-def check_backward(ours, ref, case):
+def check_backward(ours, ref, case, skip_rows=None):
+    """skip_rows (bool [P]): Gaussians left out of the comparison (helpers.fragile_gaussian_rows)."""
+    keep = None if skip_rows is None or not skip_rows.any() else ~skip_rows
     for name in helpers.GRAD_NAMES:
         if name == "dL_dsh" and case.use_colors:
             continue
-        assert_grad(name, np.asarray(ours[name]).reshape(np.asarray(ref[name]).shape), ref[name])
+        want = np.asarray(ref[name])
+        got = np.asarray(ours[name]).reshape(want.shape)
+        if keep is not None:
+            want, got = want[keep], got[keep]
+        assert_grad(name, got, want)
+
+
+def check_backward_vs_cpu_oracle(ours, ref, case):
+    """Gradients against the fp64 CPU oracle for every Gaussian that touches no fragile pixel's tile (the others are
+    masked, counted and printed -- not a reason to skip the rest)."""
+    rows = helpers.fragile_gaussian_rows(ref, case)
+    if rows.any():
+        print("fragile pixels: %d; %d of %d Gaussians masked in the gradient check" % (
+            int((np.asarray(ref["fragile"]) != 0).sum()), int(rows.sum()), case.P))
+    assert rows.mean() < 0.5 or case.P < 100, "too many Gaussians masked: %.2f" % rows.mean()
+    check_backward(ours, ref, case, skip_rows=rows)
 
 
 # ------------------------------------------------------------------------------------------ (1) golden vectors
@@ -79,8 +96,7 @@ def test_against_cpu_oracle(P, seed, deg, intr, heavy, close, sort_path, blend, 
     ref = helpers.run_oracle_cpu(case)
     ours = helpers.run_ours(case, cuda_device, sort_path=sort_path, blend=blend)
     check_forward_exact(ours, ref, case, vs_cuda_reference=False)
-    if not (ref["fragile"] != 0).any():
-        check_backward(ours, ref, case)
+    check_backward_vs_cpu_oracle(ours, ref, case)
 
 
 def test_nothing_visible(built_library, cuda_device):
@@ -106,8 +122,7 @@ def test_colors_precomp_and_sh_paths_agree_on_geometry(built_library, cuda_devic
     np.testing.assert_array_equal(a["point_list_keys"], b["point_list_keys"])
     np.testing.assert_array_equal(helpers.bits(a["out_depth"]), helpers.bits(b["out_depth"]))
     check_forward_exact(b, ref, case, vs_cuda_reference=False)
-    if not (ref["fragile"] != 0).any():
-        check_backward(b, ref, case)
+    check_backward_vs_cpu_oracle(b, ref, case)
 
 
 def test_precomputed_covariance_path(built_library, cuda_device):
@@ -128,9 +143,9 @@ def test_precomputed_covariance_path(built_library, cuda_device):
     # (Gaussians culled only by the 0.3 m scale test of the scale/rotation path are not culled here)
     both = vis & (np.asarray(ref_sr["radii"]) > 0)
     np.testing.assert_array_equal(np.asarray(ours["radii"])[both], np.asarray(ours_sr["radii"])[both])
-    if not (ref["fragile"] != 0).any():
-        for name in ("dL_dmean2D", "dL_dcolor", "dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dsh"):
-            assert_grad(name, np.asarray(ours[name]).reshape(np.asarray(ref[name]).shape), ref[name])
+    keep = ~helpers.fragile_gaussian_rows(ref, c)
+    for name in ("dL_dmean2D", "dL_dcolor", "dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dsh"):
+        assert_grad(name, np.asarray(ours[name]).reshape(np.asarray(ref[name]).shape)[keep], np.asarray(ref[name])[keep])
     assert float(np.abs(ours["dL_dscale"]).max()) == 0.0 and float(np.abs(ours["dL_drot"]).max()) == 0.0
 
 
@@ -308,3 +323,11 @@ def test_full_size_backward_is_linear_in_upstream_gradient(full_size, cuda_devic
     culled = o["radii"] == 0
     for n in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dsh", "dL_dopacity"):
         assert not o[n][culled].any(), "culled Gaussians receive no gradient"
+
+
+def test_zz_report_fragile_pixel_statistics():
+    """(runs last in this file) How often the CPU-oracle comparisons had to mask Gaussians because of fragile pixels."""
+    st = helpers.FRAGILE_STATS
+    print("CPU-oracle gradient checks: %(cases)d cases, %(cases_with_fragile_pixels)d with fragile pixels "
+          "(%(fragile_pixels)d pixels), %(gaussians_masked)d of %(gaussians)d Gaussians masked" % st)
+    assert st["cases"] > 0 and st["gaussians_masked"] <= 0.2 * st["gaussians"]
