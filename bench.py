@@ -697,7 +697,8 @@ def run_ours(args, rank, world, dev):
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "clock": "host wall clock",
                 "path": "GaussianRasterizer(settings, arena=RenderArena) (tensor-level mirror of the reference operator, "
-                        "persistent scratch, sync-free forward) + torch autograd + L1 loss; "
+                        "persistent scratch and gradient buffers, sync-free forward) + torch autograd + the L1 loss "
+                        "mean|C - target| as one fused op (rasterizer.fused_image_loss); "
                         "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream; "
                         "the host launches step i+1 before it reads step i's loss (every loss is read, one step late); "
                         "launched as: " + e2e_mode},
@@ -840,6 +841,8 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
 
     arena = rasterizer.RenderArena(dev)  # persistent scratch + sync-free forward (one render in flight at a time)
+    from gs_livm_b200 import train
+    l1_loss = train.ImageLoss(W, H, dev, lambda_dssim=0.0)
     copy_stream = torch.cuda.Stream(device=dev)
     target_dev = [torch.empty((3, H, W), device=dev) for _ in range(2)]
 
@@ -867,7 +870,7 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
             leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
             rotations=leaves["rotations"])
         main.wait_event(uploaded)
-        loss = (color - target).abs().mean() + 0.1 * acc.mean()
+        loss = rasterizer.fused_image_loss(color, target, l1_loss)  # mean|C - target| (gsr_image_loss, lambda = 0)
         loss.backward()
         if world > 1:
             # the operator's backward lays the five parameter gradients out contiguously (arena.param_grad_span) and
@@ -879,6 +882,7 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
             else:
                 for t in leaves.values():
                     dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
+            arena.invalidate_grads()  # sums now sit in the rows of Gaussians this rank culled
         loss_host[j].copy_(loss.detach().reshape(1), non_blocking=True)
 
     captured = [None, None]

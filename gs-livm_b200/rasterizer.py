@@ -100,6 +100,54 @@ class RenderArena:
         self._status_np = self._status.numpy()  # same memory
         self._head = 0
         self._unchecked = []
+        # the backward's outputs live in the arena too: ONE persistent buffer (the gradients a backward returns are views
+        # of it and are overwritten by the next backward through this arena, like the scratch buffers), which lets the
+        # library skip re-zeroing the outputs of Gaussians that were culled last time as well (gsr_bwd_args.row_state)
+        # and clear the four accumulated arrays on a side stream while the forward still runs
+        self._grad_key, self._grad_flat, self._grad_start, self.row_state = None, None, None, None
+        self._side = None
+        self._accumulators_zeroed = False
+
+    GRAD_ORDER = ("means3D", "sh", "scales", "rotations", "opacity", "means2D", "colors", "conic", "cov3D")
+
+    def grad_buffer(self, P: int, M: int):
+        """-> (flat float32 buffer, {name: first float}, {name: floats per Gaussian}); 256-byte aligned arrays, the
+        optimised parameters' gradients first (param_grad_span), the four accumulated arrays adjacent."""
+        width = dict(means3D=3, sh=M * 3, scales=3, rotations=4, opacity=1, means2D=3, colors=NUM_CHANNELS, conic=4, cov3D=6)
+        if self._grad_key != (P, M):
+            start, off = {}, 0
+            for k in self.GRAD_ORDER:
+                start[k] = off
+                off += (P * width[k] + 63) // 64 * 64
+            self._grad_flat = torch.zeros((off,), dtype=torch.float32, device=self.device)
+            self._grad_start, self._grad_key = start, (P, M)
+            self.row_state = torch.ones((P,), dtype=torch.uint8, device=self.device)
+            self._accumulators_zeroed = False
+        return self._grad_flat, self._grad_start, width
+
+    def invalidate_grads(self) -> None:
+        """Call after anything but a backward through this arena wrote into the gradient buffer (e.g. an in-place
+        all-reduce over param_grad_span: it leaves sums in the rows of Gaussians this rank culled): the next backward
+        rewrites every Gaussian's outputs."""
+        if self.row_state is not None:
+            self.row_state.fill_(1)
+
+    def prepare_backward(self, lib, P: int, M: int) -> None:
+        """Called by the forward when a backward will follow: clears the four arrays the blend backward accumulates into
+        (44 B per Gaussian) on a side stream, beside the forward."""
+        flat, start, width = self.grad_buffer(P, M)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)
+        a = _lib.BwdArgs()
+        a.P = P
+        base = flat.data_ptr()
+        a.dL_dmean2D, a.dL_dconic = base + 4 * start["means2D"], base + 4 * start["conic"]
+        a.dL_dopacity, a.dL_dcolor = base + 4 * start["opacity"], base + 4 * start["colors"]
+        with torch.cuda.stream(self._side):
+            _lib.check(lib.gsr_backward_prepare(C.byref(a), self._side.cuda_stream), "gsr_backward_prepare")
+        self._accumulators_zeroed = True
 
     def _grow(self, kind: str, nbytes: int) -> int:
         if self._bufs[kind].numel() < nbytes:
@@ -280,13 +328,16 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
     # one allocation, nine 256-byte aligned views; the gradients of the optimised parameters (mean3D, sh, scale,
     # rotation, opacity) come first, so that a view-sharded window can sum them with ONE collective over a contiguous
     # span (arena.param_grad_span) instead of one per tensor
-    order = ("means3D", "sh", "scales", "rotations", "opacity", "means2D", "colors", "conic", "cov3D")
+    order = RenderArena.GRAD_ORDER
     width = dict(means3D=3, sh=M * 3, scales=3, rotations=4, opacity=1, means2D=3, colors=NUM_CHANNELS, conic=4, cov3D=6)
-    start, off = {}, 0
-    for k in order:
-        start[k] = off
-        off += (P * width[k] + 63) // 64 * 64
-    flat = (torch.empty if P != 0 else torch.zeros)((off,), **opts)
+    if arena is not None and P != 0:
+        flat, start, _ = arena.grad_buffer(P, M)  # persistent: overwritten by the next backward through this arena
+    else:
+        start, off = {}, 0
+        for k in order:
+            start[k] = off
+            off += (P * width[k] + 63) // 64 * 64
+        flat = (torch.empty if P != 0 else torch.zeros)((off,), **opts)
     view = {k: flat[start[k]:start[k] + P * width[k]] for k in order}
     dL_dmeans3D, dL_dmeans2D, dL_dcolors = view["means3D"].view(P, 3), view["means2D"].view(P, 3), view["colors"].view(P, NUM_CHANNELS)
     dL_dconic, dL_dopacity, dL_dcov3D = view["conic"].view(P, 2, 2), view["opacity"].view(P, 1), view["cov3D"].view(P, 6)
@@ -315,6 +366,12 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
         a.dL_dcolor, a.dL_dmean3D, a.dL_dcov3D = dL_dcolors.data_ptr(), dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr()
         a.dL_dsh, a.dL_dscale, a.dL_drot = _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr()
         a.debug, a.flags = int(bool(debug)), _lib.BWD_OUTPUTS_UNINITIALIZED
+        if arena is not None:
+            a.row_state = arena.row_state.data_ptr()
+            if arena._accumulators_zeroed:  # the forward cleared them on the arena's side stream
+                torch.cuda.current_stream(dev).wait_stream(arena._side)
+                a.flags |= _lib.BWD_ACCUMULATORS_ZEROED
+                arena._accumulators_zeroed = False
         with torch.cuda.device(dev):
             st = lib.gsr_backward(C.byref(a), _stream_ptr(dev))
         _lib.check(st, "gsr_backward")
@@ -348,6 +405,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                                      cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,
                                      rs.image_height, rs.image_width, sh, rs.sh_degree, rs.camera_center,
                                      rs.prefiltered, False, arena)
+        if arena is not None and means3D.size(0) != 0 and any(ctx.needs_input_grad):
+            arena.prepare_backward(_lib.load(), means3D.size(0), sh.size(1) if sh.numel() != 0 else 0)
         ctx.raster_settings = rs
         ctx.arena = arena
         ctx.num_rendered = num_rendered
@@ -373,6 +432,29 @@ class _RasterizeGaussians(torch.autograd.Function):
             rs.camera_center, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, False, ctx.arena)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
                 grad_cov3Ds_precomp, None, None)
+
+
+class _FusedImageLoss(torch.autograd.Function):
+    """(1 - lambda) mean|image - target| + lambda (1 - mean SSIM) as ONE differentiable op over libgsr_b200's fused loss
+    kernels (gsr_image_loss; include/gs/gs/loss_utils.cuh:11-70, src/liw/lioOptimization.cpp:1729-1734): the forward
+    already produces dL/dimage, the backward scales it."""
+
+    @staticmethod
+    def forward(ctx, image, target, fused):
+        loss, grad = fused(image, target)
+        ctx.save_for_backward(grad)
+        return loss[0].reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None, None
+
+
+def fused_image_loss(image: torch.Tensor, target: torch.Tensor, fused) -> torch.Tensor:
+    """`fused`: a train.ImageLoss for the image size (it owns the scratch and the gradient buffer: one loss in flight
+    per instance). lambda_dssim = 0 gives the plain L1 loss in one pass."""
+    return _FusedImageLoss.apply(image, target, fused)
 
 
 class GaussianRasterizer(torch.nn.Module):

@@ -57,7 +57,7 @@ class OperatorSession {
     torch::cuda::synchronize();                                       // render_utils.cuh:49
     auto [color, radii, depth, acc] =
         rasterizer.forward(means3D_, means2D, opacity_, shs_, torch::Tensor(), scales_, rotations_, torch::Tensor());
-    auto loss = (color - target).abs().mean() + 0.1 * acc.mean();
+    auto loss = (color - target).abs().mean();  // the L1 term of the mapping loss (lioOptimization.cpp:1729-1734)
     loss.backward();
     last_color_ = color.detach();
     return loss.item<double>();
