@@ -73,6 +73,11 @@ class AdamGroup(C.Structure):
                 ("phase_hi", C.c_uint), ("lr_other", C.c_float)]
 
 
+class VgprParams(C.Structure):
+    _fields_ = [("grid", C.c_float), ("num_gp_side", C.c_int), ("neighbour", C.c_int), ("kernel_size", C.c_float),
+                ("variance_sensor", C.c_float), ("scale_factor", C.c_float), ("full_cover", C.c_int)]
+
+
 class ArrayView(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("stride", C.c_size_t), ("count", C.c_size_t)]
 
@@ -136,6 +141,8 @@ SYMBOLS = {
                                  C.c_void_p]),
     "gsr_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AdamGroup), C.c_int, C.c_float,
                                 C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "gsr_vgpr_gaussians": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(VgprParams), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_mark_visible": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_view_geom": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GeomView)]),
     "gsr_view_binning": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(BinningView)]),

@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgsr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CU_SOURCES = ["preprocess.cu", "binning.cu", "tile_sort.cu", "block_lists.cu", "blend_fwd_sparse.cu", "blend_bwd_sparse.cu", "geom_bwd.cu", "window_allreduce.cu", "window_factored.cu", "train_ops.cu", "gsr_api.cu"]
+CU_SOURCES = ["preprocess.cu", "binning.cu", "tile_sort.cu", "block_lists.cu", "blend_fwd_sparse.cu", "blend_bwd_sparse.cu", "geom_bwd.cu", "window_allreduce.cu", "window_factored.cu", "train_ops.cu", "vgpr.cu", "gsr_api.cu"]
 CXX_SOURCES = ["rasterizer_shim.cpp"]
 HEADERS = [os.path.join(CSRC, "gsr_common.cuh"), os.path.join(CSRC, "sh_basis.cuh"), os.path.join(ROOT, "include", "gsr.h"),
            os.path.join(ROOT, "include", "cuda_rasterizer", "rasterizer.h"),

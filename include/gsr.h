@@ -364,6 +364,28 @@ GSR_API int gsr_adam_step(float* params, const float* grads, float* exp_avg, flo
                           const gsr_adam_group* groups, int n_groups, float beta1, float beta2, float eps, int step,
                           void* stream);
 
+/* VGPR + variance-centred Gaussian initialisation (csrc/vgpr.cu), the producer of the map's Gaussians:
+ * gpProcess::forward_gp3d's per-voxel Gaussian-process regression (src/gp3d/gpprocess.cu:8-60,602-668) and
+ * fastInitial3DGS (:420-458) + the scale rule of GaussianModel::Create_from_pcd (src/gs/gaussian.cu:325-386) in ONE
+ * launch, one CTA per voxel, no cuBLAS, no per-frame allocation. Inputs per voxel: T <= 32 training points, the voxel's
+ * integer coordinates and the regressed axis (the axis closest to the smallest-eigenvalue direction of the voxel's
+ * points, cell.cpp:5-30; the caller buckets the sweep and runs the 3x3 PCA, gs_livm_b200/vgpr.py). Outputs: g*g
+ * Gaussians per voxel, g = num_gp_side / neighbour: means [V*g*g,3], covariances [V*g*g,3,3], scales
+ * sqrt(diag * scale_factor) [V*g*g,3]; var_mean [V] = 1 - mean of the variance entries (the reference's "needs more
+ * points" gate, gpprocess.cu:63-122); optional test_points [V,side^2,3] and kvar [V,side^2] (parity tests). */
+typedef struct gsr_vgpr_params {
+  float grid;            /* voxel edge, config/basic_common.yaml:72 (0.2) */
+  int num_gp_side;       /* lattice points per side (12), <= 16 */
+  int neighbour;         /* lattice points per Gaussian and side (3); divides num_gp_side */
+  float kernel_size;     /* k = exp(-kernel_size |d|) (1.0) */
+  float variance_sensor; /* sigma: sigma^2 on Ky's diagonal (0.05) */
+  float scale_factor;    /* (3.0) */
+  int full_cover;        /* lattice from edge to edge instead of cell centres (0) */
+} gsr_vgpr_params;
+GSR_API int gsr_vgpr_gaussians(int V, int T, const float* train, const int* voxel, const int* direction,
+                               const gsr_vgpr_params* params, float* means, float* covs, float* scales, float* var_mean,
+                               float* test_points, float* kvar, void* stream);
+
 GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      unsigned char* present, void* stream);
 
