@@ -27,6 +27,8 @@ Printed (rank 0, ONE JSON line), both arms with the IDENTICAL `config` dict:
               shows for it, its HBM fraction on algorithmic AND on measured DRAM bytes, and for the blends the
               executed-work FP32 fraction from the kernels' own pair counters;
   step_incl_optim  the window step INCLUDING the fused image loss and the fused Adam step (SURVEY.md 8e: t_a on its own);
+  mapping_loop  BASELINE.json configs[4] in the small: replayed synthetic stream, VGPR + Gaussian insertion on the GPU per
+              keyframe, 50 optimisation iterations per keyframe (fused loss, exchange, fused Adam), all ranks;
   sweep       the other workloads (config 1: 200 K; the shipped 376x240 SH-0 setting; config 4: 5 M @ 1920x1200), ms per
               step of this arm — not the headline;
   cpu_baseline  Oracle B (scalar CPU port, all host cores for the blend loops) on one frame of the same workload.
@@ -605,6 +607,19 @@ def run_ours(args, rank, world, dev):
     except Exception as exc:
         optim = {"status": "failed: %s" % (repr(exc)[:200],)}
 
+    # ---- BASELINE.json configs[4] in the small: the mapping loop on a replayed synthetic stream (VGPR + insertion on the
+    # GPU per keyframe, optimisation iterations with fused loss, exchange and Adam); every rank takes part
+    mapping_loop = None
+    if not args.no_sweep:
+        try:
+            from gs_livm_b200 import mapping
+            del ctx
+            torch.cuda.empty_cache()
+            mapping_loop = mapping.run_synthetic_stream(keyframes=4, iters=50, points=1_500_000, capacity=600_000, dev=dev)
+        except Exception as exc:
+            mapping_loop = {"status": "failed: %s" % (repr(exc)[:200],)}
+            ctx = None
+
     if rank != 0:
         return None
     # ---- the reference's unchanged operator files on our library (N = 1 only: the reference has no multi-GPU path)
@@ -706,13 +721,13 @@ def run_ours(args, rank, world, dev):
         "parity_check": parity,
         "exchange_max_err": exchange_max_err, "exchange_ranks_identical": exchange_identical, "exchange": exchange_info,
         "step_incl_optim": optim,
+        "mapping_loop": mapping_loop,
         "gpu_launches": launches * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_base,
     }
     if world == 1 and not args.no_sweep:
         try:
-            del ctx
             torch.cuda.empty_cache()
             out["sweep"] = sweep_ours(dev)
         except Exception as exc:

@@ -80,6 +80,7 @@ class RasterContext:
         self.lib = _lib.load()
         self.grad_numel = grad_layout(P, M)[1]
         self.P, self.M, self.W, self.H, self.D = int(P), int(M), int(width), int(height), int(sh_degree)
+        self.active = self.P  # Gaussians in use: set_active() (a growing map renders a prefix of its capacity)
         self.device = torch.device(device)
         f32 = dict(dtype=torch.float32, device=self.device)
         self.out_color = torch.zeros((3, self.H, self.W), **f32)
@@ -121,7 +122,7 @@ class RasterContext:
         a = _lib.FwdArgs()
         a.activations = int(activations)
         self._activations = int(activations)
-        a.P, a.D, a.M, a.width, a.height = self.P, self.D, self.M, self.W, self.H
+        a.P, a.D, a.M, a.width, a.height = self.active, self.D, self.M, self.W, self.H
         a.background, a.means3D, a.shs = scene["background"].data_ptr(), scene["means3D"].data_ptr(), scene["shs"].data_ptr()
         a.colors_precomp, a.opacities, a.scales = None, scene["opacities"].data_ptr(), scene["scales"].data_ptr()
         a.scale_modifier, a.rotations, a.cov3D_precomp = float(scale_modifier), scene["rotations"].data_ptr(), None
@@ -180,7 +181,7 @@ class RasterContext:
         backward(..., accumulators_zeroed=True)."""
         g = self.grads
         a = _lib.BwdArgs()
-        a.P = self.P
+        a.P = self.active
         a.dL_dmean2D, a.dL_dconic, a.dL_dopacity = g["dL_dmean2D"].data_ptr(), g["dL_dconic"].data_ptr(), g["dL_dopacity"].data_ptr()
         a.dL_dcolor = g["dL_dcolor"].data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -202,7 +203,7 @@ class RasterContext:
             raise RuntimeError("backward() before forward()")
         g = self.grads
         a = _lib.BwdArgs()
-        a.P, a.D, a.M, a.R, a.width, a.height = self.P, self.D, self.M, self.num_rendered, self.W, self.H
+        a.P, a.D, a.M, a.R, a.width, a.height = self.active, self.D, self.M, self.num_rendered, self.W, self.H
         a.background, a.means3D, a.shs, a.colors_precomp = f.background, f.means3D, f.shs, None
         a.scales, a.scale_modifier, a.rotations, a.cov3D_precomp = f.scales, f.scale_modifier, f.rotations, None
         a.viewmatrix, a.projmatrix, a.cam_pos = f.viewmatrix, f.projmatrix, f.cam_pos
@@ -276,6 +277,15 @@ class RasterContext:
         slots = self._unchecked[before:]
         del self._unchecked[before:]
         return CapturedFrame(self, graph, slots, self._fwd_args, (step_fn, self._keep))
+
+    def set_active(self, n: int) -> None:
+        """Render / differentiate only the first n <= P Gaussians from now on (a map that grows inside buffers laid out
+        for its capacity P: every per-Gaussian array a caller passes is then a [P, ...] array whose first n rows are in
+        use; the gradient arrays keep their capacity layout and rows >= n are left alone). Frames captured before the
+        change keep their old count."""
+        if not 0 < int(n) <= self.P:
+            raise ValueError("active count must be in (0, P]")
+        self.active = int(n)
 
     def invalidate_grads(self) -> None:
         """Call after anything but this context's backward wrote into the gradient buffer (a fill, an in-place

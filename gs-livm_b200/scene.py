@@ -264,3 +264,12 @@ def frame_colour(cam: Camera, intr: Dict = NTU):
         return rgb, valid
 
     return colour_of
+
+
+def procedural_image(intr: Dict = NTU) -> np.ndarray:
+    """The keyframe image frame_colour() looks colours up in, as an array [H,W,3] uint8."""
+    u, v = np.meshgrid(np.arange(intr["width"]), np.arange(intr["height"]))
+    r = 127.5 + 100.0 * np.sin(0.045 * u) * np.cos(0.03 * v)
+    g = 127.5 + 100.0 * np.sin(0.02 * u + 0.05 * v)
+    b = 127.5 + 100.0 * np.cos(0.06 * v)
+    return np.clip(np.stack([r, g, b], axis=2), 0, 255).astype(np.uint8)

@@ -65,9 +65,22 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(params)
         self.exp_avg_sq = torch.zeros_like(params)
         self.betas, self.eps, self.steps = (float(betas[0]), float(betas[1])), float(eps), 0
+        self._set(groups)
+
+    def _set(self, groups) -> None:
         self._groups = (_lib.AdamGroup * len(groups))(*[
             _lib.AdamGroup(int(f), int(c), float(lr), int(per), int(lo), int(hi), float(lro))
             for f, c, lr, per, lo, hi, lro in groups])
+
+    def set_groups(self, groups: Sequence[tuple]) -> None:
+        """New element ranges / learning rates (a map that grew inside its capacity); the moments are kept."""
+        if not 1 <= len(groups) <= 8:
+            raise ValueError("1..8 parameter groups")
+        groups = [tuple(g) + (0, 0, 0, 0.0) * (len(g) == 3) for g in groups]
+        for first, count, *_ in groups:
+            if first < 0 or count < 0 or first + count > self.params.numel():
+                raise ValueError("group outside the parameter buffer")
+        self._set(groups)
 
     def step(self, grads: torch.Tensor) -> None:
         if grads.dtype != torch.float32 or grads.numel() < self.params.numel() or not grads.is_contiguous():

@@ -208,6 +208,7 @@ class FactoredExchange:
         n_chunks = max(1, min(int(n_chunks), 32, (self.P + 127) // 128))
         per = ((self.P + n_chunks - 1) // n_chunks + 127) // 128 * 128
         self.chunks = [(f, min(per, self.P - f)) for f in range(0, self.P, per)]
+        self._chunk_per, self.active = per, self.P
         at, self.grad_floats, param_floats, self.sh_floats = engine.grad_layout(self.P, self.M)
         self._rest_first = (C.c_size_t * 4)(*[at[n][0] for n in ("dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity")])
         self.rest_floats = param_floats - self.sh_floats  # mean3D, scale, rotation, opacity: 11 floats per Gaussian
@@ -269,6 +270,15 @@ class FactoredExchange:
         self.segment_events = None
         self.cam_centres = torch.zeros((self.n_views, 3), dtype=torch.float32, device=self.device)
 
+    def set_active(self, n: int) -> None:
+        """Exchange only the first n <= P Gaussians from now on (see engine.RasterContext.set_active; the buffers keep
+        the layout of the capacity P). Every rank must set the same count."""
+        if not 0 < int(n) <= self.P:
+            raise ValueError("active count must be in (0, P]")
+        self.active = int(n)
+        per = self._chunk_per
+        self.chunks = [(f, min(per, self.active - f)) for f in range(0, self.active, per)]
+
     # slot of view v, parity q: floats [at, at + slot_floats) then the visibility words
     def _slot_at(self, v: int, q: int) -> int:
         return self._slots_at + (q * self.n_views + v) * self._slot_stride
@@ -296,7 +306,7 @@ class FactoredExchange:
         vis = (C.c_void_p * len(bases))(*[b + at + 4 * self.slot_floats for b in bases])
         for c in (range(len(self.chunks)) if chunk is None else [chunk]):
             first, count = self.chunks[c]
-            st = self.lib.gsr_window_push_rgb(ctx.geom.buf.data_ptr(), self.P, first, count, c, ctx.radii.data_ptr(),
+            st = self.lib.gsr_window_push_rgb(ctx.geom.buf.data_ptr(), self.active, first, count, c, ctx.radii.data_ptr(),
                                               ctx.grads["dL_dcolor"].data_ptr(), rgb, vis, len(bases),
                                               1 if self.push_mode == "multimem" else 0, self._comm_ref(), self._stream())
             self._lib.check(st, "gsr_window_push_rgb")
@@ -312,7 +322,7 @@ class FactoredExchange:
         rgb, vis = self._local_slots(parity)
         for c in (range(len(self.chunks)) if chunk is None else [chunk]):
             first, count = self.chunks[c]
-            st = self.lib.gsr_window_expand_sh(self.P, first, count, ctx.D, self.M, self.n_views, means3D.data_ptr(),
+            st = self.lib.gsr_window_expand_sh(self.active, first, count, ctx.D, self.M, self.n_views, means3D.data_ptr(),
                                                self.cam_centres.data_ptr(), rgb, vis, ctx.grads["dL_dsh"].data_ptr(),
                                                self._stream())
             self._lib.check(st, "gsr_window_expand_sh")
@@ -325,7 +335,7 @@ class FactoredExchange:
             return
         vis = self._local_slots(parity)[1] if self.sparse_reduce else None
         st = self.lib.gsr_window_allreduce_rest(self._comm_ref(), self._reduce_bufs, 1 if self.reduce_mode == "multimem" else 0,
-                                                self.P, 0, self.P, 0, len(self.chunks) - 1, self._rest_first,
+                                                self.active, 0, self.active, 0, len(self.chunks) - 1, self._rest_first,
                                                 self.n_views if vis is not None else 0, vis, self._stream())
         self._lib.check(st, "gsr_window_allreduce_rest")
 
