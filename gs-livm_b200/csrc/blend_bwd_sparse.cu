@@ -76,8 +76,9 @@ struct PixelState {
 // Advance the recurrence over one blended pair (reference backward.cu:546-585) and return dL/dalpha of the pair.
 // rgb = the candidate's colour.
 __device__ __forceinline__ float pair_recurrence(PixelState& s, float alpha, float r, float g, float b) {
-  // one correctly rounded reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581)
-  const float inv = __frcp_rn(1.f - alpha);
+  // one reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581). MUFU.RCP (1 ulp; 1 - alpha is in
+  // [0.01, 1]) instead of the IEEE sequence: gradients are compared at 1e-4, and the kernel is issue-bound
+  const float inv = __fdividef(1.f, 1.f - alpha);
   s.T = s.T * inv;
   const float keep = 1.f - s.last_alpha;
   s.acc0 = s.last_alpha * s.lc0 + keep * s.acc0;
@@ -93,12 +94,14 @@ __device__ __forceinline__ float pair_recurrence(PixelState& s, float alpha, flo
   return dL_dalpha;
 }
 
-// exp / alpha of a blended pair, same operation order as the forward (the pair is known to pass its tests)
+// exp / alpha of a blended pair (the pair is known to pass its tests: no threshold is decided here, so the backward
+// can use the two-instruction ex2 path -- relative error ~2e-7 for power in [-5.6, 0] -- where the forward needs expf's
+// exact bits)
 __device__ __forceinline__ void pair_alpha(const float4 qa, const float4 qb, float pxf, float pyf, float& alpha, float& G) {
   const float dx = __fadd_rn(qa.x, -pxf), dy = __fadd_rn(qa.y, -pyf);
   const float power = __fmaf_rn(__fmaf_rn(dx, __fmul_rn(dx, qa.z), __fmul_rn(dy, __fmul_rn(dy, qb.x))), -0.5f,
                                 -__fmul_rn(dy, __fmul_rn(dx, qa.w)));
-  G = expf(power);
+  G = __expf(power);
   alpha = fminf(0.99f, __fmul_rn(qb.y, G));
 }
 
