@@ -548,6 +548,7 @@ def run_ours(args, rank, world, dev):
         want = ctx.param_grads().clone()
         dist.all_reduce(want)
         ctx.grads["dL_dsh"].fill_(float("nan"))
+        exchange.mark_rows_dirty()
         ev = torch.cuda.Event()
         ev.record()
         exchange.exchange(ctx, sc["means3D"], i % 2, ev,

@@ -132,7 +132,7 @@ SYMBOLS = {
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                       C.POINTER(WindowComm), C.c_void_p]),
     "gsr_window_expand_sh": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsr_window_allreduce_rest": (C.c_int, [C.POINTER(WindowComm), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.c_int,
                                             C.POINTER(C.c_void_p), C.c_void_p]),

@@ -213,14 +213,16 @@ struct ExpandArgs {
   const float* rgb[kMaxViews];  // gathered masked dRGB, [P,3] per view
   const uint32_t* vis[kMaxViews];
   float* dL_dsh;                // [P,16,3]
+  uint32_t* row_state;          // optional [ceil(P/32)]: bit = the row may hold non-zero data (see expand_sh_kernel)
 };
 
 // dL_dsh[g] = sum over the views that rendered g of basis(dir) (x) dRGB, accumulated in view order with one FMA per
 // term. The basis is the one geom_bwd uses (same sh_basis, same bits), so with one view the rows equal geom_bwd's bit
 // for bit (fma(b, c, 0) is the rounded product); with more views they differ from the dense sum of the views' rounded
-// rows by the usual last-place effects of a different summation. Rows nobody rendered are written as zeros. (Leaving rows alone
-// that are known to hold zeros already -- a third of the bench's Gaussians is rendered by no view of a step -- was
-// measured SLOWER: 107 vs 57 us for the partial row stream.)
+// rows by the usual last-place effects of a different summation. Rows nobody rendered are written as zeros -- or, with
+// row_state, left alone when they are known to hold zeros already (a third of the bench's Gaussians is rendered by no
+// view of a step: 71 MB of zero rows per step). The state word is requested at the top of the kernel and looked at only
+// when the rows go out: as a dependent load in front of the stores the same idea was SLOWER (107 vs 57 us alone).
 __global__ void __launch_bounds__(kExpBlock) expand_sh_kernel(const ExpandArgs a) {
   __shared__ __align__(16) float4 s_row[kExpBlock * kExpRow];
   __shared__ float s_cam[kMaxViews * 3];
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(kExpBlock) expand_sh_kernel(const ExpandArgs a
   const int base = a.first + blockIdx.x * kExpBlock;
   const int n = min(kExpBlock, a.end - base);
   const int idx = base + tid;
+  const uint32_t may_be_nonzero = (a.row_state && tid < n) ? a.row_state[idx >> 5] : 0xffffffffu;
   float acc[48];
 #pragma unroll
   for (int i = 0; i < 48; ++i) acc[i] = 0.f;
@@ -264,13 +267,21 @@ __global__ void __launch_bounds__(kExpBlock) expand_sh_kernel(const ExpandArgs a
       }
     }
   }
+  // rows that go out: rendered by some view, or still holding an earlier step's data
+  const uint32_t now = __ballot_sync(0xffffffffu, seen != 0);
+  const bool out = tid < n && (((now | may_be_nonzero) >> (tid & 31)) & 1u);
+  if (a.row_state && tid < n && (tid & 31) == 0 && now != may_be_nonzero) a.row_state[idx >> 5] = now;
+  __shared__ uint8_t s_out[kExpBlock];
+  s_out[tid] = out;
+  if (out) {
 #pragma unroll
-  for (int i = 0; i < 12; ++i)
-    s_row[tid * kExpRow + i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    for (int i = 0; i < 12; ++i)
+      s_row[tid * kExpRow + i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
   __syncthreads();
   float4* d4 = reinterpret_cast<float4*>(a.dL_dsh) + (size_t)base * 12;
   for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kExpBlock) {
-    d4[q] = s_row[row * kExpRow + rem];
+    if (s_out[row]) d4[q] = s_row[row * kExpRow + rem];
     { rem += kExpBlock % 12, row += kExpBlock / 12; if (rem >= 12) rem -= 12, ++row; }
   }
 }
@@ -451,12 +462,14 @@ int gsr_window_push_rgb(char* geom_buffer, int P, int first, int count, int sub,
 }
 
 int gsr_window_expand_sh(int P, int first, int count, int D, int M, int n_views, const float* means3D, const float* cam_pos,
-                         const void* const* rgb_slots, const void* const* vis_slots, float* dL_dsh, void* stream) {
+                         const void* const* rgb_slots, const void* const* vis_slots, float* dL_dsh, uint32_t* row_state,
+                         void* stream) {
   if (!range_ok(P, first, count) || D < 0 || D > 3 || M != 16 || n_views < 1 || n_views > kMaxViews || !means3D || !cam_pos ||
       !rgb_slots || !vis_slots || !dL_dsh || (reinterpret_cast<uintptr_t>(dL_dsh) & 15u))
     return GSR_ERR_INVALID;
   ExpandArgs a;
   a.first = first, a.end = first + count, a.D = D, a.V = n_views, a.means3D = means3D, a.cam_pos = cam_pos, a.dL_dsh = dL_dsh;
+  a.row_state = row_state;
   for (int v = 0; v < kMaxViews; ++v) {
     const bool on = v < n_views;
     a.rgb[v] = on ? static_cast<const float*>(rgb_slots[v]) : nullptr;

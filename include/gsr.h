@@ -306,7 +306,10 @@ GSR_API int gsr_window_allreduce_p2p_rows(void* const* peer_buffers, size_t n_fl
  *   gsr_window_expand_sh     dL_dsh[g] for the chunk's Gaussians = sum over v < n_views (in that order, identical on
  *       every rank) of basis(normalize(means3D - cam_pos[v])) (x) rgb_slots[v], skipping views whose visibility bit is
  *       clear; rows no view rendered are written as zeros. cam_pos: DEVICE array [n_views,3]; rgb_slots / vis_slots:
- *       host arrays of n_views device pointers; n_views <= 16, M == 16.
+ *       host arrays of n_views device pointers; n_views <= 16, M == 16. row_state (optional): ceil(P / 32) words of
+ *       device memory, all ones when dL_dsh holds arbitrary data, kept by the kernel from then on (bit = the row may
+ *       be non-zero): rows no view rendered are then rewritten only if they still hold an earlier step's data. Chunks
+ *       must start at multiples of 128 Gaussians for this (they do).
  *   gsr_window_allreduce_rest  (after the per-Gaussian backward of the chunk, GSR_BWD_ONLY_GEOM | GSR_BWD_SH_FACTORED):
  *       sum over the ranks of dL_dmean3D [P,3], dL_dscale [P,3], dL_drot [P,4], dL_dopacity [P] (the chunk's part), which
  *       start at floats first_float[0..3] (multiples of 4) of ONE symmetric buffer: buffers[r] = rank r's buffer
@@ -332,7 +335,7 @@ GSR_API int gsr_window_push_rgb(char* geom_buffer, int P, int first, int count, 
                                 int multicast, const gsr_window_comm* comm, void* stream);
 GSR_API int gsr_window_expand_sh(int P, int first, int count, int D, int M, int n_views, const float* means3D,
                                  const float* cam_pos, const void* const* rgb_slots, const void* const* vis_slots,
-                                 float* dL_dsh, void* stream);
+                                 float* dL_dsh, uint32_t* row_state, void* stream);
 GSR_API int gsr_window_allreduce_rest(const gsr_window_comm* comm, void* const* buffers, int multicast, int P, int first,
                                       int count, int sub, int pushed_sub, const size_t* first_float, int n_views,
                                       const void* const* vis_slots, void* stream);

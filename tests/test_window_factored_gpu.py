@@ -12,14 +12,14 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 
-def _setup(P, dev, n_views, seed=20241017 + 5, deg=3, chunks=4):
+def _setup(P, dev, n_views, seed=20241017 + 5, deg=3, chunks=4, track=False):
     import gs_livm_b200  # noqa: F401
     from gs_livm_b200 import engine, scene, window
     sc_cpu = scene.make_scene(P, seed, deg)
     sc = {k: v.to(dev) for k, v in sc_cpu.items()}
     cams = [scene.scene_camera(sc_cpu, i, scene.NTU).to(dev) for i in (0, 3)]
     H, W = cams[0].height, cams[0].width
-    ex = window.FactoredExchange(P, 16, dev, n_views=n_views, n_chunks=chunks)
+    ex = window.FactoredExchange(P, 16, dev, n_views=n_views, n_chunks=chunks, track_zero_rows=track)
     ctx = engine.RasterContext(P, 16, W, H, dev, deg, grad_flat=ex.flat)
     g = torch.Generator().manual_seed(seed + 1)
     dC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
@@ -31,10 +31,11 @@ def _setup(P, dev, n_views, seed=20241017 + 5, deg=3, chunks=4):
 def test_one_view_rows_equal_geom_bwd_bit_for_bit(P, chunks, built_library, cuda_device):
     """chunks: the exchange pipelines push / per-Gaussian backward / expansion over that many ranges of Gaussians."""
     dev = cuda_device
-    sc, cams, ex, ctx, dC, dS = _setup(P, dev, 1, chunks=chunks)
+    sc, cams, ex, ctx, dC, dS = _setup(P, dev, 1, chunks=chunks, track=(P == 50_000))
     ex.cam_centres[0].copy_(cams[0].camera_center)
     ctx.grad_flat.fill_(float("nan"))
     ctx.invalidate_grads()
+    ex.mark_rows_dirty()
     ex.render_step(ctx, sc, cams[0], dC, dS, parity=0)
     torch.cuda.synchronize()
     got = {n: ctx.grads[n].clone() for n in ("dL_dsh", "dL_dmean3D", "dL_dscale", "dL_drot", "dL_dopacity", "dL_dcov3D")}
@@ -55,6 +56,7 @@ def test_one_view_rows_equal_geom_bwd_bit_for_bit(P, chunks, built_library, cuda
     frame = ctx.capture(lambda: ex.render_step(ctx, sc, cams[0], dC, dS, parity=1))
     ctx.grad_flat.fill_(float("nan"))
     ctx.invalidate_grads()
+    ex.mark_rows_dirty()
     frame.replay()
     torch.cuda.synchronize()
     assert ctx.check()
@@ -80,6 +82,7 @@ def test_two_views_rows_are_the_sum_of_the_views_rows(built_library, cuda_device
         vis.append((ctx.radii > 0).clone())
     assert int((vis[0] & vis[1]).sum()) > 1000 and int((vis[0] ^ vis[1]).sum()) > 1000, "views must overlap partly"
     ctx.grads["dL_dsh"].fill_(float("nan"))
+    ex.mark_rows_dirty()
     ex.expand(ctx, sc["means3D"], parity=0)
     torch.cuda.synchronize()
     # one FMA per term: fma(b1, c1, round(b0 c0)) against round(round(b0 c0) + round(b1 c1)) -- half an ulp of a term

@@ -62,6 +62,7 @@ for reduce_mode, push_mode, sparse, track in combos:
         dist.all_reduce(want)
         # factored: push + geom half without the SH rows + exchange, from the same accumulators
         ctx.grads["dL_dsh"].fill_(float("nan"))
+        ex.mark_rows_dirty()
         ev = torch.cuda.Event(); ev.record()
         ex.exchange(ctx, sc["means3D"], i % 2, ev,
                     lambda: ctx.backward(dC, dS, part="geom", sh_factored=True))
