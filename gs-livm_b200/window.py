@@ -375,7 +375,7 @@ class FactoredExchange:
                 self.push(ctx, parity, chunk=c)
                 pushed[c].record(self.hi_push)
             mark("push_end", self.hi_push)
-        with torch.cuda.stream(self.side):
+        with torch.cuda.stream(self.side):  # (normal priority: as a high-priority stream it starves geom_bwd, 761 vs 685 us)
             for c in range(n):
                 self.side.wait_event(pushed[c])
                 self.wait_pushed(c)
