@@ -41,7 +41,7 @@ for r in rows[2:]:
             print(f"  {w:82s} {r[i]:>16s} {units[i]}")
 seen = set()
 for nm in names:
-    short = nm.split('(')[0].split('::')[-1]
+    short = nm.split('(')[0].split('::')[-1].split('<')[0].replace('void ', '').strip()
     if short in seen or (kre and kre not in short):
         continue
     seen.add(short)
