@@ -724,7 +724,9 @@ def run_ours(args, rank, world, dev):
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "clock": "host wall clock, median of %d windows of K steps" % E2E_WINDOWS,
                 "path": "GaussianRasterizer(settings, arena=RenderArena) (tensor-level mirror of the reference operator, "
                         "persistent scratch and gradient buffers, sync-free forward) + torch autograd + the L1 loss "
-                        "mean|C - target| as one fused op (rasterizer.fused_image_loss); "
+                        "mean|C - target| as one fused op (rasterizer.fused_image_loss)" + (
+                            "; the arena's backward sums the parameter gradients over the ranks itself (factored "
+                            "exchange inside the operator, in the graph)" if world > 1 else "") + "; "
                         "target image H2D on a copy stream overlapping the forward, camera H2D and loss D2H on the main stream; "
                         "the host launches step i+1 before it reads step i's loss (every loss is read, one step late); "
                         "median of %d windows of K steps; " % E2E_WINDOWS +
@@ -867,8 +869,17 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
     h2d_bytes = host_targets[0].numel() * 4 + host_cams[0].numel() * 4
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
 
-    arena = rasterizer.RenderArena(dev)  # persistent scratch + sync-free forward (one render in flight at a time)
-    from gs_livm_b200 import train
+    # persistent scratch + sync-free forward (one render in flight at a time); with several ranks the arena's backward
+    # sums the parameter gradients over the window itself (factored exchange): no all-reduce in the step
+    from gs_livm_b200 import train, window
+    ex2 = None
+    if world > 1:
+        try:
+            ex2 = window.FactoredExchange(P_GAUSS, 16, dev)
+        except RuntimeError:
+            ex2 = None  # (all ranks agree) -> NCCL all-reduce of the dense span below
+    arena = rasterizer.RenderArena(dev, exchange=ex2)
+    centre_stage = [torch.zeros((world, 3)).pin_memory() for _ in range(2)]
     l1_loss = train.ImageLoss(W, H, dev, lambda_dssim=0.0)
     copy_stream = torch.cuda.Stream(device=dev)
     target_dev = [torch.empty((3, H, W), device=dev) for _ in range(2)]
@@ -881,6 +892,9 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
         eagerly or captured once and replayed (rasterizer.CapturedStep). j: which target staging buffer."""
         main = torch.cuda.current_stream(dev)
         cam_dev.copy_(cam_stage[j], non_blocking=True)
+        if ex2 is not None:  # the camera centres of the step's views (all ranks), and the step's parity
+            ex2.cam_centres.copy_(centre_stage[j], non_blocking=True)
+            arena.exchange_parity = j
         # the step's target image goes up on a copy stream while the forward renders; the loss waits for it
         copy_stream.wait_stream(main)  # the buffer's previous use (two steps ago) is over
         with torch.cuda.stream(copy_stream):
@@ -899,7 +913,7 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
         main.wait_event(uploaded)
         loss = rasterizer.fused_image_loss(color, target, l1_loss)  # mean|C - target| (gsr_image_loss, lambda = 0)
         loss.backward()
-        if world > 1:
+        if world > 1 and ex2 is None:
             # the operator's backward lays the five parameter gradients out contiguously (arena.param_grad_span) and
             # autograd hands them to .grad without a copy: one collective instead of five
             span = arena.param_grad_span
@@ -916,6 +930,7 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
     # same (pinned) memory, without torch's per-op overhead
     cam_stage_np, loss_np = [c.numpy() for c in cam_stage], [t.numpy() for t in loss_host]
     host_cams_np = [c.numpy() for c in host_cams]
+    centre_np = [c.numpy() for c in centre_stage]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     losses = []
     lag = 0 if os.environ.get("GSR_BENCH_E2E_LAG", "1") == "0" else 1
@@ -933,6 +948,9 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
         every step's loss is read on the host, one step late. Staging buffers alternate (j)."""
         j = i % 2
         cam_stage_np[j][:] = host_cams_np[(rank + i) % WINDOW]  # 140 bytes, host to pinned host
+        if ex2 is not None:
+            for r in range(world):
+                centre_np[j][r, :] = host_cams_np[(r + i) % WINDOW][32:35]
         if captured[j] is not None:
             captured[j].replay()  # the whole step, copies included, is one graph launch
         else:
@@ -991,6 +1009,12 @@ def time_e2e_mirror(args, rank, world, dev, sc, cams_cpu, cams, W, H, rasterizer
         gc.enable()
     e2e_ms = statistics.median(windows)
     assert len(losses) == 4 + E2E_WINDOWS * args.steps
+    if world > 1:  # every rank must hold the same summed gradients after the last step
+        torch.cuda.synchronize()
+        chk = torch.stack([t.grad.double().sum() for t in leaves.values()] + [t.grad.double().abs().sum() for t in leaves.values()])
+        lst = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        e2e_mode += "; summed gradients identical on all ranks: %s" % bool(all(torch.equal(x, lst[0]) for x in lst))
     return e2e_ms, e2e_mode, h2d_bytes
 
 

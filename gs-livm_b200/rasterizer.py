@@ -90,8 +90,15 @@ class RenderArena:
     synchronisation the loop does anyway, e.g. reading the loss — tells whether every render since the last call
     fitted; a render that did not produced an empty image and has to be repeated."""
 
-    def __init__(self, device):
+    def __init__(self, device, exchange=None):
+        """exchange (optional): a window.FactoredExchange. The backward through this arena then writes its gradients into
+        the exchange's buffer and sums them over the ranks itself (one view per rank: every rank's backward takes part),
+        so the parameter gradients autograd hands out are the WINDOW's: no all-reduce in the caller's step. Before every
+        step the caller puts the camera centres of the step's views (rank order) into exchange.cam_centres and sets
+        `exchange_parity` to the step's parity (0 / 1 alternating)."""
         self.device = torch.device(device)
+        self.exchange = exchange
+        self.exchange_parity = 0
         self._bufs = {k: torch.empty(0, dtype=torch.uint8, device=self.device) for k in ("geom", "binning", "image")}
         self._fns = {k: _lib.ALLOC_FN(lambda _ctx, n, _k=k: self._grow(_k, n)) for k in self._bufs}
         self.capacity = 0
@@ -114,6 +121,18 @@ class RenderArena:
         """-> (flat float32 buffer, {name: first float}, {name: floats per Gaussian}); 256-byte aligned arrays, the
         optimised parameters' gradients first (param_grad_span), the four accumulated arrays adjacent."""
         width = dict(means3D=3, sh=M * 3, scales=3, rotations=4, opacity=1, means2D=3, colors=NUM_CHANNELS, conic=4, cov3D=6)
+        if self.exchange is not None and self._grad_key != (P, M):
+            # the exchange's symmetric buffer in engine.grad_layout's order; no zero-row tracking (sums land in the rows
+            # of Gaussians this rank culled)
+            from . import engine
+            if self.exchange.P != P or M != 16:
+                raise ValueError("the arena's exchange was built for %d Gaussians with 16 SH coefficients" % self.exchange.P)
+            at = engine.grad_layout(P, M)[0]
+            names = dict(means3D="dL_dmean3D", sh="dL_dsh", scales="dL_dscale", rotations="dL_drot", opacity="dL_dopacity",
+                         means2D="dL_dmean2D", colors="dL_dcolor", conic="dL_dconic", cov3D="dL_dcov3D")
+            self._grad_flat, self._grad_start = self.exchange.flat, {k: at[v][0] for k, v in names.items()}
+            self._grad_key, self.row_state = (P, M), None
+            self._accumulators_zeroed = False
         if self._grad_key != (P, M):
             start, off = {}, 0
             for k in self.GRAD_ORDER:
@@ -343,7 +362,7 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
     dL_dconic, dL_dopacity, dL_dcov3D = view["conic"].view(P, 2, 2), view["opacity"].view(P, 1), view["cov3D"].view(P, 6)
     dL_dsh, dL_dscales, dL_drotations = view["sh"].view(P, M, 3), view["scales"].view(P, 3), view["rotations"].view(P, 4)
     if arena is not None:
-        arena.param_grad_span = flat[:start["means2D"]]
+        arena.param_grad_span = flat[:start["means2D"]]  # (with an exchange: engine.grad_layout's order, sh first)
     if have_cov and P != 0:
         dL_dscales.zero_()
         dL_drotations.zero_()
@@ -367,14 +386,36 @@ def rasterize_gaussians_backward_cuda(background, means3D, radii, colors, scales
         a.dL_dsh, a.dL_dscale, a.dL_drot = _ptr(dL_dsh), dL_dscales.data_ptr(), dL_drotations.data_ptr()
         a.debug, a.flags = int(bool(debug)), _lib.BWD_OUTPUTS_UNINITIALIZED
         if arena is not None:
-            a.row_state = arena.row_state.data_ptr()
+            a.row_state = arena.row_state.data_ptr() if arena.row_state is not None else None
             if arena._accumulators_zeroed:  # the forward cleared them on the arena's side stream
                 torch.cuda.current_stream(dev).wait_stream(arena._side)
                 a.flags |= _lib.BWD_ACCUMULATORS_ZEROED
                 arena._accumulators_zeroed = False
+        ex = arena.exchange if arena is not None else None
         with torch.cuda.device(dev):
-            st = lib.gsr_backward(C.byref(a), _stream_ptr(dev))
-        _lib.check(st, "gsr_backward")
+            if ex is None:
+                _lib.check(lib.gsr_backward(C.byref(a), _stream_ptr(dev)), "gsr_backward")
+            else:
+                # the backward in halves around the window's factored exchange (window.FactoredExchange.exchange)
+                if M != 16 or have_cov:
+                    raise ValueError("the window exchange needs SH colours (M = 16) and scale / rotation inputs")
+                base_flags = a.flags
+                a.flags = base_flags | _lib.BWD_ONLY_BLEND
+                _lib.check(lib.gsr_backward(C.byref(a), _stream_ptr(dev)), "gsr_backward")
+                blend_done = torch.cuda.Event()
+                blend_done.record(torch.cuda.current_stream(dev))
+
+                def geom_half():
+                    a.flags = (base_flags | _lib.BWD_ONLY_GEOM | _lib.BWD_SH_FACTORED) & ~_lib.BWD_ACCUMULATORS_ZEROED
+                    _lib.check(lib.gsr_backward(C.byref(a), _stream_ptr(dev)), "gsr_backward")
+
+                class _Ctx:  # what FactoredExchange reads of an engine.RasterContext
+                    pass
+                cx = _Ctx()
+                cx.geom, cx.radii, cx.D = _Ctx(), radii_c, int(degree)
+                cx.geom.buf = geomBuffer
+                cx.grads = {"dL_dcolor": dL_dcolors, "dL_dsh": dL_dsh}
+                ex.exchange(cx, m3_c, int(arena.exchange_parity), blend_done, geom_half)
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 

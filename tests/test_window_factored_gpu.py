@@ -92,3 +92,46 @@ def test_two_views_rows_are_the_sum_of_the_views_rows(built_library, cuda_device
     np.testing.assert_array_equal(ctx.grads["dL_dsh"][only0].cpu().numpy(), dense[0][only0].cpu().numpy())
     none = ~(vis[0] | vis[1])
     assert int(none.sum()) > 0 and float(ctx.grads["dL_dsh"][none].abs().max()) == 0.0
+
+
+def test_operator_arena_with_an_exchange_returns_the_same_gradients(built_library, cuda_device):
+    """GaussianRasterizer(settings, arena=RenderArena(exchange=FactoredExchange)): the operator's backward runs in halves
+    around the factored exchange and hands out its gradients from the exchange's buffer; on one rank they must be the
+    gradients of the plain operator."""
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import rasterizer, scene, window
+    from tolerances import assert_grad
+    dev = cuda_device
+    P = 40_000
+    sc_cpu = scene.make_scene(P, 20241017 + 9, 3)
+    cam_cpu = scene.scene_camera(sc_cpu, 1, scene.NTU)
+    cam = cam_cpu.to(dev)
+    H, W = cam.height, cam.width
+    g = torch.Generator().manual_seed(3)
+    wC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
+    wS = (torch.randn((1, H, W), generator=g) / (H * W)).to(dev)
+    rs = scene.settings_for(cam, sc_cpu["background"].to(dev), 3)
+
+    def run(arena):
+        leaves = {k: sc_cpu[k].to(dev).clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        out = None
+        for _ in range(2):  # the second render goes through the sync-free path when there is an arena
+            for t in leaves.values():
+                t.grad = None
+            color, radii, depth, acc = rasterizer.GaussianRasterizer(rs, arena=arena)(
+                leaves["means3D"], m2, leaves["opacities"], shs=leaves["shs"], scales=leaves["scales"],
+                rotations=leaves["rotations"])
+            ((color * wC).sum() + (acc * wS).sum()).backward()
+            torch.cuda.synchronize()
+            if arena is not None:
+                assert arena.check()
+            out = {k: v.grad.detach().cpu().numpy().copy() for k, v in leaves.items()}
+        return out
+
+    want = run(None)
+    ex = window.FactoredExchange(P, 16, dev)
+    ex.cam_centres[0].copy_(cam.camera_center)
+    got = run(rasterizer.RenderArena(dev, exchange=ex))
+    for k in want:
+        assert_grad(k, got[k], want[k])
