@@ -570,7 +570,7 @@ def run_ours(args, rank, world, dev):
         lst = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(lst, chk)
         exchange_identical = bool(all(torch.equal(x, lst[0]) for x in lst))
-        exchange_info = {"reduce": exchange.reduce_mode, "push": exchange.push_mode}
+        exchange_info = {"reduce": exchange.reduce_mode, "push": exchange.push_mode, "wait_timed_out": exchange.timed_out()}
         del want
         ctx.check()
 

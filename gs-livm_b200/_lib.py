@@ -127,6 +127,7 @@ SYMBOLS = {
                                                 C.c_void_p]),
     "gsr_window_slot_floats": (C.c_size_t, [C.c_int]),
     "gsr_window_pad_words": (C.c_size_t, []),
+    "gsr_window_status": (C.c_int, [C.POINTER(WindowComm), C.POINTER(C.c_uint32)]),
     "gsr_window_wait": (C.c_int, [C.POINTER(WindowComm), C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gsr_window_push_rgb": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,

@@ -33,8 +33,12 @@ constexpr int kMaxRanks = 16;
 constexpr int kMaxViews = 16;
 enum { CH_READY = 0, CH_PART = 1, CH_DONE = 2, CH_PUSHED = 3 };
 // local words behind the flag rows of the own pad: the epoch and the last-block tickets of the signalling kernels
-enum { L_EPOCH = 0, L_TICKET_PUSH = 1, L_TICKET_A = 2, L_TICKET_B = 3 };
+enum { L_EPOCH = 0, L_TICKET_PUSH = 1, L_TICKET_A = 2, L_TICKET_B = 3, L_TIMEOUT = 4 };
 constexpr int kLocalAt = GSR_WINDOW_FLAG_CHANNELS * kMaxRanks;
+// A wait gives up after this many SM cycles (~4 s at 1.9 GHz) instead of hanging the GPU when a peer has died or the
+// ranks issue different call sequences: it records 1 + channel in the pad's L_TIMEOUT word (gsr_window_status) and lets
+// the kernel run on -- the step's result is then garbage, but the process can report it and exit.
+constexpr long long kWaitCycles = 8000000000ll;
 
 struct Comm {
   int rank, world;            // world == 1: no cross-rank work at all
@@ -66,7 +70,12 @@ __device__ __forceinline__ void wait_peers(const Comm& c, int channel, uint32_t 
   const int p = threadIdx.x;
   if (p < c.world && p != c.rank) {
     const uint32_t* f = c.pad[c.rank] + channel * kMaxRanks + p;
-    while ((int32_t)(ld_acquire_sys(f) - e) < 0) {
+    const long long t0 = clock64();
+    for (uint32_t spins = 0; (int32_t)(ld_acquire_sys(f) - e) < 0; ++spins) {
+      if ((spins & 1023u) == 1023u && clock64() - t0 > kWaitCycles) {
+        atomicExch(c.pad[c.rank] + kLocalAt + L_TIMEOUT, 1u + (uint32_t)channel);
+        break;
+      }
     }
     __threadfence_system();
   }
@@ -421,7 +430,18 @@ using namespace gsr;
 extern "C" {
 
 size_t gsr_window_slot_floats(int P) { return P > 0 ? 12 * (((size_t)P + 3) / 4) : 0; }
-size_t gsr_window_pad_words(void) { return kLocalAt + 4; }
+size_t gsr_window_pad_words(void) { return kLocalAt + 8; }
+
+int gsr_window_status(const gsr_window_comm* comm, uint32_t* timed_out_channel) {
+  Comm c;
+  if (!make_comm(comm, c) || !timed_out_channel) return GSR_ERR_INVALID;
+  *timed_out_channel = 0;
+  if (c.world == 1) return GSR_OK;
+  if (cudaMemcpy(timed_out_channel, c.pad[c.rank] + kLocalAt + L_TIMEOUT, sizeof(uint32_t), cudaMemcpyDeviceToHost) !=
+      cudaSuccess)
+    return GSR_ERR_CUDA;
+  return GSR_OK;
+}
 
 static bool range_ok(int P, int first, int count) {
   return P > 0 && first >= 0 && count > 0 && (first % 128) == 0 && (long long)first + count <= P;

@@ -305,6 +305,16 @@ class FactoredExchange:
         if self.row_state is not None:
             self.row_state.fill_(-1)
 
+    def timed_out(self) -> int:
+        """0, or 1 + the channel on which one of this rank's waits gave up (~4 s: a peer died or the ranks diverged).
+        Synchronises. The waits never hang the GPU; after a time-out the exchanged gradients are void."""
+        if self._comm is None:
+            return 0
+        torch.cuda.synchronize(self.device)
+        v = self._C.c_uint32(0)
+        self._lib.check(self.lib.gsr_window_status(self._comm_ref(), self._C.byref(v)), "gsr_window_status")
+        return int(v.value)
+
     def push(self, ctx, parity: int, view: Optional[int] = None, chunk: Optional[int] = None) -> None:
         """This rank's masked dRGB + visibility words (of one chunk, or all of them one after the other) into slot `view`
         (default: this rank's) of every rank, each followed by its PUSHED signal (current stream). Needs the blend half of
