@@ -37,6 +37,7 @@ struct __align__(16) WarpBuf {
   float4 b[32];  // {conic.z, opacity, r, g}
   float cb[32];  // b
   float4 pix[32];  // per pixel {dL/dC_r, dL/dC_g, dL/dC_b, -}
+  float2 pxy[32];  // per pixel its coordinates as floats (phase C: no int -> float conversions per pair)
   float2 slot[32 * kSlotStride];
 };
 
@@ -78,7 +79,8 @@ struct PixelState {
 __device__ __forceinline__ float pair_recurrence(PixelState& s, float alpha, float r, float g, float b) {
   // one reciprocal serves both divisions by (1 - alpha) of the reference (:546, :581). MUFU.RCP (1 ulp; 1 - alpha is in
   // [0.01, 1]) instead of the IEEE sequence: gradients are compared at 1e-4, and the kernel is issue-bound
-  const float inv = __fdividef(1.f, 1.f - alpha);
+  float inv;  // (div.approx would add its |y| > 2^126 scaling sequence: ~12 instructions per pair)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(1.f - alpha));
   s.T = s.T * inv;
   const float keep = 1.f - s.last_alpha;
   s.acc0 = s.last_alpha * s.lc0 + keep * s.acc0;
@@ -149,7 +151,7 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
     st.dacc = a.dL_dacc[p];
   }
   st.bg_dot = __ldg(a.bg) * st.dpx0 + __ldg(a.bg + 1) * st.dpx1 + __ldg(a.bg + 2) * st.dpx2;
-  if (slot == 0) buf.pix[pix] = make_float4(st.dpx0, st.dpx1, st.dpx2, 0.f);
+  if (slot == 0) buf.pix[pix] = make_float4(st.dpx0, st.dpx1, st.dpx2, 0.f), buf.pxy[pix] = make_float2(pxf, pyf);
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
   const float wxf = (float)wx, wyf = (float)wy;
 
@@ -258,8 +260,8 @@ __device__ __forceinline__ void blend_bwd_block(const BwdArgs& a, WarpBuf& buf, 
         todo &= todo - 1u;
         const float2 uw = row[k];
         const float4 dp = buf.pix[k];
-        const float kx = (float)(SLOTS == 1 ? (k & 7) : (k & 3)), ky = (float)(SLOTS == 1 ? (k >> 3) : (k >> 2));
-        const float dx = mx - (wxf + kx), dy = my - (wyf + ky);
+        const float2 pq = buf.pxy[k];
+        const float dx = mx - pq.x, dy = my - pq.y;
         const float v = op * uw.x;
         const float vdx = v * dx, vdy = v * dy;
         s_op += uw.x;

@@ -88,9 +88,10 @@ __global__ void __launch_bounds__(kBlock) geom_bwd_kernel(const GeomBwdArgs a) {
   __syncthreads();
   if (kVec16) {
     const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
+    const uint32_t sh0 = smem_u32(s_sh);  // (once: the conversion is not hoisted out of the loop by itself)
     for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {  // row = q / 12 without dividing
       if (s_active[row]) {
-        const uint32_t dst = smem_u32(&s_sh[row * kShRow + rem]);
+        const uint32_t dst = sh0 + (uint32_t)(row * kShRow + rem) * 16u;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
       }
       { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }

@@ -112,11 +112,14 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
   __shared__ __align__(16) float s_means[kBlock * 3];
   __shared__ __align__(16) float s_scales[kBlock * 3];
   __shared__ uint8_t s_survive[kBlock];
-  __shared__ uint32_t s_tile_key[kTileSlots], s_tile_cnt[kTileSlots];  // per-CTA tile -> instance count (see below)
+  __shared__ __align__(16) uint32_t s_tile_key[kTileSlots], s_tile_cnt[kTileSlots];  // per-CTA tile -> instance count (see below)
   extern __shared__ __align__(16) float4 s_sh[];  // [kBlock][kShRow] when kVec16
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < (int)kTileSlots; i += kBlock) s_tile_key[i] = 0xffffffffu, s_tile_cnt[i] = 0u;
+  const uint32_t sh0 = kVec16 ? smem_u32(s_sh) : 0u;  // (once: the conversion is not hoisted out of the staging loops)
+  static_assert(kTileSlots == 4 * kBlock, "one 16-byte store per thread and table");
+  reinterpret_cast<uint4*>(s_tile_key)[tid] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  reinterpret_cast<uint4*>(s_tile_cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
   const int base = blockIdx.x * kBlock;
   const int n = min(kBlock, a.P - base);
   for (int i = tid; i < 35; i += kBlock) {  // the camera: 16 + 16 + 3 floats
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
     const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
     for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {  // row = q / 12 without dividing
       if (s_survive[row]) {
-        const uint32_t dst = smem_u32(&s_sh[row * kShRow + rem]);
+        const uint32_t dst = sh0 + (uint32_t)(row * kShRow + rem) * 16u;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
       }
       { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }
@@ -346,9 +349,9 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
   // this kernel's time) and sends ONE global atomic per tile it touched. A tile that finds no slot within kProbes
   // probes is counted in global memory directly.
   {
-    for (uint32_t k = 0; k < out_tiles; ++k) {
-      const int ry = (int)k / rect_w;
-      const uint32_t t = (uint32_t)((rect_y0 + ry) * a.grid_x + rect_x0 + ((int)k - ry * rect_w));
+    for (uint32_t k = 0, rx = 0, t_row = (uint32_t)(rect_y0 * a.grid_x + rect_x0); k < out_tiles; ++k) {
+      const uint32_t t = t_row + rx;  // row-major walk of the rectangle without dividing
+      if (++rx == (uint32_t)rect_w) rx = 0, t_row += (uint32_t)a.grid_x;
       uint32_t slot = (t * 2654435761u) >> (32 - kTileSlotBits);
       bool counted = false;
       for (uint32_t pr = 0; pr < kTileProbes && !counted; ++pr, slot = (slot + 1) & (kTileSlots - 1)) {
@@ -361,9 +364,15 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
       if (!counted) atomicAdd(&a.tile_count[t], 1u);
     }
     __syncthreads();
-    for (uint32_t i = tid; i < kTileSlots; i += kBlock) {
-      const uint32_t c = s_tile_cnt[i];
-      if (c) atomicAdd(&a.tile_count[s_tile_key[i]], c);
+    {  // this thread's four slots (one 16-byte load: most are empty)
+      const uint4 c = reinterpret_cast<const uint4*>(s_tile_cnt)[tid];
+      if (c.x | c.y | c.z | c.w) {
+        const uint4 k4 = reinterpret_cast<const uint4*>(s_tile_key)[tid];
+        if (c.x) atomicAdd(&a.tile_count[k4.x], c.x);
+        if (c.y) atomicAdd(&a.tile_count[k4.y], c.y);
+        if (c.z) atomicAdd(&a.tile_count[k4.z], c.z);
+        if (c.w) atomicAdd(&a.tile_count[k4.w], c.w);
+      }
     }
   }
 
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(kBlock) preprocess_fwd_kernel(const PreArgs a)
       const float4* g4 = reinterpret_cast<const float4*>(a.shs) + (size_t)base * 12;
       for (int q = tid, row = tid / 12, rem = tid % 12; q < n * 12; q += kBlock) {
         if (s_survive[row]) {
-          const uint32_t dst = smem_u32(&s_sh[row * kShRow + rem]);
+          const uint32_t dst = sh0 + (uint32_t)(row * kShRow + rem) * 16u;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g4 + q) : "memory");
         }
         { rem += kBlock % 12, row += kBlock / 12; if (rem >= 12) rem -= 12, ++row; }

@@ -152,9 +152,11 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
     rw = rmaxx - rminx;
     ntiles = (uint32_t)rw * (uint32_t)(rmaxy - rminy);
   }
-  auto tile_of = [&](uint32_t k) -> uint32_t {
-    const int ry = (int)k / rw;
-    return (uint32_t)((rminy + ry) * grid_x + rminx + ((int)k - ry * rw));
+  // row-major walk of the Gaussian's tile rectangle without dividing: (tile, column) -> next
+  const uint32_t t_first = (uint32_t)(rminy * grid_x + rminx);
+  auto next_tile = [&](uint32_t& t, uint32_t& rx) {
+    ++t;
+    if (++rx == (uint32_t)rw) rx = 0, t += (uint32_t)(grid_x - rw);
   };
   // The 256 Gaussians of a CTA are neighbours in the map and fall into a few dozen tiles, and L2 serialises
   // returning atomics to one address (~15 ns each: a 10 000-instance list would cost its tile's cursor ~40 us even
@@ -164,8 +166,10 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
   // kProbes probes (never seen on real frames) goes to the global cursor directly; the table only grows, so the
   // same probe sequence fails again in the second walk and nothing is counted twice.
   constexpr uint32_t kSlots = 1024, kProbes = 16, kEmpty = 0xffffffffu;
-  __shared__ uint32_t h_key[kSlots], h_cnt[kSlots];
-  for (uint32_t i = threadIdx.x; i < kSlots; i += blockDim.x) h_key[i] = kEmpty, h_cnt[i] = 0;
+  __shared__ __align__(16) uint32_t h_key[kSlots], h_cnt[kSlots];
+  static_assert(kSlots == 4 * 256, "one 16-byte store per thread and table");
+  reinterpret_cast<uint4*>(h_key)[threadIdx.x] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+  reinterpret_cast<uint4*>(h_cnt)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   auto find = [&](uint32_t t, bool insert) -> int {
     uint32_t slot = (t * 2654435761u) >> 22;  // top 10 bits
@@ -175,8 +179,8 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
     }
     return -1;
   };
-  for (uint32_t k = 0; k < ntiles; ++k) {
-    const int slot = find(tile_of(k), true);
+  for (uint32_t k = 0, t = t_first, rx = 0; k < ntiles; ++k, next_tile(t, rx)) {
+    const int slot = find(t, true);
     if (slot >= 0) atomicAdd(&h_cnt[slot], 1u);
   }
   __syncthreads();
@@ -185,8 +189,7 @@ __global__ void __launch_bounds__(256) scatter_instances_kernel(int P, const Spl
     if (c) h_cnt[i] = atomicAdd(&cursor[h_key[i]], c);  // from here on: the CTA's cursor inside the tile's segment
   }
   __syncthreads();
-  for (uint32_t k = 0; k < ntiles; ++k) {
-    const uint32_t t = tile_of(k);
+  for (uint32_t k = 0, t = t_first, rx = 0; k < ntiles; ++k, next_tile(t, rx)) {
     const int slot = find(t, false);
     const uint32_t pos = slot >= 0 ? atomicAdd(&h_cnt[slot], 1u) : atomicAdd(&cursor[t], 1u);
     seg_keys[pos] = depth_bits;

@@ -1,17 +1,28 @@
-"""Per-source-line totals (warp instructions executed, stall samples) of one kernel in an .ncu-rep.
-usage: python tools/ncu_lines.py REPORT.ncu-rep kernel-regex [topN]"""
-import csv, io, subprocess, sys
+"""Per CUDA source line: warp instructions executed and stall samples of one kernel of an .ncu-rep (needs -lineinfo and
+--import-source on).  usage: python tools/ncu_lines.py REPORT.ncu-rep kernel-regex [topN]"""
+import collections, csv, io, subprocess, sys
 rep, kre = sys.argv[1], sys.argv[2]
-topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-name', 'regex:' + kre],
+topn = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv', '--kernel-name', 'regex:' + kre],
                      capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
-h = next(r for r in rows if r and r[0] == 'Line No')
-si, ei, ti = h.index('Warp Stall Sampling (All Samples)'), h.index('Instructions Executed'), h.index('Thread Instructions Executed')
-lines = [(int(r[0]), r[1], int(r[si]), int(r[ei]), int(r[ti])) for r in rows if r and r[0].isdigit() and r[si].isdigit()]
-tots, tote = sum(l[2] for l in lines) or 1, sum(l[3] for l in lines) or 1
-print(f"total samples {tots}, warp instructions {tote}")
-print("by line number:")
-for ln, text, s, e, t in sorted(lines):
-    if s * 200 >= tots or e * 200 >= tote:
-        print(f"  L{ln:4d} samples {100*s/tots:5.1f}%  inst {100*e/tote:5.1f}% ({e:9d}, {t/max(e,1):4.1f} thr)  {text.strip()[:90]}")
+rows = list(csv.reader(io.StringIO(raw)))
+agg = collections.OrderedDict()
+fname, hdr = '?', None
+for r in rows:
+    if len(r) == 2 and r[0] == 'File Path':
+        fname = r[1].split('/')[-1]
+    elif r and r[0] == 'Line No':
+        hdr = r
+    elif hdr and len(r) == len(hdr) and r[0].isdigit():
+        ie, ss = hdr.index('Instructions Executed'), hdr.index('Warp Stall Sampling (All Samples)')
+        key = (fname, int(r[0]))
+        a = agg.setdefault(key, [r[1].strip(), 0, 0])
+        try:
+            a[1] += int(r[ie]); a[2] += int(r[ss])
+        except ValueError:
+            pass
+tot_i = sum(v[1] for v in agg.values()) or 1
+tot_s = sum(v[2] for v in agg.values()) or 1
+print(f"{kre}: {tot_i / 1e6:.1f} M warp instructions, {tot_s} stall samples")
+for (f, ln), (src, i, s) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
+    print(f"  {100 * i / tot_i:5.1f}% instr {100 * s / tot_s:5.1f}% stall  {f}:{ln:<4d} {src[:110]}")
