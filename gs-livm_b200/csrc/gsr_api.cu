@@ -237,6 +237,11 @@ size_t gsr_sizeof(int which) {
     case 3: return sizeof(gsr_geom_view);
     case 4: return sizeof(gsr_binning_view);
     case 5: return sizeof(gsr_image_view);
+    case 6: return sizeof(gsr_adam_group);
+    case 7: return sizeof(gsr_window_comm);
+    case 8: return sizeof(gsr_vgpr_params);
+    case 9: return sizeof(gsr_async_status);
+    case 10: return sizeof(gsr_window_rows);
     default: return 0;
   }
 }

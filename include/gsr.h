@@ -210,7 +210,8 @@ typedef struct gsr_image_view {
 
 GSR_API int gsr_abi_version(void);
 /* sizeof of an ABI struct as this library was compiled: 0 gsr_fwd_args, 1 gsr_bwd_args, 2 gsr_array_view,
- * 3 gsr_geom_view, 4 gsr_binning_view, 5 gsr_image_view; 0 for an unknown index. Lets FFI bindings check layout. */
+ * 3 gsr_geom_view, 4 gsr_binning_view, 5 gsr_image_view, 6 gsr_adam_group, 7 gsr_window_comm, 8 gsr_vgpr_params,
+ * 9 gsr_async_status, 10 gsr_window_rows; 0 for an unknown index. Lets FFI bindings check layout. */
 GSR_API size_t gsr_sizeof(int which);
 GSR_API const char* gsr_last_error(void);
 

@@ -35,7 +35,8 @@ def test_library_exports_every_declared_symbol(built_library):
 def test_ctypes_struct_layout_matches_the_library(built_library):
     from gs_livm_b200 import _lib
     for which, st in enumerate((_lib.FwdArgs, _lib.BwdArgs, _lib.ArrayView, _lib.GeomView, _lib.BinningView,
-                                _lib.ImageView)):
+                                _lib.ImageView, _lib.AdamGroup, _lib.WindowComm, _lib.VgprParams, _lib.AsyncStatus,
+                                _lib.WindowRows)):
         assert built_library.gsr_sizeof(which) == C.sizeof(st), st.__name__
     assert built_library.gsr_sizeof(99) == 0
 

@@ -127,3 +127,24 @@ def test_oracle_key_layout_and_sortedness():
     # stable: equal keys keep ascending Gaussian index
     same = keys[1:] == keys[:-1]
     assert (out["point_list"][1:][same] > out["point_list"][:-1][same]).all()
+
+
+def test_gradient_layout_is_16_byte_aligned_and_ordered():
+    """engine.grad_layout: every array starts on a 16-byte boundary (float4 accesses in geom_bwd and the exchange
+    kernels) whatever P, the SH rows come first, the 11 other parameter-gradient floats behind them and the four arrays
+    the blend backward accumulates into are adjacent (one memset) when P is a multiple of 4."""
+    import gs_livm_b200  # noqa: F401
+    from gs_livm_b200 import engine
+    for P in (1, 3, 130, 49_999, 1_000_000):
+        at, total, param_floats, sh_floats = engine.grad_layout(P, 16)
+        assert list(at)[0] == "dL_dsh" and at["dL_dsh"][0] == 0 and sh_floats == at["dL_dmean3D"][0] >= 48 * P
+        assert all(off % 4 == 0 for off, _ in at.values()) and total % 4 == 0
+        order = [n for n, _ in engine.GRAD_LAYOUT]
+        for a, b in zip(order, order[1:]):
+            assert at[b][0] >= at[a][0] + at[a][1] * P, "arrays must not overlap"
+        assert param_floats == at["dL_dmean2D"][0]
+        assert param_floats - sh_floats >= 11 * P
+    at = engine.grad_layout(1000, 16)[0]
+    acc = ["dL_dopacity", "dL_dmean2D", "dL_dconic", "dL_dcolor"]
+    for a, b in zip(acc, acc[1:]):
+        assert at[b][0] == at[a][0] + at[a][1] * 1000
