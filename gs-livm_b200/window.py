@@ -5,15 +5,16 @@ snapshot, sums their losses and takes one optimiser step (src/liw/lioOptimizatio
 1822-1832). The renders are independent, so the window shards by view: Gaussians (and optimiser state)
 are replicated on every GPU, each rank renders its share of the views forward+backward with the
 single-GPU kernels, and the per-Gaussian parameter gradients (59 floats = 236 B per Gaussian at SH degree
-3) are summed with ONE all-reduce over a flat buffer (NCCL over NVLink/NVSwitch) before the identical
-update is applied everywhere. There is no other cross-rank traffic on the data path.
+3) are summed over the ranks before the identical update is applied everywhere. There is no other cross-rank
+traffic on the data path.
 
-The exchange is ours where the fabric allows it (GradExchange): the gradient buffer is a symmetric allocation
-(torch's _symmetric_memory: peer-mapped and, on NVSwitch systems, one multicast object) and the sum is taken by
-libgsr_b200's own kernels over peer memory — multimem.ld_reduce / multimem.st through the switch, or a two-shot
-peer-to-peer reduce-scatter + all-gather — bracketed by the symmetric-memory barrier. NCCL's all-reduce remains the
-fallback (no peer access, gloo/CPU tests). The gradients are only complete when the last kernel of the backward has
-finished, so there is no tile-by-tile overlap to be had with the compute ("multi-GPU").
+FactoredExchange (default, csrc/window_factored.cu): the SH rows — 81 % of those bytes — are rank one per view, so the
+ranks exchange 3 dRGB floats per rendered Gaussian and view (pushed into every rank's memory under geom_bwd), all-reduce
+only the other 11 floats for the Gaussians some view rendered, and rebuild the SH rows locally; the cross-rank flags
+live inside the kernels, so a whole step is one CUDA graph. GradExchange (round 1, csrc/window_allreduce.cu): dense
+all-reduce of the flat buffer by the library's NVSwitch-multicast / peer-to-peer kernels, NCCL as last resort; kept as
+the fallback where no peer-mapped memory exists. Both need torch's symmetric memory for the peer mappings; the gloo /
+CPU tests exercise the host logic with NCCL-style all-reduce only.
 """
 from __future__ import annotations
 
