@@ -185,7 +185,8 @@ class FactoredExchange:
     factorisation against the rows geom_bwd writes."""
 
     def __init__(self, P: int, M: int, device, group=None, reduce_mode: str = "auto", push_mode: str = "auto",
-                 n_views: Optional[int] = None, sparse_reduce: bool = True, n_chunks: int = 1, track_zero_rows: bool = False):
+                 n_views: Optional[int] = None, sparse_reduce: bool = True, n_chunks: int = 1, track_zero_rows: bool = False,
+                 expand_after_reduce: bool = False):
         """n_views: gather slots = views summed per step (default: one per rank; more only make sense where the caller
         pushes several views itself, as the single-GPU tests do). sparse_reduce: the 11-float all-reduce skips the
         Gaussians no view rendered. n_chunks: ranges of Gaussians the push -> expansion pipeline works on. (Cutting the
@@ -255,6 +256,7 @@ class FactoredExchange:
         if not mc and "multimem" in (self.reduce_mode, self.push_mode):
             raise RuntimeError("no multicast mapping on this system")
         self.sparse_reduce = bool(sparse_reduce)
+        self.expand_after_reduce = bool(expand_after_reduce)  # the expansion behind the all-reduce instead of beside it
         # track_zero_rows: dL_dsh rows no view rendered are rewritten only if they still hold an earlier step's data (the
         # buffer starts zeroed and state 'unknown'); after anything but expand() wrote dL_dsh call mark_rows_dirty().
         # Off by default: 71 MB fewer writes per step, but no measurable gain at N = 8 (668 vs 665 us per step) -- the
@@ -378,7 +380,7 @@ class FactoredExchange:
         mark = (lambda n, s: ev.setdefault(n, torch.cuda.Event(enable_timing=True)).record(s)) if ev is not None else (lambda n, s: None)
         n = len(self.chunks)
         pushed = [torch.cuda.Event() for _ in range(n)]
-        geom_done = torch.cuda.Event()
+        geom_done, reduced = torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(self.hi_push):
             self.hi_push.wait_event(blend_done)
             mark("push_begin", self.hi_push)
@@ -386,12 +388,16 @@ class FactoredExchange:
                 self.push(ctx, parity, chunk=c)
                 pushed[c].record(self.hi_push)
             mark("push_end", self.hi_push)
-        with torch.cuda.stream(self.side):  # (normal priority: as a high-priority stream it starves geom_bwd, 761 vs 685 us)
-            for c in range(n):
-                self.side.wait_event(pushed[c])
-                self.wait_pushed(c)
-                self.expand(ctx, means3D, parity, chunk=c)
-            mark("expand_end", self.side)
+        def expansion():
+            with torch.cuda.stream(self.side):  # (normal priority: as a high-priority stream it starves geom_bwd, 761 vs 685 us)
+                for c in range(n):
+                    self.side.wait_event(pushed[c])
+                    self.wait_pushed(c)
+                    self.expand(ctx, means3D, parity, chunk=c)
+                mark("expand_end", self.side)
+
+        if not (self.expand_after_reduce and self._comm is not None):
+            expansion()
         mark("geom_begin", main)
         geom()
         geom_done.record(main)
@@ -402,6 +408,10 @@ class FactoredExchange:
                 self.hi_reduce.wait_event(pushed[n - 1])
                 self.allreduce_rest_(parity)
                 mark("reduce_end", self.hi_reduce)
+                reduced.record(self.hi_reduce)
+            if self.expand_after_reduce:
+                self.side.wait_event(reduced)
+                expansion()
             main.wait_stream(self.hi_reduce)
         main.wait_stream(self.hi_push)
         main.wait_stream(self.side)

@@ -25,13 +25,14 @@ dC = (torch.randn((3, H, W), generator=g) / (H * W)).to(dev)
 dS = (torch.randn((1, H, W), generator=g) / (H * W)).to(dev)
 
 combos = [("p2p", "p2p", True, 1), ("multimem", "multimem", True, 1), ("multimem", "multimem", True, 2),
-          ("multimem", "multimem", True, 4), ("multimem", "multimem", False, 1), ("auto", "auto", True, 4)]
+          ("multimem", "multimem", True, 4), ("multimem", "multimem", False, 1), ("auto", "auto", True, 4),
+          ("multimem", "multimem", True, -1), ("p2p", "p2p", True, -1)]  # chunks -1: one chunk, expansion behind the reduce
 if len(sys.argv) > 2:
     combos = [c for i, c in enumerate(combos) if str(i) in sys.argv[2]]
 for reduce_mode, push_mode, sparse, track in combos:
     try:
         ex = window.FactoredExchange(P, 16, dev, reduce_mode=reduce_mode, push_mode=push_mode, sparse_reduce=sparse,
-                                     n_chunks=track)
+                                     n_chunks=max(track, 1), expand_after_reduce=track < 0)
     except RuntimeError as e:
         if rank == 0:
             print(f"factored reduce={reduce_mode} push={push_mode}: skipped ({e})", flush=True)
