@@ -312,11 +312,6 @@ __device__ __forceinline__ bool group_rendered(const RestLayout& L, uint32_t j) 
   for (int v = 0; v < L.V; ++v) u |= __ldg(L.vis[v] + (j >> 3));
   return ((u >> (4 * (j & 7))) & 0xfu) != 0;
 }
-__device__ __forceinline__ void slice_of(const RestLayout& L, int rank, int world, uint32_t& lo, uint32_t& hi) {
-  const uint32_t per = (L.g_end - L.g_first + world - 1) / world;
-  lo = min(L.g_end, L.g_first + per * (uint32_t)rank);
-  hi = min(L.g_end, lo + per);
-}
 // entry of the reducing kernels: every rank's gradients of the chunk are complete (and, for the sparse exchange, every
 // rank's visibility words of the chunk have landed here)
 __device__ __forceinline__ uint32_t rest_entry(const RestLayout& L, const Comm& c) {
@@ -327,46 +322,56 @@ __device__ __forceinline__ uint32_t rest_entry(const RestLayout& L, const Comm& 
   return e;
 }
 
-// Every float4 word of the groups [glo, ghi) that takes part, array by array so that the lanes of a warp touch
-// consecutive words (512 contiguous bytes per warp instruction: what peer and multicast accesses need), four words per
-// thread in flight: v = load(word) for all four, then store(word, v).
+// Ownership: the groups are dealt to the ranks in blocks of 256 (1024 Gaussians), block bk -> rank bk % world. (A
+// contiguous slice per rank leaves the ranks with very different amounts of work: the Gaussians some view rendered are
+// clustered in index space, and the exchange takes as long as its busiest rank.)
+constexpr uint32_t kOwnShift = 8;
+// Every float4 word of `owner`'s groups that takes part, array by array so that the lanes of a warp touch consecutive
+// words (512 contiguous bytes per warp instruction: what peer and multicast accesses need), four words per thread in
+// flight: v = load(word) for all four, then store(word, v).
 constexpr int kRestInFlight = 4;
 template <typename Load, typename Store>
-__device__ __forceinline__ void rest_for_each_word(const RestLayout& L, uint32_t glo, uint32_t ghi, Load load, Store store) {
+__device__ __forceinline__ void rest_for_each_word(const RestLayout& L, int owner, int world, Load load, Store store) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t bk_lo = L.g_first >> kOwnShift, bk_hi = (L.g_end + (1u << kOwnShift) - 1u) >> kOwnShift;
+  const uint32_t first_bk = bk_lo + (uint32_t)((owner + world - (int)(bk_lo % (uint32_t)world)) % world);
+  if (first_bk >= bk_hi) return;
+  const uint32_t n_blocks = (bk_hi - first_bk + (uint32_t)world - 1u) / (uint32_t)world;
 #pragma unroll 1
   for (int arr = 0; arr < 4; ++arr) {
     const uint32_t per = arr < 2 ? 3u : (arr == 2 ? 4u : 1u);  // words per group
     const size_t first = arr == 0 ? L.mean4 : (arr == 1 ? L.scale4 : (arr == 2 ? L.rot4 : L.opac4));
     const size_t n_arr = arr < 2 ? L.n_mean4 : (arr == 2 ? L.n_rot4 : L.n_opac4);
-    const size_t end = min((size_t)per * ghi, n_arr);
-    for (size_t w = (size_t)per * glo + t0; w < end; w += kRestInFlight * stride) {
+    const size_t block_words = (size_t)per << kOwnShift, total = (size_t)n_blocks * block_words;
+    for (size_t u = t0; u < total; u += kRestInFlight * stride) {
       float4 v[kRestInFlight];
+      size_t w[kRestInFlight];
       bool on[kRestInFlight];
 #pragma unroll
       for (int k = 0; k < kRestInFlight; ++k) {
-        const size_t wk = w + k * stride;
-        on[k] = wk < end && group_rendered(L, (uint32_t)(wk / per));
+        const size_t uk = u + k * stride;
+        const size_t i = (uk >> kOwnShift) / per;  // which of the owner's blocks
+        w[k] = ((size_t)first_bk + i * (size_t)world) * block_words + (uk - i * block_words);
+        const uint32_t g = (uint32_t)(w[k] / per);
+        on[k] = uk < total && g >= L.g_first && g < L.g_end && w[k] < n_arr && group_rendered(L, g);
       }
 #pragma unroll
       for (int k = 0; k < kRestInFlight; ++k)
-        if (on[k]) v[k] = load(first + w + k * stride);
+        if (on[k]) v[k] = load(first + w[k]);
 #pragma unroll
       for (int k = 0; k < kRestInFlight; ++k)
-        if (on[k]) store(first + w + k * stride, v[k]);
+        if (on[k]) store(first + w[k], v[k]);
     }
   }
 }
 
-// NVSwitch path: rank r pulls the words of ITS slice of groups already reduced by the switch and multicasts them back.
+// NVSwitch path: rank r pulls the words of ITS groups already reduced by the switch and multicasts them back.
 // Entry: READY signalled / awaited (every rank's gradients are complete); exit: DONE signalled by the last block.
 __global__ void __launch_bounds__(512) rest_multimem_kernel(float4* mc, RestLayout L, Comm c) {
   const uint32_t e = rest_entry(L, c);
-  uint32_t lo, hi;
-  slice_of(L, c.rank, c.world, lo, hi);
   rest_for_each_word(
-      L, lo, hi, [&](size_t w) { return multimem_ld_reduce_add(mc + w); },
+      L, c.rank, c.world, [&](size_t w) { return multimem_ld_reduce_add(mc + w); },
       [&](size_t w, const float4& v) { multimem_st4(mc + w, v); });
   if (last_block(c, L_TICKET_A)) signal_peers(c, CH_DONE, e);
 }
@@ -374,14 +379,12 @@ __global__ void __launch_bounds__(512) rest_multimem_kernel(float4* mc, RestLayo
 struct PeerBuf {
   float4* p[kMaxRanks];
 };
-// peer-to-peer path, phase 1: rank r sums its slice over all ranks' buffers (fixed rank order) into its own buffer
+// peer-to-peer path, phase 1: rank r sums its groups over all ranks' buffers (fixed rank order) into its own buffer
 __global__ void __launch_bounds__(512) rest_reduce_scatter_kernel(PeerBuf peers, RestLayout L, Comm c) {
   const uint32_t e = rest_entry(L, c);
-  uint32_t lo, hi;
-  slice_of(L, c.rank, c.world, lo, hi);
   float4* own = peers.p[c.rank];
   rest_for_each_word(
-      L, lo, hi,
+      L, c.rank, c.world,
       [&](size_t w) {
         float4 acc = peers.p[0][w];
         for (int r = 1; r < c.world; ++r) {
@@ -393,18 +396,16 @@ __global__ void __launch_bounds__(512) rest_reduce_scatter_kernel(PeerBuf peers,
       [&](size_t w, const float4& v) { own[w] = v; });
   if (last_block(c, L_TICKET_A)) signal_peers(c, CH_PART, e);
 }
-// phase 2: every rank copies the other slices from their owners
+// phase 2: every rank copies the other ranks' groups from their owners
 __global__ void __launch_bounds__(512) rest_all_gather_kernel(PeerBuf peers, RestLayout L, Comm c) {
   const uint32_t e = step_target(c, L.sub);
   wait_peers(c, CH_PART, e);
   float4* own = peers.p[c.rank];
   for (int o = 1; o < c.world; ++o) {
     const int src = (c.rank + o) % c.world;  // everybody starts on a different owner
-    uint32_t lo, hi;
-    slice_of(L, src, c.world, lo, hi);
     const float4* from = peers.p[src];
     rest_for_each_word(
-        L, lo, hi, [&](size_t w) { return from[w]; }, [&](size_t w, const float4& v) { own[w] = v; });
+        L, src, c.world, [&](size_t w) { return from[w]; }, [&](size_t w, const float4& v) { own[w] = v; });
   }
   if (last_block(c, L_TICKET_B)) signal_peers(c, CH_DONE, e);
 }
