@@ -606,6 +606,7 @@ def run_ours(args, rank, world, dev):
                 "status": "oracle/_ref/gsr_ref_ext.so missing"}
         except Exception as exc:  # the checker must never take the measurement down
             parity = {"status": "checker failed: %s" % (repr(exc)[:200],)}
+    barrier_sync(world)  # (the other ranks wait here for rank 0's check: the exchange's waits are bounded)
 
     # ---- the window step including the optimiser: fused image loss -> dL_dC, backward, exchange,
     # fused Adam over the flat parameter buffer. Learning rates are ZERO so that the timed scene stays the bench scene

@@ -35,10 +35,10 @@ enum { CH_READY = 0, CH_PART = 1, CH_DONE = 2, CH_PUSHED = 3 };
 // local words behind the flag rows of the own pad: the epoch and the last-block tickets of the signalling kernels
 enum { L_EPOCH = 0, L_TICKET_PUSH = 1, L_TICKET_A = 2, L_TICKET_B = 3, L_TIMEOUT = 4 };
 constexpr int kLocalAt = GSR_WINDOW_FLAG_CHANNELS * kMaxRanks;
-// A wait gives up after this many SM cycles (~4 s at 1.9 GHz) instead of hanging the GPU when a peer has died or the
+// A wait gives up after this many SM cycles (~10 s at 1.9 GHz) instead of hanging the GPU when a peer has died or the
 // ranks issue different call sequences: it records 1 + channel in the pad's L_TIMEOUT word (gsr_window_status) and lets
 // the kernel run on -- the step's result is then garbage, but the process can report it and exit.
-constexpr long long kWaitCycles = 8000000000ll;
+constexpr long long kWaitCycles = 20000000000ll;
 
 struct Comm {
   int rank, world;            // world == 1: no cross-rank work at all

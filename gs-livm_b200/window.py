@@ -309,7 +309,7 @@ class FactoredExchange:
             self.row_state.fill_(-1)
 
     def timed_out(self) -> int:
-        """0, or 1 + the channel on which one of this rank's waits gave up (~4 s: a peer died or the ranks diverged).
+        """0, or 1 + the channel on which one of this rank's waits gave up (~10 s: a peer died or the ranks diverged).
         Synchronises. The waits never hang the GPU; after a time-out the exchanged gradients are void."""
         if self._comm is None:
             return 0

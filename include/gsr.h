@@ -330,7 +330,7 @@ typedef struct gsr_window_comm {
 } gsr_window_comm;
 GSR_API size_t gsr_window_slot_floats(int P);
 GSR_API size_t gsr_window_pad_words(void);
-/* Synchronous (blocking copy): 0, or 1 + the channel on which a wait of this rank gave up after ~4 s (a peer died, or
+/* Synchronous (blocking copy): 0, or 1 + the channel on which a wait of this rank gave up after ~10 s (a peer died, or
  * the ranks issued different call sequences). The waits never hang the GPU; after a time-out the results are void. */
 GSR_API int gsr_window_status(const gsr_window_comm* comm, uint32_t* timed_out_channel);
 GSR_API int gsr_window_wait(const gsr_window_comm* comm, int channel, int sub, int advance_epoch, void* stream);
