@@ -148,3 +148,23 @@ def test_gradient_layout_is_16_byte_aligned_and_ordered():
     acc = ["dL_dopacity", "dL_dmean2D", "dL_dconic", "dL_dcolor"]
     for a, b in zip(acc, acc[1:]):
         assert at[b][0] == at[a][0] + at[a][1] * 1000
+
+
+def test_bench_arms_share_one_config_object():
+    """bench.py: both arms build their `config` with the same function from the same constants (the driver compares the
+    two dicts), and everything arm-specific lives elsewhere."""
+    import importlib.util
+    import inspect
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = bench.bench_config(752, 480, [3, 1, 2, 4, 5, 6, 7, 8])
+    b = bench.bench_config(752, 480, (3, 1, 2, 4, 5, 6, 7, 8))
+    assert a == b and a["P"] == 1_000_000 and a["window_poses"] == 8 and len(a["R_per_pose"]) == 8
+    assert set(a) == {"workload", "P", "sh_degree", "width", "height", "window_poses", "R_per_pose", "seed", "l2"}
+    for fn in (bench.run_ours, bench.run_reference):
+        assert '"config": bench_config(W, H, R_per_pose)' in inspect.getsource(fn)
+    names = [e[0] for e in bench.SWEEP]
+    assert len(names) == len(set(names)) == 3
